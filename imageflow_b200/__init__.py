@@ -1,0 +1,20 @@
+"""imageflow_b200 -- B200-native stand-in for imageflow's BGRA resample hot path.
+
+Host-side mirror of the reference seam (paths relative to the imageflow checkout):
+  graphics/scaling.rs:9-23      ScaleAndRenderParams, scale_and_render(input, canvas, &params)
+  graphics/color_matrix.rs:5    window_bgra32_apply_color_matrix(window, matrix)
+  graphics/weights.rs:45-78     Filter
+  graphics/bitmaps.rs:156-160   BitmapCompositing
+All arithmetic runs in hand-written sm_100a kernels inside libifb200.so (include/ifb200.h);
+this package only marshals arguments.  Nothing here imports the CPU oracle.
+"""
+from .graphics import (Batch, BitmapCompositing, BitmapWindow, ErrorKind, Filter, FlowError, ScaleAndRenderParams,
+                       WorkingFloatspace, color_filter_matrix, device_count, populate_weights, scale_and_render,
+                       window_bgra32_apply_color_matrix)
+from ._lib import LIB_PATH, ResampleDesc, lib
+
+__all__ = [
+    "Batch", "BitmapCompositing", "BitmapWindow", "ErrorKind", "Filter", "FlowError", "ScaleAndRenderParams",
+    "WorkingFloatspace", "color_filter_matrix", "device_count", "populate_weights", "scale_and_render",
+    "window_bgra32_apply_color_matrix", "LIB_PATH", "ResampleDesc", "lib",
+]

@@ -1,0 +1,666 @@
+// ifb_engine.cu -- host side of libifb200.so: plans, batch object, C ABI (include/ifb200.h).
+//
+// Mirrors the reference seam graphics/scaling.rs:19-90 (validation + dispatch on the canvas'
+// compositing mode) and color_matrix.rs:5-28; the arithmetic runs in ifb_kernels.cuh on the GPU.
+// There is deliberately no CPU path in this file: if CUDA is unusable the calls fail.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/ifb200.h"
+#include "ifb_kernels.cuh"
+#include "ifb_weights.h"
+
+namespace {
+
+using namespace ifbk;
+
+struct Err {
+    int code; std::string msg;
+};
+#define IFB_THROW(code_, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); throw Err{(code_), std::string(b_)}; } while (0)
+#define CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    int c_ = (e_ == cudaErrorMemoryAllocation) ? IFB200_ERR_OUT_OF_MEMORY : \
+             (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver || e_ == cudaErrorInvalidDevice) ? IFB200_ERR_NO_DEVICE : IFB200_ERR_CUDA; \
+    IFB_THROW(c_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+
+void put_err(char* err, size_t cap, const std::string& m) {
+    if (!err || cap == 0) return;
+    size_t n = std::min(cap - 1, m.size());
+    memcpy(err, m.data(), n);
+    err[n] = 0;
+}
+
+template <class F>
+int guarded(char* err, size_t cap, F&& f) {
+    try {
+        f();
+        if (err && cap) err[0] = 0;
+        return IFB200_OK;
+    } catch (const Err& e) {
+        put_err(err, cap, e.msg);
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        put_err(err, cap, "host allocation failed");
+        return IFB200_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        put_err(err, cap, e.what());
+        return IFB200_ERR_INVALID_STATE;
+    } catch (...) {
+        put_err(err, cap, "unknown failure");
+        return IFB200_ERR_INVALID_STATE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffer helper
+template <class T>
+struct DevVec {
+    T* p = nullptr; size_t n = 0;
+    void upload(const std::vector<T>& h) {
+        n = h.size();
+        if (!n) return;
+        CUDA_OK(cudaMalloc(&p, n * sizeof(T)));
+        CUDA_OK(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    ~DevVec() { if (p) cudaFree(p); }
+    DevVec() = default;
+    DevVec(const DevVec&) = delete;
+    DevVec& operator=(const DevVec&) = delete;
+};
+
+struct AxisOnDev {
+    DevVec<uint32_t> left, right, off; DevVec<float> w;
+    void upload(const ifb::AxisWeights& a) { left.upload(a.left); right.upload(a.right); off.upload(a.offset); w.upload(a.w); }
+    AxisDev view() const { return AxisDev{left.p, right.p, off.p, w.p}; }
+};
+
+// Supported (AV, SH) instantiations of the fused kernel.
+constexpr int kAvChoices[] = {2, 4, 6};
+constexpr int kShChoices[] = {3, 5, 6, 7, 8};
+constexpr int kPrefetch = 4;
+
+struct FusedVariantTables {      // depends on NT (strips) and band count
+    int nt = 0, n_strips = 0;
+    DevVec<StripDev> strips;
+    DevVec<float> hw; DevVec<int> hxa; DevVec<uint32_t> hrd;
+    std::map<int, std::unique_ptr<DevVec<BandDev>>> bands;   // by band count
+};
+
+struct Plan {
+    uint32_t in_w, in_h, out_w, out_h;
+    ifb::AxisWeights wv, wh;
+    AxisOnDev dv, dh;
+    // fused
+    bool fused_ok = false; std::string fused_reason;
+    int av = 0, sh = 0;
+    DevVec<float> vw; DevVec<uint32_t> vdone;
+    std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
+};
+
+bool monotone(const ifb::AxisWeights& a) {
+    for (uint32_t i = 1; i < a.out_size; ++i)
+        if (a.left[i] < a.left[i - 1] || a.right[i] < a.right[i - 1]) return false;
+    return true;
+}
+
+int pick(const int* choices, int n, int need) {
+    for (int i = 0; i < n; ++i) if (choices[i] >= need) return choices[i];
+    return 0;
+}
+
+void build_fused_v(Plan& p) {
+    const auto& a = p.wv;
+    if (!monotone(a) || !monotone(p.wh)) { p.fused_reason = "non-monotone windows"; return; }
+    if (p.in_w % 4 != 0 || p.in_w < 4) { p.fused_reason = "in_w not a multiple of 4"; return; }
+    // ring depth: smallest A with left[y+A] > right[y] for all y
+    int need = 1;
+    for (;; ++need) {
+        bool ok = true;
+        for (uint32_t y = 0; y + need < a.out_size && ok; ++y) ok = a.left[y + need] > a.right[y];
+        if (ok) break;
+        if (need > 64) break;
+    }
+    p.av = pick(kAvChoices, (int)(sizeof kAvChoices / sizeof *kAvChoices), need);
+    if (!p.av) { p.fused_reason = "vertical ring depth " + std::to_string(need) + " > 6"; return; }
+    // horizontal slots per aligned group of 4 source columns
+    std::vector<int> cnt(p.in_w / 4 + 1, 0);
+    for (uint32_t X = 0; X < p.wh.out_size; ++X)
+        for (uint32_t g = p.wh.left[X] / 4; g <= p.wh.right[X] / 4; ++g) cnt[g]++;
+    int hneed = *std::max_element(cnt.begin(), cnt.end());
+    p.sh = pick(kShChoices, (int)(sizeof kShChoices / sizeof *kShChoices), hneed);
+    if (!p.sh) { p.fused_reason = "horizontal slots " + std::to_string(hneed) + " > 8"; return; }
+
+    std::vector<float> vw((size_t)p.in_h * p.av, 0.0f);
+    std::vector<uint32_t> vdone(p.in_h, 0u);
+    for (uint32_t y = 0; y < a.out_size; ++y) {
+        const float* w = a.w.data() + a.offset[y];
+        for (uint32_t j = a.left[y]; j <= a.right[y]; ++j) vw[(size_t)j * p.av + (y % p.av)] = w[j - a.left[y]];
+        uint32_t& d = vdone[a.right[y]];
+        if ((d & 0xffu) == 0) d = (y << 8) | 1u; else d += 1u;
+        if ((d & 0xffu) == 0xffu) { p.fused_reason = "too many rows complete at once"; return; }
+    }
+    p.vw.upload(vw); p.vdone.upload(vdone);
+    p.fused_ok = true;
+}
+
+FusedVariantTables& fused_tables(Plan& p, int nt) {
+    auto it = p.by_nt.find(nt);
+    if (it != p.by_nt.end()) return *it->second;
+    auto ft = std::make_unique<FusedVariantTables>();
+    ft->nt = nt;
+    const auto& h = p.wh;
+    const uint32_t span = 4u * nt;
+    auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1)
+        uint32_t k0 = (h.left[X0] / 4) * 4;
+        return (X1 - X0) <= (uint32_t)nt && h.right[X1 - 1] < k0 + span;
+    };
+    // greedy count, then balance
+    uint32_t ns = 0;
+    for (uint32_t X0 = 0; X0 < h.out_size; ++ns) {
+        uint32_t X1 = X0 + 1;
+        if (!fits(X0, X1)) IFB_THROW(IFB200_ERR_INVALID_STATE, "strip cannot hold one output column (taps %u, nt %d)", h.max_taps, nt);
+        while (X1 < h.out_size && fits(X0, X1 + 1)) ++X1;
+        X0 = X1;
+    }
+    std::vector<StripDev> strips;
+    for (;; ++ns) {
+        strips.clear();
+        bool ok = true;
+        for (uint32_t s = 0; s < ns && ok; ++s) {
+            uint32_t X0 = (uint32_t)((uint64_t)h.out_size * s / ns), X1 = (uint32_t)((uint64_t)h.out_size * (s + 1) / ns);
+            if (X1 <= X0) { ok = false; break; }
+            ok = fits(X0, X1);
+            strips.push_back(StripDev{(int)X0, (int)X1, (int)((h.left[X0] / 4) * 4), 0});
+        }
+        if (ok) break;
+        if (ns > h.out_size) IFB_THROW(IFB200_ERR_INVALID_STATE, "strip partition failed");
+    }
+    ft->n_strips = (int)ns;
+    const int SH = p.sh;
+    std::vector<float> hw((size_t)ns * SH * 4 * nt, 0.0f);
+    std::vector<int> hxa((size_t)ns * nt, 0);
+    std::vector<uint32_t> hrd((size_t)ns * nt, 0u);
+    for (uint32_t s = 0; s < ns; ++s) {
+        const StripDev& sd = strips[s];
+        uint32_t Xlo = sd.X0;     // first output of the strip whose window may still reach the current group
+        for (int t = 0; t < nt; ++t) {
+            const uint32_t c0 = sd.k0 + 4u * t, c1 = c0 + 3u;
+            while (Xlo < (uint32_t)sd.X1 && h.right[Xlo] < c0) ++Xlo;
+            uint32_t Xa = Xlo, n = 0;
+            for (uint32_t X = Xlo; X < (uint32_t)sd.X1 && h.left[X] <= c1; ++X) ++n;
+            if (n > (uint32_t)SH) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: %u outputs in one column group > SH=%d", n, SH);
+            hxa[(size_t)s * nt + t] = (int)(n ? Xa : 0);
+            for (uint32_t q = 0; q < n; ++q) {
+                const uint32_t X = Xa + q;
+                const float* w = h.w.data() + h.offset[X];
+                for (uint32_t i = 0; i < 4; ++i) {
+                    const uint32_t k = c0 + i;
+                    if (k >= h.left[X] && k <= h.right[X])
+                        hw[(((size_t)s * SH + q) * 4 + i) * nt + t] = w[k - h.left[X]];
+                }
+            }
+        }
+        for (uint32_t X = sd.X0; X < (uint32_t)sd.X1; ++X) {
+            const uint32_t tg0 = h.left[X] / 4 - sd.k0 / 4, ng = h.right[X] / 4 - h.left[X] / 4 + 1;
+            if (tg0 + ng > (uint32_t)nt) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: reader range outside strip");
+            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 16);
+        }
+    }
+    ft->strips.upload(strips); ft->hw.upload(hw); ft->hxa.upload(hxa); ft->hrd.upload(hrd);
+    auto& ref = *ft;
+    p.by_nt[nt] = std::move(ft);
+    return ref;
+}
+
+const BandDev* fused_bands(Plan& p, FusedVariantTables& ft, int nb) {
+    auto it = ft.bands.find(nb);
+    if (it != ft.bands.end()) return it->second->p;
+    std::vector<BandDev> b;
+    for (int i = 0; i < nb; ++i) {
+        int Y0 = (int)((int64_t)p.out_h * i / nb), Y1 = (int)((int64_t)p.out_h * (i + 1) / nb);
+        b.push_back(BandDev{Y0, Y1, (int)p.wv.left[Y0], (int)p.wv.right[Y1 - 1]});
+    }
+    auto dv = std::make_unique<DevVec<BandDev>>();
+    dv->upload(b);
+    const BandDev* r = dv->p;
+    ft.bands[nb] = std::move(dv);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused kernel dispatch table
+using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
+struct FusedEntry { int av, sh, ch; FusedFn fn; };
+#define IFB_FUSED(AV_, SH_) \
+    {AV_, SH_, 3, fused_down_kernel<AV_, SH_, 3, kPrefetch>}, {AV_, SH_, 4, fused_down_kernel<AV_, SH_, 4, kPrefetch>}
+const FusedEntry kFused[] = {
+    IFB_FUSED(2, 3), IFB_FUSED(2, 5), IFB_FUSED(2, 6), IFB_FUSED(2, 7), IFB_FUSED(2, 8),
+    IFB_FUSED(4, 3), IFB_FUSED(4, 5), IFB_FUSED(4, 6), IFB_FUSED(4, 7), IFB_FUSED(4, 8),
+    IFB_FUSED(6, 3), IFB_FUSED(6, 5), IFB_FUSED(6, 6), IFB_FUSED(6, 7), IFB_FUSED(6, 8),
+};
+FusedFn find_fused(int av, int sh, int ch) {
+    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch) return e.fn;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct PinnedSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+
+}  // namespace
+
+struct ifb200_batch {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    std::mutex mu;
+    DevVec<float> t_lin, t_srgb; DevVec<uint8_t> lut16k;
+    Tables tables{};
+    using Key = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t>;
+    std::map<Key, std::unique_ptr<Plan>> plans;
+    std::vector<PinnedSlot> pinned;
+    // options
+    bool force_generic = false; int nt = 256; int min_ctas = 296;
+    // counters
+    uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0;
+
+    ~ifb200_batch() {
+        cudaSetDevice(device);
+        for (auto& s : pinned) { if (s.ev) cudaEventDestroy(s.ev); if (s.p) cudaFreeHost(s.p); }
+        plans.clear();
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    void* stage(size_t bytes, cudaEvent_t* ev_out) {
+        for (auto& s : pinned) {
+            if (s.used && cudaEventQuery(s.ev) == cudaSuccess) s.used = false;
+        }
+        for (auto& s : pinned) if (!s.used && s.cap >= bytes) { s.used = true; *ev_out = s.ev; return s.p; }
+        PinnedSlot s;
+        s.cap = std::max<size_t>(bytes, 1 << 16);
+        CUDA_OK(cudaMallocHost(&s.p, s.cap));
+        CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        s.used = true;
+        pinned.push_back(s);
+        *ev_out = s.ev;
+        return s.p;
+    }
+
+    Plan& plan_for(const ifb200_resample_desc& d) {
+        uint32_t sbits; float sp = d.sharpen_percent > 0.0f ? d.sharpen_percent : 0.0f;
+        memcpy(&sbits, &sp, 4);
+        Key k{d.in_w, d.in_h, d.w, d.h, d.filter, sbits};
+        auto it = plans.find(k);
+        if (it != plans.end()) return *it->second;
+        auto p = std::make_unique<Plan>();
+        p->in_w = d.in_w; p->in_h = d.in_h; p->out_w = d.w; p->out_h = d.h;
+        const ifb::Lobe lobe = sp > 0.0f ? ifb::Lobe::SharpenPercent : ifb::Lobe::Natural;   // scaling.rs:104-106
+        int rc = ifb::compute_axis_weights(d.filter, 1.0, lobe, sp, d.h, d.in_h, p->wv);
+        if (rc) IFB_THROW(rc, "vertical weights failed: %s", ifb200_status_name(rc));
+        rc = ifb::compute_axis_weights(d.filter, 1.0, lobe, sp, d.w, d.in_w, p->wh);
+        if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
+        p->dv.upload(p->wv); p->dh.upload(p->wh);
+        build_fused_v(*p);
+        Plan& ref = *p;
+        plans[k] = std::move(p);
+        return ref;
+    }
+};
+
+namespace {
+
+void validate(const ifb200_resample_desc& d) {
+    if (!d.in || !d.canvas) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
+    if ((uint64_t)d.h + d.y > d.cv_h || (uint64_t)d.w + d.x > d.cv_w)                     // scaling.rs:24-29
+        IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "Destination rectangle for scale2d is out of bounds");
+    if (d.w == 0 || d.h == 0 || d.in_w == 0 || d.in_h == 0) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "empty bitmap");
+    if (d.in_stride < d.in_w * 4ull || d.cv_stride < d.cv_w * 4ull || (d.in_stride & 3) || (d.cv_stride & 3))
+        IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
+    if (d.compose < 0 || d.compose > 2) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "unknown compositing mode %d", d.compose);
+    if (d.filter < 1 || d.filter > 31) IFB_THROW(IFB200_ERR_BAD_FILTER, "unknown filter id %d", d.filter);
+}
+
+JobDev make_job(const ifb200_resample_desc& d, const float* t_lin_host, const float* t_srgb_host) {
+    JobDev j{};
+    j.in = d.in;
+    j.out = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
+    j.in_stride = d.in_stride; j.out_stride = d.cv_stride;
+    j.flags = (d.linear ? JF_LINEAR : 0u) | (d.alpha_meaningful ? JF_ALPHA : 0u) | ((uint32_t)d.compose << JF_COMPOSE_SHIFT);
+    if (d.compose == IFB200_BLEND_WITH_MATTE && d.alpha_meaningful) {
+        const float* T = d.linear ? t_lin_host : t_srgb_host;
+        const float ma = (float)d.matte_bgra[3] * (1.0f / 255.0f);
+        j.matte[0] = T[d.matte_bgra[0]] * ma; j.matte[1] = T[d.matte_bgra[1]] * ma; j.matte[2] = T[d.matte_bgra[2]] * ma; j.matte[3] = ma;
+    }
+    if (d.color_matrix) {
+        j.flags |= JF_CM;
+        const float* m = d.color_matrix;      // m[row][col]; output channel c = sum_k m[k][c]*in_k + 255*m[4][c]
+        for (int c = 0; c < 4; ++c) {
+            for (int k = 0; k < 4; ++k) j.cm[c * 5 + k] = m[k * 5 + c];
+            j.cm[c * 5 + 4] = m[4 * 5 + c] * 255.0f;
+        }
+    }
+    return j;
+}
+
+float g_t_lin_host[256], g_t_srgb_host[256];
+std::once_flag g_tables_once;
+void host_tables() {
+    std::call_once(g_tables_once, [] { ifb::byte_to_float_table(true, g_t_lin_host); ifb::byte_to_float_table(false, g_t_srgb_host); });
+}
+
+void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, cudaStream_t st) {
+    if (n == 0) return;
+    host_tables();
+    CUDA_OK(cudaSetDevice(b->device));
+    // group jobs by (plan, kernel class)
+    struct Group { Plan* plan; int ch; bool fused; std::vector<size_t> idx; };
+    std::vector<Group> groups;
+    for (size_t i = 0; i < n; ++i) {
+        validate(descs[i]);
+        Plan& p = b->plan_for(descs[i]);
+        const ifb200_resample_desc& d = descs[i];
+        bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
+        const int ch = d.alpha_meaningful ? 4 : 3;
+        if (fused && !find_fused(p.av, p.sh, ch)) fused = false;
+        Group* g = nullptr;
+        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.fused == fused) { g = &gg; break; }
+        if (!g) { groups.push_back(Group{&p, ch, fused, {}}); g = &groups.back(); }
+        g->idx.push_back(i);
+    }
+    // job array -> device (pinned staging, stream ordered)
+    cudaEvent_t ev;
+    JobDev* hj = static_cast<JobDev*>(b->stage(n * sizeof(JobDev), &ev));
+    size_t pos = 0;
+    std::vector<size_t> gstart;
+    for (auto& g : groups) {
+        gstart.push_back(pos);
+        for (size_t i : g.idx) hj[pos++] = make_job(descs[i], g_t_lin_host, g_t_srgb_host);
+    }
+    JobDev* dj = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dj), n * sizeof(JobDev), st));
+    CUDA_OK(cudaMemcpyAsync(dj, hj, n * sizeof(JobDev), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(ev, st));
+
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group& g = groups[gi];
+        Plan& p = *g.plan;
+        const JobDev* jobs = dj + gstart[gi];
+        const size_t nj = g.idx.size();
+        if (g.fused) {
+            FusedVariantTables& ft = fused_tables(p, b->nt);
+            int nb = 1;
+            const size_t base = nj * ft.n_strips;
+            if (base < (size_t)b->min_ctas) nb = (int)std::min<size_t>((b->min_ctas + base - 1) / base, std::max<uint32_t>(1u, p.out_h / 8u));
+            FusedPlanDev pl{};
+            pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
+            pl.n_strips = ft.n_strips; pl.n_bands = nb;
+            pl.vw = p.vw.p; pl.vdone = p.vdone.p; pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
+            pl.hw = ft.hw.p; pl.hxa = ft.hxa.p; pl.hrd = ft.hrd.p;
+            FusedFn fn = find_fused(p.av, p.sh, g.ch);
+            const size_t smem = (512 + (size_t)2 * g.ch * p.sh * b->nt) * sizeof(float);
+            CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            for (size_t off = 0; off < nj; off += 65535) {
+                const size_t cnt = std::min<size_t>(65535, nj - off);
+                dim3 grid((unsigned)(ft.n_strips * nb), (unsigned)cnt);
+                fn<<<grid, b->nt, smem, st>>>(jobs + off, b->tables, pl);
+                CUDA_OK(cudaGetLastError());
+                b->launches++;
+            }
+            b->fused_jobs += nj;
+        } else {
+            // generic pair; bound the float4 intermediate to ~1 GiB per chunk
+            const size_t per = (size_t)p.out_h * p.in_w * sizeof(float4);
+            const size_t chunk = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nj, 65535), ((size_t)1 << 30) / std::max<size_t>(per, 1)));
+            float4* inter = nullptr;
+            CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&inter), per * chunk, st));
+            for (size_t off = 0; off < nj; off += chunk) {
+                const size_t cnt = std::min(chunk, nj - off);
+                dim3 gv((p.in_w + 127) / 128, p.out_h, (unsigned)cnt);
+                vpass_generic_kernel<<<gv, 128, 0, st>>>(jobs + off, b->tables, p.dv.view(), p.in_w, p.out_h, inter);
+                CUDA_OK(cudaGetLastError());
+                dim3 gh((p.out_w + 127) / 128, p.out_h, (unsigned)cnt);
+                hpass_generic_kernel<<<gh, 128, 0, st>>>(jobs + off, b->tables, p.dh.view(), p.in_w, p.out_w, p.out_h, inter);
+                CUDA_OK(cudaGetLastError());
+                b->launches += 2;
+            }
+            CUDA_OK(cudaFreeAsync(inter, st));
+            b->generic_jobs += nj;
+        }
+    }
+    CUDA_OK(cudaFreeAsync(dj, st));
+}
+
+void color_matrix_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, const float* m, cudaStream_t st) {
+    if (!dev_px || !m) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+    if (w == 0 || h == 0) return;
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+    CUDA_OK(cudaSetDevice(b->device));
+    cudaEvent_t ev;
+    float* hm = static_cast<float*>(b->stage(20 * sizeof(float), &ev));
+    for (int c = 0; c < 4; ++c) {
+        for (int k = 0; k < 4; ++k) hm[c * 5 + k] = m[k * 5 + c];
+        hm[c * 5 + 4] = m[4 * 5 + c] * 255.0f;                 // color_matrix.rs:9-12
+    }
+    float* dm = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dm), 20 * sizeof(float), st));
+    CUDA_OK(cudaMemcpyAsync(dm, hm, 20 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(ev, st));
+    const uint64_t total = (uint64_t)w * h;
+    if (total > 0xffffffffull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap too large");
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148ull * 16);
+    color_matrix_kernel<<<blocks, 256, 0, st>>>(dev_px, w, h, stride, dm);
+    CUDA_OK(cudaGetLastError());
+    b->launches++;
+    CUDA_OK(cudaFreeAsync(dm, st));
+}
+
+// per-thread context for the host-buffer drop-in calls
+struct HostCtx {
+    ifb200_batch* batch = nullptr;
+    uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
+    ~HostCtx() {
+        if (batch) { cudaSetDevice(batch->device); if (d_in) cudaFree(d_in); if (d_cv) cudaFree(d_cv); delete batch; }
+    }
+};
+thread_local HostCtx t_ctx;
+
+ifb200_batch* create_batch(int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        IFB_THROW(IFB200_ERR_NO_DEVICE, "no usable CUDA device (%s); libifb200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_OK(cudaSetDevice(device));
+    std::unique_ptr<ifb200_batch> b(new ifb200_batch());
+    b->device = device;
+    CUDA_OK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    std::vector<float> tl(256), ts(256); std::vector<uint8_t> lut(16384);
+    ifb::byte_to_float_table(true, tl.data()); ifb::byte_to_float_table(false, ts.data()); ifb::linear_to_srgb_table(lut.data());
+    b->t_lin.upload(tl); b->t_srgb.upload(ts); b->lut16k.upload(lut);
+    b->tables = Tables{b->t_lin.p, b->t_srgb.p, b->lut16k.p};
+    return b.release();
+}
+
+HostCtx& host_ctx() {
+    if (!t_ctx.batch) {
+        int dev = 0;
+        if (const char* s = getenv("IFB200_DEVICE")) dev = atoi(s);
+        t_ctx.batch = create_batch(dev);
+    }
+    return t_ctx;
+}
+
+void ensure(uint8_t*& p, size_t& cap, size_t need) {
+    if (cap >= need) return;
+    if (p) CUDA_OK(cudaFree(p));
+    p = nullptr; cap = 0;
+    CUDA_OK(cudaMalloc(&p, need));
+    cap = need;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+uint32_t ifb200_abi_version(void) { return (IFB200_ABI_VERSION_MAJOR << 16) | IFB200_ABI_VERSION_MINOR; }
+
+const char* ifb200_status_name(int s) {
+    switch (s) {
+    case IFB200_OK: return "Ok";
+    case IFB200_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+    case IFB200_ERR_NOT_IMPLEMENTED: return "MethodNotImplemented";
+    case IFB200_ERR_INVALID_STATE: return "InvalidState";
+    case IFB200_ERR_TOTAL_WEIGHT_ZERO: return "TotalWeightZero";
+    case IFB200_ERR_SOURCE_COUNT_TOO_LARGE: return "SourcePixelCountTooLarge";
+    case IFB200_ERR_NO_PIXEL_INPUTS: return "NoPixelInputs";
+    case IFB200_ERR_BAD_FILTER: return "BadFilter";
+    case IFB200_ERR_CAPACITY: return "Capacity";
+    case IFB200_ERR_NO_DEVICE: return "NoDevice";
+    case IFB200_ERR_CUDA: return "CudaError";
+    case IFB200_ERR_OUT_OF_MEMORY: return "OutOfMemory";
+    default: return "Unknown";
+    }
+}
+
+int ifb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ifb200_weights(int filter, double kws, int lobe_mode, float lobe_value, uint32_t out_size, uint32_t in_size,
+                   uint32_t* left, uint32_t* right, uint32_t* offsets, float* weights, size_t cap) {
+    try {
+        if (!left || !right || !offsets || !weights) return IFB200_ERR_INVALID_ARGUMENT;
+        if (lobe_mode < 0 || lobe_mode > 2) return IFB200_ERR_INVALID_ARGUMENT;
+        ifb::AxisWeights a;
+        int rc = ifb::compute_axis_weights(filter, kws, static_cast<ifb::Lobe>(lobe_mode), lobe_value, out_size, in_size, a);
+        if (rc) return rc;
+        if (a.w.size() > cap) return IFB200_ERR_CAPACITY;
+        memcpy(left, a.left.data(), sizeof(uint32_t) * out_size);
+        memcpy(right, a.right.data(), sizeof(uint32_t) * out_size);
+        memcpy(offsets, a.offset.data(), sizeof(uint32_t) * ((size_t)out_size + 1));
+        memcpy(weights, a.w.data(), sizeof(float) * a.w.size());
+        return IFB200_OK;
+    } catch (...) { return IFB200_ERR_OUT_OF_MEMORY; }
+}
+
+void ifb200_byte_to_float_table(int linear, float out[256]) { ifb::byte_to_float_table(linear != 0, out); }
+void ifb200_linear_to_srgb_table(uint8_t out[16384]) { ifb::linear_to_srgb_table(out); }
+int  ifb200_color_filter_matrix(int which, float p, float out[25]) { return out ? ifb::color_filter_matrix(which, p, out) : IFB200_ERR_INVALID_ARGUMENT; }
+
+int ifb200_batch_create(int device, ifb200_batch** out, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!out) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null out pointer");
+        *out = nullptr;
+        *out = create_batch(device);
+    });
+}
+
+int ifb200_batch_enqueue(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b || (!descs && n)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch or descriptor array");
+        std::lock_guard<std::mutex> lk(b->mu);
+        enqueue_locked(b, descs, n, stream ? static_cast<cudaStream_t>(stream) : b->own_stream);
+    });
+}
+
+int ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, const float m[25],
+                              void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        color_matrix_locked(b, dev_px, w, h, stride, m, stream ? static_cast<cudaStream_t>(stream) : b->own_stream);
+    });
+}
+
+int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        CUDA_OK(cudaSetDevice(b->device));
+        CUDA_OK(cudaStreamSynchronize(b->own_stream));
+    });
+}
+
+void ifb200_batch_destroy(ifb200_batch* b) {
+    if (!b) return;
+    try { cudaSetDevice(b->device); cudaDeviceSynchronize(); delete b; } catch (...) {}
+}
+
+int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
+    if (!b) return IFB200_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lk(b->mu);
+    switch (option) {
+    case IFB200_OPT_FORCE_GENERIC: b->force_generic = value != 0; return IFB200_OK;
+    case IFB200_OPT_THREADS_PER_CTA:
+        if (value < 32 || value > 256 || (value % 32)) return IFB200_ERR_INVALID_ARGUMENT;
+        b->nt = (int)value; return IFB200_OK;
+    case IFB200_OPT_MIN_CTAS:
+        if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
+        b->min_ctas = (int)value; return IFB200_OK;
+    default: return IFB200_ERR_INVALID_ARGUMENT;
+    }
+}
+uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b) { return b ? b->launches : 0; }
+uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b) { return b ? b->fused_jobs : 0; }
+uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b) { return b ? b->generic_jobs : 0; }
+
+// ---- drop-in calls with HOST buffers -----------------------------------------------------------
+int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!desc) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null descriptor");
+        validate(*desc);
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        cudaStream_t st = b->own_stream;
+        const ifb200_resample_desc& d = *desc;
+        // device images: input window with a 16-byte aligned pitch; destination rect only
+        const size_t in_pitch = ((size_t)d.in_w * 4 + 63) / 64 * 64;
+        const size_t cv_pitch = ((size_t)d.w * 4 + 63) / 64 * 64;
+        ensure(c.d_in, c.cap_in, in_pitch * d.in_h);
+        ensure(c.d_cv, c.cap_cv, cv_pitch * d.h);
+        CUDA_OK(cudaMemcpy2DAsync(c.d_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h, cudaMemcpyHostToDevice, st));
+        uint8_t* host_rect = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
+        if (d.compose == IFB200_BLEND_WITH_SELF)        // the composite reads the canvas (scaling.rs:271-283)
+            CUDA_OK(cudaMemcpy2DAsync(c.d_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h, cudaMemcpyHostToDevice, st));
+        ifb200_resample_desc dd = d;
+        dd.in = c.d_in; dd.in_stride = (uint32_t)in_pitch;
+        dd.canvas = c.d_cv; dd.cv_w = d.w; dd.cv_h = d.h; dd.cv_stride = (uint32_t)cv_pitch; dd.x = 0; dd.y = 0;
+        enqueue_locked(b, &dd, 1, st);
+        CUDA_OK(cudaMemcpy2DAsync(host_rect, d.cv_stride, c.d_cv, cv_pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float m[25], char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!px || !m) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (w == 0 || h == 0) return;
+        if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        cudaStream_t st = b->own_stream;
+        const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
+        ensure(c.d_cv, c.cap_cv, pitch * h);
+        CUDA_OK(cudaMemcpy2DAsync(c.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        color_matrix_locked(b, c.d_cv, w, h, (uint32_t)pitch, m, st);
+        CUDA_OK(cudaMemcpy2DAsync(px, stride, c.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+"""Python mirror of the reference's operator interface for the hot path (argument meaning and error
+behaviour follow graphics/scaling.rs:19-90 and graphics/color_matrix.rs:5-28); thin marshalling over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from ._lib import ResampleDesc, lib
+
+
+class Filter(enum.IntEnum):
+    """graphics/weights.rs:45-78 (repr(C) discriminants)."""
+    RobidouxFast = 1; Robidoux = 2; RobidouxSharp = 3; Ginseng = 4; GinsengSharp = 5; Lanczos = 6
+    LanczosSharp = 7; Lanczos2 = 8; Lanczos2Sharp = 9; CubicFast = 10; Cubic = 11; CubicSharp = 12
+    CatmullRom = 13; Mitchell = 14; CubicBSpline = 15; Hermite = 16; Jinc = 17; RawLanczos3 = 18
+    RawLanczos3Sharp = 19; RawLanczos2 = 20; RawLanczos2Sharp = 21; Triangle = 22; Linear = 23; Box = 24
+    CatmullRomFast = 25; CatmullRomFastSharp = 26; Fastest = 27; MitchellFast = 28; NCubic = 29
+    NCubicSharp = 30; LegacyIDCTFilter = 31
+
+
+class WorkingFloatspace(enum.IntEnum):
+    """graphics/color.rs:4-9 (Gamma is not reachable from scale_and_render)."""
+    StandardRGB = 0
+    LinearRGB = 1
+
+
+class BitmapCompositing(enum.IntEnum):
+    """graphics/bitmaps.rs:156-160."""
+    ReplaceSelf = 0
+    BlendWithSelf = 1
+    BlendWithMatte = 2
+
+
+class ErrorKind(enum.IntEnum):
+    Ok = 0; InvalidArgument = 1; MethodNotImplemented = 2; InvalidState = 3
+    TotalWeightZero = 10; SourcePixelCountTooLarge = 11; NoPixelInputs = 12; BadFilter = 13; Capacity = 14
+    NoDevice = 20; CudaError = 21; OutOfMemory = 22
+
+
+class FlowError(RuntimeError):
+    """Mirror of imageflow's FlowError{kind, message}."""
+    def __init__(self, code: int, message: str):
+        try:
+            self.kind = ErrorKind(code)
+        except ValueError:
+            self.kind = ErrorKind.InvalidState
+        self.code = code
+        super().__init__(f"{self.kind.name}: {message}")
+
+
+def _check(rc: int, buf) -> None:
+    if rc:
+        raise FlowError(rc, buf.value.decode("utf-8", "replace"))
+
+
+@dataclass
+class ScaleAndRenderParams:
+    """graphics/scaling.rs:9-17."""
+    x: int = 0
+    y: int = 0
+    w: int = 0
+    h: int = 0
+    sharpen_percent_goal: float = 0.0
+    interpolation_filter: Filter = Filter.Robidoux
+    scale_in_colorspace: WorkingFloatspace = WorkingFloatspace.LinearRGB
+
+
+@dataclass
+class BitmapWindow:
+    """BitmapWindowMut<u8> for a BGRA bitmap: host (numpy) or device (raw pointer) pixels + the bits of
+    BitmapInfo that scale_and_render reads (alpha_meaningful, compose; bitmaps.rs)."""
+    ptr: int
+    w: int
+    h: int
+    stride: int
+    alpha_meaningful: bool = False
+    compose: BitmapCompositing = BitmapCompositing.ReplaceSelf
+    matte_bgra: Sequence[int] = (0, 0, 0, 0)
+    pixel_layout: str = "BGRA"
+    _keep: object = field(default=None, repr=False)
+
+    @staticmethod
+    def from_numpy(a: np.ndarray, **kw) -> "BitmapWindow":
+        assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 4 and a.strides[2] == 1 and a.strides[1] == 4
+        return BitmapWindow(a.ctypes.data, a.shape[1], a.shape[0], a.strides[0], _keep=a, **kw)
+
+    @staticmethod
+    def from_torch(t, **kw) -> "BitmapWindow":
+        """t: uint8 CUDA tensor of shape (H, W, 4) (row stride may be padded)."""
+        assert t.dim() == 3 and t.shape[2] == 4 and t.stride(2) == 1 and t.stride(1) == 4
+        return BitmapWindow(t.data_ptr(), t.shape[1], t.shape[0], t.stride(0), _keep=t, **kw)
+
+    def window(self, x1: int, y1: int, x2: int, y2: int) -> Optional["BitmapWindow"]:
+        """bitmaps.rs:413-431: sub-rect view (None when out of bounds)."""
+        if not (0 <= x1 < x2 <= self.w and 0 <= y1 < y2 <= self.h):
+            return None
+        return BitmapWindow(self.ptr + y1 * self.stride + x1 * 4, x2 - x1, y2 - y1, self.stride, self.alpha_meaningful,
+                            self.compose, self.matte_bgra, self.pixel_layout, self._keep)
+
+
+def _desc(inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRenderParams, color_matrix=None, keep=None) -> ResampleDesc:
+    if inp.pixel_layout != "BGRA" or canvas.pixel_layout != "BGRA":            # scaling.rs:43-48
+        raise FlowError(ErrorKind.MethodNotImplemented, "scale_and_render only supports BGRA bitmaps")
+    d = ResampleDesc()
+    d.in_ = inp.ptr; d.in_w = inp.w; d.in_h = inp.h; d.in_stride = inp.stride
+    d.canvas = canvas.ptr; d.cv_w = canvas.w; d.cv_h = canvas.h; d.cv_stride = canvas.stride
+    d.x, d.y, d.w, d.h = info.x, info.y, info.w, info.h
+    d.filter = int(info.interpolation_filter)
+    d.sharpen_percent = float(info.sharpen_percent_goal)
+    d.linear = 1 if info.scale_in_colorspace == WorkingFloatspace.LinearRGB else 0
+    d.alpha_meaningful = int(bool(inp.alpha_meaningful))
+    d.compose = int(canvas.compose)
+    d.matte_bgra = (C.c_uint8 * 4)(*canvas.matte_bgra)
+    if color_matrix is not None:
+        cm = np.ascontiguousarray(color_matrix, np.float32).reshape(25)
+        d.color_matrix = cm.ctypes.data
+        (keep if keep is not None else []).append(cm)
+        d._cm = cm
+    return d
+
+
+def scale_and_render(inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRenderParams, color_matrix=None) -> None:
+    """graphics/scaling.rs:19-90 with HOST bitmaps (the drop-in call). Raises FlowError."""
+    d = _desc(inp, canvas, info, color_matrix)
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_scale_and_render(C.byref(d), buf, 512), buf)
+
+
+def window_bgra32_apply_color_matrix(window: BitmapWindow, m) -> None:
+    """graphics/color_matrix.rs:5-28, in place on a HOST window; m is [[f32;5];5]."""
+    mm = np.ascontiguousarray(m, np.float32).reshape(25)
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_color_matrix_bgra8(window.ptr, window.w, window.h, window.stride,
+                                            mm.ctypes.data_as(C.POINTER(C.c_float)), buf, 512), buf)
+
+
+def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
+    """flow/nodes/color.rs:86-225 presets (0 sepia ... 9 saturation)."""
+    m = np.zeros(25, np.float32)
+    rc = lib().ifb200_color_filter_matrix(which, p, m.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc:
+        raise FlowError(rc, "unknown colour filter")
+    return m.reshape(5, 5)
+
+
+def populate_weights(filter: int, out_size: int, in_size: int, kernel_width_scale: float = 1.0,
+                     lobe_mode: int = 0, lobe_value: float = 0.0):
+    """graphics/weights.rs:681-788 -> [(left_pixel, right_pixel, weights f32[])] per output pixel."""
+    left = np.zeros(out_size, np.uint32); right = np.zeros(out_size, np.uint32); off = np.zeros(out_size + 1, np.uint32)
+    cap = out_size * (int(2 * (6.5 * max(1.0, in_size / max(out_size, 1)) * max(kernel_width_scale, 1.0))) + 8)
+    w = np.zeros(cap, np.float32)
+    u32p, f32p = C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    rc = lib().ifb200_weights(int(filter), kernel_width_scale, lobe_mode, lobe_value, out_size, in_size,
+                              left.ctypes.data_as(u32p), right.ctypes.data_as(u32p), off.ctypes.data_as(u32p),
+                              w.ctypes.data_as(f32p), cap)
+    if rc:
+        raise FlowError(rc, "populate_weights failed")
+    return [(int(left[i]), int(right[i]), w[off[i]:off[i + 1]].copy()) for i in range(out_size)]
+
+
+def device_count() -> int:
+    return lib().ifb200_device_count()
+
+
+class Batch:
+    """Device-resident batch executor (ifb200_batch_*): many independent scale_and_render calls whose
+    bitmaps already live in HBM of one GPU, enqueued on a CUDA stream."""
+    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS = 1, 2, 3
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_create(device, C.byref(self._h), buf, 512), buf)
+        self.device = device
+        self._keep = []
+
+    def set_option(self, option: int, value: int) -> None:
+        rc = lib().ifb200_batch_set_option(self._h, option, value)
+        if rc:
+            raise FlowError(rc, f"bad option {option}={value}")
+
+    def make_descs(self, jobs):
+        """jobs: iterable of (input BitmapWindow, canvas BitmapWindow, ScaleAndRenderParams[, color_matrix])."""
+        jobs = list(jobs)
+        arr = (ResampleDesc * len(jobs))()
+        keep = []
+        for i, j in enumerate(jobs):
+            arr[i] = _desc(j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
+        return arr, keep
+
+    def enqueue(self, descs, stream: int = 0, keep=None) -> None:
+        if keep:
+            self._keep.append(keep)
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_enqueue(self._h, descs, len(descs), C.c_void_p(stream) if stream else None, buf, 512), buf)
+
+    def scale_and_render_many(self, jobs, stream: int = 0) -> None:
+        descs, keep = self.make_descs(jobs)
+        self.enqueue(descs, stream, keep)
+
+    def color_matrix(self, dev_ptr: int, w: int, h: int, stride: int, m, stream: int = 0) -> None:
+        mm = np.ascontiguousarray(m, np.float32).reshape(25)
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_color_matrix(self._h, dev_ptr, w, h, stride, mm.ctypes.data_as(C.POINTER(C.c_float)),
+                                                C.c_void_p(stream) if stream else None, buf, 512), buf)
+
+    def sync(self) -> None:
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_sync(self._h, buf, 512), buf)
+        self._keep.clear()
+
+    @property
+    def kernel_launches(self) -> int:
+        return lib().ifb200_batch_kernel_launches(self._h)
+
+    @property
+    def fused_jobs(self) -> int:
+        return lib().ifb200_batch_fused_jobs(self._h)
+
+    @property
+    def generic_jobs(self) -> int:
+        return lib().ifb200_batch_generic_jobs(self._h)
+
+    def close(self) -> None:
+        if self._h:
+            lib().ifb200_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

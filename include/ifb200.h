@@ -1,0 +1,134 @@
+/*
+ * ifb200.h -- C ABI of the B200-native resample engine (libifb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of imazen/imageflow: the BGRA8
+ * resample / composite / colour-matrix path behind
+ *     imageflow_core::graphics::scaling::scale_and_render        (graphics/scaling.rs:19-90)
+ *     imageflow_core::graphics::color_matrix::window_bgra32_apply_color_matrix (graphics/color_matrix.rs:5-28)
+ * which the flow-graph executors DrawImageDef::render (flow/nodes/scale_render.rs:304-313) and
+ * ColorMatrixSrgbMutDef::mutate (flow/nodes/color.rs:26-28) call.  (All paths relative to the
+ * reference checkout; INTEGRATION.md shows the Rust `extern "C"` block that binds these symbols.)
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every function is thread-safe, never throws
+ * or aborts across the boundary, never retains caller pointers after it returns (batch jobs: after
+ * ifb200_batch_sync returns).  There is NO CPU fallback: without a usable CUDA device every compute
+ * entry point fails with IFB200_ERR_NO_DEVICE.
+ */
+#ifndef IFB200_H
+#define IFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFB200_ABI_VERSION_MAJOR 1
+#define IFB200_ABI_VERSION_MINOR 0
+
+/* Error codes.  1..3 map onto the imageflow ErrorKind values raised by scale_and_render
+ * (scaling.rs:24-48,145,191,202,240); 10..12 onto WeightsError (weights.rs:494-504). */
+enum ifb200_status {
+    IFB200_OK = 0,
+    IFB200_ERR_INVALID_ARGUMENT = 1,      /* ErrorKind::InvalidArgument  (scaling.rs:24-29,38-40) */
+    IFB200_ERR_NOT_IMPLEMENTED = 2,       /* ErrorKind::MethodNotImplemented (scaling.rs:43-48)   */
+    IFB200_ERR_INVALID_STATE = 3,         /* ErrorKind::InvalidState (scaling.rs:145,191,202,240) */
+    IFB200_ERR_TOTAL_WEIGHT_ZERO = 10,    /* WeightsError::TotalWeightZero (weights.rs:755-757)   */
+    IFB200_ERR_SOURCE_COUNT_TOO_LARGE = 11,
+    IFB200_ERR_NO_PIXEL_INPUTS = 12,
+    IFB200_ERR_BAD_FILTER = 13,
+    IFB200_ERR_CAPACITY = 14,
+    IFB200_ERR_NO_DEVICE = 20,            /* no CUDA device / driver: there is no CPU fallback    */
+    IFB200_ERR_CUDA = 21,                 /* a CUDA runtime call failed; message has the detail   */
+    IFB200_ERR_OUT_OF_MEMORY = 22
+};
+
+/* weights.rs:45-78 -- `Filter` repr(C) discriminants, used verbatim. */
+enum ifb200_filter {
+    IFB200_FILTER_ROBIDOUX_FAST = 1, IFB200_FILTER_ROBIDOUX = 2, IFB200_FILTER_ROBIDOUX_SHARP = 3,
+    IFB200_FILTER_GINSENG = 4, IFB200_FILTER_GINSENG_SHARP = 5, IFB200_FILTER_LANCZOS = 6,
+    IFB200_FILTER_LANCZOS_SHARP = 7, IFB200_FILTER_LANCZOS2 = 8, IFB200_FILTER_LANCZOS2_SHARP = 9,
+    IFB200_FILTER_CUBIC_FAST = 10, IFB200_FILTER_CUBIC = 11, IFB200_FILTER_CUBIC_SHARP = 12,
+    IFB200_FILTER_CATMULL_ROM = 13, IFB200_FILTER_MITCHELL = 14, IFB200_FILTER_CUBIC_BSPLINE = 15,
+    IFB200_FILTER_HERMITE = 16, IFB200_FILTER_JINC = 17, IFB200_FILTER_RAW_LANCZOS3 = 18,
+    IFB200_FILTER_RAW_LANCZOS3_SHARP = 19, IFB200_FILTER_RAW_LANCZOS2 = 20, IFB200_FILTER_RAW_LANCZOS2_SHARP = 21,
+    IFB200_FILTER_TRIANGLE = 22, IFB200_FILTER_LINEAR = 23, IFB200_FILTER_BOX = 24,
+    IFB200_FILTER_CATMULL_ROM_FAST = 25, IFB200_FILTER_CATMULL_ROM_FAST_SHARP = 26, IFB200_FILTER_FASTEST = 27,
+    IFB200_FILTER_MITCHELL_FAST = 28, IFB200_FILTER_NCUBIC = 29, IFB200_FILTER_NCUBIC_SHARP = 30,
+    IFB200_FILTER_LEGACY_IDCT = 31
+};
+
+/* graphics/bitmaps.rs:156-160 BitmapCompositing */
+enum ifb200_compose { IFB200_REPLACE_SELF = 0, IFB200_BLEND_WITH_SELF = 1, IFB200_BLEND_WITH_MATTE = 2 };
+/* weights.rs:16-23 LobeRatio */
+enum ifb200_lobe { IFB200_LOBE_NATURAL = 0, IFB200_LOBE_EXACT = 1, IFB200_LOBE_SHARPEN_PERCENT = 2 };
+
+/* One scale_and_render call: (input window, canvas window, ScaleAndRenderParams) -- scaling.rs:9-23. */
+typedef struct ifb200_resample_desc {
+    const uint8_t* in;  uint32_t in_w, in_h, in_stride;   /* BGRA8 sRGB, straight alpha; stride in bytes (bitmaps.rs:712-740) */
+    uint8_t* canvas;    uint32_t cv_w, cv_h, cv_stride;   /* the canvas BEFORE cropping to (x,y,w,h) (scaling.rs:30-41)      */
+    uint32_t x, y, w, h;                                   /* ScaleAndRenderParams.x/y/w/h                                    */
+    int32_t  filter;                                       /* enum ifb200_filter (ScaleAndRenderParams.interpolation_filter)   */
+    float    sharpen_percent;                              /* sharpen_percent_goal; <= 0 means off (scaling.rs:104-106)       */
+    int32_t  linear;                                       /* 1 = WorkingFloatspace::LinearRGB, 0 = StandardRGB (scaling.rs:52) */
+    int32_t  alpha_meaningful;                             /* input.info().alpha_meaningful() (scaling.rs:51)                 */
+    int32_t  compose;                                      /* enum ifb200_compose = canvas.info().compose() (scaling.rs:50)   */
+    uint8_t  matte_bgra[4];                                /* BlendWithMatte colour as to_bgra8() (scaling.rs:67)            */
+    const float* color_matrix;                             /* optional fused ColorMatrixSrgb (row-major [5][5]) applied to the
+                                                              destination rect after the render; NULL = none (color_matrix.rs) */
+} ifb200_resample_desc;
+
+/* ---- library / device ---------------------------------------------------------------------- */
+uint32_t    ifb200_abi_version(void);                      /* (major << 16) | minor */
+const char* ifb200_status_name(int status);
+int         ifb200_device_count(void);                     /* 0 when no CUDA device / driver is usable */
+
+/* ---- host-side specification helpers (no GPU needed) ----------------------------------------
+ * populate_weights (weights.rs:681-788) for one axis. left/right hold out_size entries, offsets
+ * out_size+1 (prefix offsets into weights[]).  kernel_width_scale = set_kernel_width_scale factor
+ * (weights.rs:156-158), lobe_* = LobeRatio (weights.rs:16-40). */
+int ifb200_weights(int filter, double kernel_width_scale, int lobe_mode, float lobe_value,
+                   uint32_t out_size, uint32_t in_size,
+                   uint32_t* left, uint32_t* right, uint32_t* offsets,
+                   float* weights, size_t weights_cap);
+/* ColorContext::byte_to_float (color.rs:23-48) and LINEAR_TO_SRGB_LUT (lut.rs:14) as uploaded to the device */
+void ifb200_byte_to_float_table(int linear, float out[256]);
+void ifb200_linear_to_srgb_table(uint8_t out[16384]);
+/* ColorFilterSrgb presets (flow/nodes/color.rs:86-225): 0 sepia, 1 grayscale_ntsc, 2 grayscale_flat,
+ * 3 grayscale_bt709, 4 grayscale_ry, 5 invert, 6 alpha(p), 7 contrast(p), 8 brightness(p), 9 saturation(p) */
+int  ifb200_color_filter_matrix(int which, float p, float out[25]);
+
+/* ---- drop-in calls: HOST buffers, synchronous (what the Rust adapter calls) ------------------
+ * Replaces the bodies of scaling.rs:93-251 (resize_to_canvas / resize_with_matte /
+ * resize_and_composite).  err (may be NULL) receives a NUL-terminated message on failure. */
+int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t err_cap);
+/* Replaces color_matrix.rs:5-28 (in place). */
+int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float m[25],
+                              char* err, size_t err_cap);
+
+/* ---- device-resident batch API (the metric path; not in the reference) -----------------------
+ * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
+ * enqueue is asynchronous on `cuda_stream` (a cudaStream_t; NULL = the batch's own stream). */
+typedef struct ifb200_batch ifb200_batch;
+int  ifb200_batch_create(int device, ifb200_batch** out, char* err, size_t err_cap);
+int  ifb200_batch_enqueue(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, void* cuda_stream,
+                          char* err, size_t err_cap);
+int  ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
+                               const float m[25], void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
+void ifb200_batch_destroy(ifb200_batch* b);
+/* knobs / introspection (benchmarks, tests) */
+enum ifb200_option {
+    IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
+    IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size (multiple of 32)                           */
+    IFB200_OPT_MIN_CTAS = 3            /* split images into row bands until the grid has this many CTAs   */
+};
+int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
+uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */
+uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b);        /* jobs that took the fused kernel */
+uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b);      /* jobs that took the generic pair */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFB200_H */

@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): <= 1 level per 8-bit channel against the reference; here we hold the
+kernels to the stricter bar of BIT-EXACT BGRA8 output against the oracle (same fp32 operation order).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ifb():
+    import imageflow_b200
+    assert imageflow_b200.device_count() > 0, "CUDA extension loaded but no device: GPU tests cannot fall back"
+    return imageflow_b200
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _oracle(inp, canvas, **kw):
+    out = canvas.copy()
+    oracle.scale_and_render(inp, out, **kw)
+    return out
+
+
+def _gpu_batch(ifb, torch, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen=0.0, linear=True,
+               alpha_meaningful=False, compose=0, matte=(0, 0, 0, 0), color_matrix=None, force_generic=False, nt=256,
+               min_ctas=None):
+    b = ifb.Batch(0)
+    b.set_option(ifb.Batch.OPT_FORCE_GENERIC, int(force_generic))
+    b.set_option(ifb.Batch.OPT_THREADS_PER_CTA, nt)
+    if min_ctas is not None:
+        b.set_option(ifb.Batch.OPT_MIN_CTAS, min_ctas)
+    # device copies with a 64-byte padded pitch like Bitmap::create_u8 (bitmaps.rs:803-804)
+    def up(a):
+        hh, ww, _ = a.shape
+        pitch = (ww * 4 + 63) // 64 * 64
+        t = torch.zeros((hh, pitch), dtype=torch.uint8, device="cuda")
+        v = t.as_strided((hh, ww, 4), (pitch, 4, 1))
+        v.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        return v
+    ti, tc = up(inp), up(canvas)
+    wi = ifb.BitmapWindow.from_torch(ti, alpha_meaningful=alpha_meaningful)
+    wc = ifb.BitmapWindow.from_torch(tc, compose=ifb.BitmapCompositing(compose), matte_bgra=matte)
+    p = ifb.ScaleAndRenderParams(x=x, y=y, w=canvas.shape[1] - x if w is None else w, h=canvas.shape[0] - y if h is None else h,
+                                 sharpen_percent_goal=sharpen, interpolation_filter=ifb.Filter(filter),
+                                 scale_in_colorspace=ifb.WorkingFloatspace(int(linear)))
+    b.scale_and_render_many([(wi, wc, p, color_matrix)], stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    took_fused = b.fused_jobs
+    out = tc.cpu().numpy().copy()
+    b.close()
+    return out, took_fused
+
+
+CASES = [
+    # (in_w, in_h, out_w, out_h, filter, alpha, linear)
+    (640, 480, 200, 150, 2, False, True),        # config-1 shaped (Robidoux, opaque, linear)
+    (480, 360, 200, 150, 2, False, True),        # what config 1 really feeds the path
+    (800, 600, 400, 300, 2, True, True),         # bench_graphics full_scale_pipeline (alpha meaningful)
+    (1920, 1080, 640, 360, 2, True, True),
+    (768, 432, 512, 288, 6, False, True),        # Lanczos, 1.5x
+    (960, 540, 128, 128, 6, True, True),         # Lanczos 7.5x / 4.2x (config-2 ratios)
+    (512, 384, 128, 96, 14, False, False),       # Mitchell in sRGB space
+    (400, 300, 100, 75, 4, True, False),         # Ginseng, alpha, sRGB space
+    (1024, 64, 96, 17, 13, True, True),          # wide strip, CatmullRom
+    (260, 250, 61, 59, 2, False, True),          # ragged sizes
+    (256, 256, 256, 256, 2, False, True),        # 1:1 (Robidoux still blurs)
+    (128, 128, 37, 41, 24, False, True),         # Box
+    (128, 128, 50, 50, 22, True, True),          # Triangle
+    (64, 64, 128, 128, 14, True, True),          # 2x upscale (generic path)
+    (100, 60, 333, 200, 4, False, True),         # 3.33x upscale Ginseng
+    (33, 17, 7, 5, 2, True, True),               # in_w not a multiple of 4 (generic path)
+    (8, 8, 1, 1, 2, True, True),
+    (4, 4, 4, 1, 17, False, True),               # Jinc
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
+def test_replace_self_bit_exact(ifb, torch_mod, case, force_generic):
+    iw, ih, ow, oh, flt, alpha, linear = case
+    inp = util.noise(iw, ih, seed=iw * 31 + ih, alpha_mode="mixed" if alpha else "opaque")
+    canvas = np.zeros((oh, ow, 4), np.uint8)
+    exp = _oracle(inp, canvas, filter=flt, alpha_meaningful=alpha, linear=linear)
+    got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, filter=flt, alpha_meaningful=alpha, linear=linear, force_generic=force_generic)
+    mx, n = util.diff_stats(got, exp)
+    assert mx == 0, f"max |delta| {mx} on {n} channel values"
+
+
+def test_fused_kernel_is_the_one_that_runs(ifb, torch_mod):
+    inp = util.gradient(960, 540)
+    canvas = np.zeros((128, 128, 4), np.uint8)
+    _, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2)
+    assert fused == 1
+    _, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, force_generic=True)
+    assert fused == 0
+
+
+@pytest.mark.parametrize("nt,min_ctas", [(128, 1), (256, 1), (256, 4096), (64, 64)])
+def test_fused_decompositions_agree(ifb, torch_mod, nt, min_ctas):
+    """strip width and row-band count must not change a single bit."""
+    inp = util.noise(1280, 720, seed=7, alpha_mode="mixed")
+    canvas = np.zeros((180, 320, 4), np.uint8)
+    exp = _oracle(inp, canvas, filter=2, alpha_meaningful=True)
+    got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, alpha_meaningful=True, nt=nt, min_ctas=min_ctas)
+    assert fused == 1
+    assert util.diff_stats(got, exp)[0] == 0
+
+
+@pytest.mark.parametrize("compose,alpha", [(1, True), (1, False), (2, True), (2, False)])
+@pytest.mark.parametrize("force_generic", [False, True], ids=["auto", "generic"])
+def test_compose_modes_bit_exact(ifb, torch_mod, compose, alpha, force_generic):
+    inp = util.noise(640, 400, seed=3, alpha_mode="mixed" if alpha else "opaque")
+    canvas = util.noise(200, 125, seed=99, alpha_mode="mixed")
+    kw = dict(filter=2, alpha_meaningful=alpha, compose=compose, matte=(40, 120, 250, 200))
+    exp = _oracle(inp, canvas, **kw)
+    got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, force_generic=force_generic, **kw)
+    assert util.diff_stats(got, exp)[0] == 0
+
+
+def test_dest_rect_inside_canvas_and_untouched_border(ifb, torch_mod):
+    inp = util.noise(512, 512, seed=5, alpha_mode="mixed")
+    canvas = util.noise(300, 200, seed=6, alpha_mode="mixed")
+    kw = dict(x=37, y=11, w=128, h=128, filter=6, alpha_meaningful=True, compose=1)
+    exp = _oracle(inp, canvas, **kw)
+    got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, **kw)
+    assert util.diff_stats(got, exp)[0] == 0
+    mask = np.ones((200, 300), bool)
+    mask[11:139, 37:165] = False
+    assert np.array_equal(got[mask], canvas[mask])
+
+
+def test_sharpen_percent_bit_exact(ifb, torch_mod):
+    inp = util.noise(800, 600, seed=8)
+    canvas = np.zeros((150, 200, 4), np.uint8)
+    exp0 = _oracle(inp, canvas, filter=2)
+    exp = _oracle(inp, canvas, filter=2, sharpen=50.0)
+    got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, sharpen=50.0)
+    assert util.diff_stats(got, exp)[0] == 0
+    assert util.diff_stats(exp, exp0)[1] > 0          # sharpening really changes the weights
+
+
+def test_fused_color_matrix_epilogue(ifb, torch_mod):
+    inp = util.noise(640, 480, seed=9, alpha_mode="mixed")
+    canvas = util.noise(160, 120, seed=10, alpha_mode="mixed")
+    sepia = ifb.color_filter_matrix(0)
+    assert np.array_equal(sepia, oracle.color_filter_matrix(0))
+    for compose in (0, 1):
+        kw = dict(filter=14, alpha_meaningful=True, compose=compose, color_matrix=sepia)
+        exp = _oracle(inp, canvas, **kw)
+        got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, **kw)
+        assert util.diff_stats(got, exp)[0] == 0
+
+
+def test_dropin_host_call_matches_oracle(ifb):
+    """ifb200_scale_and_render with pageable HOST buffers, padded strides and a sub-rect."""
+    inp = util.padded(util.noise(1000, 700, seed=11, alpha_mode="mixed"))
+    canvas0 = util.padded(util.noise(333, 222, seed=12, alpha_mode="mixed"))
+    for compose, alpha in ((0, True), (1, True), (2, True), (0, False)):
+        exp = canvas0.copy()
+        oracle.scale_and_render(inp, exp, x=13, y=7, w=250, h=175, filter=2, alpha_meaningful=alpha, compose=compose, matte=(9, 8, 7, 255))
+        got = util.padded(np.ascontiguousarray(canvas0))
+        wi = ifb.BitmapWindow.from_numpy(inp, alpha_meaningful=alpha)
+        wc = ifb.BitmapWindow.from_numpy(got, compose=ifb.BitmapCompositing(compose), matte_bgra=(9, 8, 7, 255))
+        ifb.scale_and_render(wi, wc, ifb.ScaleAndRenderParams(x=13, y=7, w=250, h=175))
+        assert util.diff_stats(got, exp)[0] == 0
+
+
+def test_standalone_color_matrix(ifb):
+    px = util.padded(util.noise(321, 123, seed=13, alpha_mode="mixed"))
+    for which, p in ((0, 0.0), (1, 0.0), (5, 0.0), (6, 0.5), (7, 0.3), (8, -0.2), (9, 0.7)):
+        m = ifb.color_filter_matrix(which, p)
+        assert np.array_equal(m, oracle.color_filter_matrix(which, p))
+        exp = np.ascontiguousarray(px).copy()
+        oracle.color_matrix(exp, m)
+        got = util.padded(np.ascontiguousarray(px))
+        ifb.window_bgra32_apply_color_matrix(ifb.BitmapWindow.from_numpy(got), m)
+        assert util.diff_stats(got, exp)[0] == 0
+
+
+def test_error_behaviour(ifb):
+    a = np.zeros((8, 8, 4), np.uint8)
+    c = np.zeros((4, 4, 4), np.uint8)
+    wi, wc = ifb.BitmapWindow.from_numpy(a), ifb.BitmapWindow.from_numpy(c)
+    with pytest.raises(ifb.FlowError) as e:                      # scaling.rs:24-29
+        ifb.scale_and_render(wi, wc, ifb.ScaleAndRenderParams(x=2, y=0, w=3, h=4))
+    assert e.value.kind == ifb.ErrorKind.InvalidArgument and "out of bounds" in str(e.value)
+    wi.pixel_layout = "BGR"
+    with pytest.raises(ifb.FlowError) as e:                      # scaling.rs:43-48
+        ifb.scale_and_render(wi, wc, ifb.ScaleAndRenderParams(w=4, h=4))
+    assert e.value.kind == ifb.ErrorKind.MethodNotImplemented
+    wi.pixel_layout = "BGRA"
+    assert ifb.lib().ifb200_batch_set_option(None, 1, 1) == int(ifb.ErrorKind.InvalidArgument)
+    with pytest.raises(ifb.FlowError) as e:
+        ifb.scale_and_render(wi, wc, ifb.ScaleAndRenderParams(w=4, h=4, interpolation_filter=77))
+    assert e.value.kind == ifb.ErrorKind.BadFilter
+
+
+def test_batch_of_mixed_jobs(ifb, torch_mod):
+    """several geometries / modes in one enqueue (config-5 shaped), each checked against the oracle."""
+    torch = torch_mod
+    rng = np.random.default_rng(5)
+    b = ifb.Batch(0)
+    jobs, keep, expects = [], [], []
+    for i in range(12):
+        iw = int(rng.integers(16, 160)) * 4
+        ih = int(rng.integers(40, 500))
+        ow = max(1, iw // int(rng.integers(2, 6)))
+        oh = max(1, ih // int(rng.integers(2, 6)))
+        alpha = bool(i % 2)
+        flt = [2, 6, 14][i % 3]
+        inp = util.noise(iw, ih, seed=100 + i, alpha_mode="mixed" if alpha else "opaque")
+        cv = util.noise(ow, oh, seed=200 + i, alpha_mode="mixed")
+        compose = i % 3
+        exp = cv.copy()
+        oracle.scale_and_render(inp, exp, filter=flt, alpha_meaningful=alpha, compose=compose, matte=(1, 2, 3, 255))
+        ti = torch.from_numpy(inp).cuda()
+        tc = torch.from_numpy(cv).cuda()
+        keep += [ti, tc]
+        jobs.append((ifb.BitmapWindow.from_torch(ti, alpha_meaningful=alpha),
+                     ifb.BitmapWindow.from_torch(tc, compose=ifb.BitmapCompositing(compose), matte_bgra=(1, 2, 3, 255)),
+                     ifb.ScaleAndRenderParams(w=ow, h=oh, interpolation_filter=ifb.Filter(flt))))
+        expects.append((tc, exp))
+    b.scale_and_render_many(jobs, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for tc, exp in expects:
+        assert util.diff_stats(tc.cpu().numpy(), exp)[0] == 0
+    assert b.fused_jobs + b.generic_jobs == 12
+    b.close()
