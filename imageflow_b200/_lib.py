@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libifb200.so")
+LIB_PATH = os.environ.get("IFB200_LIB") or os.path.join(_HERE, "libifb200.so")   # IFB200_LIB: A/B builds during development
 
 # every symbol include/ifb200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = [

@@ -88,7 +88,10 @@ struct AxisOnDev {
 // Supported (AV, SH) instantiations of the fused kernel.
 constexpr int kAvChoices[] = {2, 4, 6};
 constexpr int kShChoices[] = {3, 5, 6, 7, 8};
-constexpr int kPrefetch = 4;
+#ifndef IFB_PF
+#define IFB_PF 3
+#endif
+constexpr int kPrefetch = IFB_PF;   // rows per prefetch set (two sets in registers)
 
 struct FusedVariantTables {      // depends on NT (strips) and band count
     int nt = 0, n_strips = 0;
@@ -104,7 +107,8 @@ struct Plan {
     // fused
     bool fused_ok = false; std::string fused_reason;
     int av = 0, sh = 0;
-    DevVec<float> vw; DevVec<uint32_t> vdone;
+    std::vector<uint32_t> vdone_host;
+    std::unique_ptr<DevVec<uint32_t>> vprog[2];        // [f2]
     std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
 };
 
@@ -141,17 +145,41 @@ void build_fused_v(Plan& p) {
     p.sh = pick(kShChoices, (int)(sizeof kShChoices / sizeof *kShChoices), hneed);
     if (!p.sh) { p.fused_reason = "horizontal slots " + std::to_string(hneed) + " > 8"; return; }
 
-    std::vector<float> vw((size_t)p.in_h * p.av, 0.0f);
     std::vector<uint32_t> vdone(p.in_h, 0u);
     for (uint32_t y = 0; y < a.out_size; ++y) {
-        const float* w = a.w.data() + a.offset[y];
-        for (uint32_t j = a.left[y]; j <= a.right[y]; ++j) vw[(size_t)j * p.av + (y % p.av)] = w[j - a.left[y]];
         uint32_t& d = vdone[a.right[y]];
         if ((d & 0xffu) == 0) d = (y << 8) | 1u; else d += 1u;
         if ((d & 0xffu) == 0xffu) { p.fused_reason = "too many rows complete at once"; return; }
     }
-    p.vw.upload(vw); p.vdone.upload(vdone);
+    p.vdone_host = std::move(vdone);
     p.fused_ok = true;
+}
+
+// per-source-row program: ring-slot weights (float bits, duplicated pairs when f2) then the completion word
+const uint32_t* fused_vprog(Plan& p, bool f2) {
+    auto& slot = p.vprog[f2 ? 1 : 0];
+    if (slot) return slot->p;
+    const int nw = f2 ? 2 * p.av : p.av;
+    const int words = (nw + 1 + 3) / 4 * 4;
+    std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
+    const auto& a = p.wv;
+    // relative ring: at source row j slot r holds output row (number of rows completed before j) + r
+    std::vector<uint32_t> done_before(p.in_h + 1, 0u);
+    for (uint32_t j = 0; j < p.in_h; ++j) done_before[j + 1] = done_before[j] + (p.vdone_host[j] & 0xffu);
+    for (uint32_t y = 0; y < a.out_size; ++y) {
+        const float* w = a.w.data() + a.offset[y];
+        for (uint32_t j = a.left[y]; j <= a.right[y]; ++j) {
+            const uint32_t s = y - done_before[j];
+            if (s >= (uint32_t)p.av) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: ring slot %u >= %d", s, p.av);
+            uint32_t bits; memcpy(&bits, &w[j - a.left[y]], 4);
+            uint32_t* rec = prog.data() + (size_t)j * words;
+            if (f2) { rec[2 * s] = bits; rec[2 * s + 1] = bits; } else rec[s] = bits;
+        }
+    }
+    for (uint32_t j = 0; j < p.in_h; ++j) prog[(size_t)j * words + nw] = p.vdone_host[j];
+    slot = std::make_unique<DevVec<uint32_t>>();
+    slot->upload(prog);
+    return slot->p;
 }
 
 FusedVariantTables& fused_tables(Plan& p, int nt) {
@@ -213,8 +241,8 @@ FusedVariantTables& fused_tables(Plan& p, int nt) {
         }
         for (uint32_t X = sd.X0; X < (uint32_t)sd.X1; ++X) {
             const uint32_t tg0 = h.left[X] / 4 - sd.k0 / 4, ng = h.right[X] / 4 - h.left[X] / 4 + 1;
-            if (tg0 + ng > (uint32_t)nt) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: reader range outside strip");
-            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 16);
+            if (tg0 + ng > (uint32_t)nt || ng >= 4096u) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: reader range outside strip");
+            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12);
         }
     }
     ft->strips.upload(strips); ft->hw.upload(hw); ft->hxa.upload(hxa); ft->hrd.upload(hrd);
@@ -241,17 +269,33 @@ const BandDev* fused_bands(Plan& p, FusedVariantTables& ft, int nb) {
 // ------------------------------------------------------------------------------------------------
 // fused kernel dispatch table
 using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
-struct FusedEntry { int av, sh, ch; FusedFn fn; };
+struct FusedEntry { int av, sh, ch, rep; bool f2; int nt; FusedFn fn; };
+#define IFB_FUSED_V(AV_, SH_, CH_, REP_, F2_) \
+    {AV_, SH_, CH_, REP_, F2_, 256, fused_down_kernel<AV_, SH_, CH_, kPrefetch, REP_, F2_, 256>}, \
+    {AV_, SH_, CH_, REP_, F2_, 128, fused_down_kernel<AV_, SH_, CH_, kPrefetch, REP_, F2_, 128>}
+#ifdef IFB_ALL_VARIANTS      /* development builds: every (LUT replication, FFMA2) combination for A/B timing */
 #define IFB_FUSED(AV_, SH_) \
-    {AV_, SH_, 3, fused_down_kernel<AV_, SH_, 3, kPrefetch>}, {AV_, SH_, 4, fused_down_kernel<AV_, SH_, 4, kPrefetch>}
+    IFB_FUSED_V(AV_, SH_, 3, 32, true), IFB_FUSED_V(AV_, SH_, 4, 32, true), IFB_FUSED_V(AV_, SH_, 3, 32, false), IFB_FUSED_V(AV_, SH_, 4, 32, false), \
+    IFB_FUSED_V(AV_, SH_, 3, 1, true), IFB_FUSED_V(AV_, SH_, 4, 1, true), IFB_FUSED_V(AV_, SH_, 3, 1, false), IFB_FUSED_V(AV_, SH_, 4, 1, false)
+#else
+#define IFB_FUSED(AV_, SH_) IFB_FUSED_V(AV_, SH_, 3, 32, true), IFB_FUSED_V(AV_, SH_, 4, 32, true)
+#endif
 const FusedEntry kFused[] = {
+#ifdef IFB_FEW_SHAPES
+    IFB_FUSED(4, 5), IFB_FUSED(6, 7),
+#else
     IFB_FUSED(2, 3), IFB_FUSED(2, 5), IFB_FUSED(2, 6), IFB_FUSED(2, 7), IFB_FUSED(2, 8),
     IFB_FUSED(4, 3), IFB_FUSED(4, 5), IFB_FUSED(4, 6), IFB_FUSED(4, 7), IFB_FUSED(4, 8),
     IFB_FUSED(6, 3), IFB_FUSED(6, 5), IFB_FUSED(6, 6), IFB_FUSED(6, 7), IFB_FUSED(6, 8),
+#endif
 };
-FusedFn find_fused(int av, int sh, int ch) {
-    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch) return e.fn;
+FusedFn find_fused(int av, int sh, int ch, int rep, bool f2, int nt) {
+    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch && e.rep == rep && e.f2 == f2 && e.nt == nt) return e.fn;
     return nullptr;
+}
+size_t fused_smem_bytes(int av, int sh, int ch, int rep, bool f2, int nt) {
+    const int nw = f2 ? 2 * av : av, words = (nw + 1 + 3) / 4 * 4;
+    return sizeof(float) * ((size_t)256 * rep + (size_t)2 * kProgChunk * words + (size_t)sh * 4 * nt + (size_t)2 * ch * sh * nt + (size_t)nt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,7 +313,7 @@ struct ifb200_batch {
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
-    bool force_generic = false; int nt = 256; int min_ctas = 296;
+    bool force_generic = false; int nt = 256; int min_ctas = 296; int lut_rep = 32; bool f2 = true;
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0;
 
@@ -370,7 +414,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         const ifb200_resample_desc& d = descs[i];
         bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
         const int ch = d.alpha_meaningful ? 4 : 3;
-        if (fused && !find_fused(p.av, p.sh, ch)) fused = false;
+        if (fused && !find_fused(p.av, p.sh, ch, b->lut_rep, b->f2, b->nt)) fused = false;
         Group* g = nullptr;
         for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.fused == fused) { g = &gg; break; }
         if (!g) { groups.push_back(Group{&p, ch, fused, {}}); g = &groups.back(); }
@@ -403,10 +447,10 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             FusedPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
             pl.n_strips = ft.n_strips; pl.n_bands = nb;
-            pl.vw = p.vw.p; pl.vdone = p.vdone.p; pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
+            pl.vprog = fused_vprog(p, b->f2); pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
             pl.hw = ft.hw.p; pl.hxa = ft.hxa.p; pl.hrd = ft.hrd.p;
-            FusedFn fn = find_fused(p.av, p.sh, g.ch);
-            const size_t smem = (512 + (size_t)2 * g.ch * p.sh * b->nt) * sizeof(float);
+            FusedFn fn = find_fused(p.av, p.sh, g.ch, b->lut_rep, b->f2, b->nt);
+            const size_t smem = fused_smem_bytes(p.av, p.sh, g.ch, b->lut_rep, b->f2, b->nt);
             CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (size_t off = 0; off < nj; off += 65535) {
                 const size_t cnt = std::min<size_t>(65535, nj - off);
@@ -571,7 +615,7 @@ int ifb200_batch_enqueue(ifb200_batch* b, const ifb200_resample_desc* descs, siz
     return guarded(err, cap, [&] {
         if (!b || (!descs && n)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch or descriptor array");
         std::lock_guard<std::mutex> lk(b->mu);
-        enqueue_locked(b, descs, n, stream ? static_cast<cudaStream_t>(stream) : b->own_stream);
+        enqueue_locked(b, descs, n, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
     });
 }
 
@@ -580,7 +624,7 @@ int ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
         std::lock_guard<std::mutex> lk(b->mu);
-        color_matrix_locked(b, dev_px, w, h, stride, m, stream ? static_cast<cudaStream_t>(stream) : b->own_stream);
+        color_matrix_locked(b, dev_px, w, h, stride, m, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
     });
 }
 
@@ -603,11 +647,14 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     switch (option) {
     case IFB200_OPT_FORCE_GENERIC: b->force_generic = value != 0; return IFB200_OK;
     case IFB200_OPT_THREADS_PER_CTA:
-        if (value < 32 || value > 256 || (value % 32)) return IFB200_ERR_INVALID_ARGUMENT;
+        if (value != 128 && value != 256) return IFB200_ERR_INVALID_ARGUMENT;
         b->nt = (int)value; return IFB200_OK;
     case IFB200_OPT_MIN_CTAS:
         if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
         b->min_ctas = (int)value; return IFB200_OK;
+    case IFB200_OPT_KERNEL_VARIANT:
+        if (value < 0 || value > 3) return IFB200_ERR_INVALID_ARGUMENT;
+        b->f2 = (value & 1) == 0; b->lut_rep = (value & 2) ? 1 : 32; return IFB200_OK;
     default: return IFB200_ERR_INVALID_ARGUMENT;
     }
 }

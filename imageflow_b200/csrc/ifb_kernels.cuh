@@ -6,7 +6,7 @@
 // window_bgra32_apply_color_matrix (color_matrix.rs:5-28) as store epilogues.
 //
 // Arithmetic contract (identical in every kernel here and in oracle/ifb_oracle.c):
-//   load   p = (T[b]*af, T[g]*af, T[r]*af, af), af = A8[a]          alpha meaningful   (CH = 4)
+//   load   p = (T[b]*af, T[g]*af, T[r]*af, af), af = a*(1/255f)     alpha meaningful   (CH = 4)
 //          p = (T[b], T[g], T[r])                                    otherwise          (CH = 3)
 //   V pass fmaf chain over source rows, ascending, from +0
 //   H pass per aligned group of 4 source columns an fmaf chain from +0, group partials added ascending
@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 namespace ifbk {
 
@@ -45,8 +47,9 @@ struct BandDev  { int Y0, Y1, j0, j1; };        // output rows [Y0,Y1) read sour
 struct FusedPlanDev {
     uint32_t in_w, in_h, out_w, out_h;
     int n_strips, n_bands;
-    const float* vw;            // [in_h][AV] ring-slot weights per source row
-    const uint32_t* vdone;      // [in_h]  (first completed y << 8) | count
+    uint32_t zero;              // always 0 (run-time constant used to order loads after a scoreboard wait)
+    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weights of the open output rows, oldest first (float bits;
+                                //   duplicated pairs for the FFMA2 variant), then ((first completed y << 8) | count)
     const StripDev* strips;
     const BandDev* bands;
     const float* hw;            // [strip][SH][4][NT]
@@ -205,22 +208,48 @@ __global__ void __launch_bounds__(256) color_matrix_kernel(uint8_t* __restrict__
 // One CTA = (job, strip of output columns, band of output rows).  Thread t owns source columns
 // k0+4t .. k0+4t+3 for the whole band:
 //   pass 1 (V): streams source rows top to bottom straight from HBM into registers (one 16-byte load
-//               per row), converts through the shared-memory LUT once, and accumulates into a ring of
-//               AV register accumulators (one per output row whose window covers the current row).
-//   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its
-//               register-resident H weights into <= SH per-output partial sums, parks them in shared
-//               memory; after one __syncthreads thread u sums the partials of output column X0+u in
-//               ascending order, runs the store epilogue and writes one coalesced BGRA8 row segment.
+//               per row, PF rows in flight per thread), converts through a bank-conflict-free
+//               (lane-replicated) shared-memory LUT once, and accumulates into a ring of AV register
+//               accumulators (one per output row whose window covers the current source row).  The
+//               per-row "program" (ring weights + which output rows complete) is streamed through a
+//               double-buffered shared-memory chunk with cp.async.
+//   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its H weights
+//               into <= SH per-output partial sums and parks them in shared memory; after one
+//               __syncthreads thread u sums the partials of output column X0+u in ascending order,
+//               runs the store epilogue and writes one coalesced BGRA8 row segment.
 // Every source pixel is read from HBM once (plus strip/band halos), converted once, and the
 // V-filtered intermediate never leaves the SM.
-template <int AV, int SH, int CH, int PF>
-__global__ void __launch_bounds__(256, (AV * 4 * CH + SH * 4 <= 84) ? 2 : 1) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
-    extern __shared__ float smem[];
+constexpr int kProgChunk = 64;                       // source rows per program chunk
+
+template <int AV, bool F2> struct ProgLayout {
+    static constexpr int kW = F2 ? 2 * AV : AV;      // weight words (duplicated pairs for FFMA2)
+    static constexpr int kDone = kW;                 // index of the completion word
+    static constexpr int kWords = (kW + 1 + 3) / 4 * 4;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+// (a & mask) | c in one LOP3
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int AV, int SH, int CH, int PF, int REP, bool F2, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
+    using PL = ProgLayout<AV, F2>;
+    constexpr int NV = 4 * CH;                      // working floats per thread per row
+    extern __shared__ __align__(16) float smem[];
     const int t = threadIdx.x;
-    const int NT = blockDim.x;
-    float* sT = smem;                              // 256: colour transfer table
-    float* sA = smem + 256;                        // 256: alpha table (only CH == 4)
-    float* sPart = smem + 512;                     // 2 x CH x SH x NT partial sums
+    float* sT = smem;                                // 256*REP colour transfer table, [v][replica]
+    uint32_t* sProg = reinterpret_cast<uint32_t*>(sT + 256 * REP);                    // 2 x kProgChunk x PL::kWords
+    float* sHw = reinterpret_cast<float*>(sProg + 2 * kProgChunk * PL::kWords);       // SH x 4 x NT
+    float* sPart = sHw + SH * 4 * NT;                // 2 x CH x SH x NT partial sums
+    uint32_t* sMeta = reinterpret_cast<uint32_t*>(sPart + 2 * CH * SH * NT);          // NT: reader range | first plane
 
     const JobDev& job = jobs[blockIdx.y];
     const int strip = blockIdx.x % pl.n_strips;
@@ -230,104 +259,168 @@ __global__ void __launch_bounds__(256, (AV * 4 * CH + SH * 4 <= 84) ? 2 : 1) fus
 
     {
         const float* __restrict__ T = (job.flags & JF_LINEAR) ? tb.t_lin : tb.t_srgb;
-        for (int i = t; i < 256; i += NT) { sT[i] = __ldg(T + i); sA[i] = __ldg(tb.t_srgb + i); }
+        for (int i = t; i < 256 * REP; i += NT) sT[i] = __ldg(T + i / REP);
+        for (int i = t; i < SH * 4 * NT; i += NT) sHw[i] = __ldg(pl.hw + (size_t)strip * SH * 4 * NT + i);
     }
-    float hw[SH][4];
-#pragma unroll
-    for (int q = 0; q < SH; ++q)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hw[q][i] = __ldg(pl.hw + ((size_t)(strip * SH + q) * 4 + i) * NT + t);
-    int plane0 = __ldg(pl.hxa + strip * NT + t) % SH;
-    const uint32_t rd = __ldg(pl.hrd + strip * NT + t);
+    sMeta[t] = __ldg(pl.hrd + strip * NT + t) | ((uint32_t)(__ldg(pl.hxa + strip * NT + t) % SH) << 24);
+    // outputs of this strip are finished by alternating halves of the CTA when they fit in one half
     const int NX = sd.X1 - sd.X0;
+    const bool alternate = NX <= NT / 2;
+
+    // program chunk 0
+    const uint32_t* __restrict__ gprog = pl.vprog + (size_t)bd.j0 * PL::kWords;
+    const int total_rows = bd.j1 - bd.j0 + 1;
+    {
+        const int n16 = min(kProgChunk, total_rows) * PL::kWords / 4;
+        for (int i = t; i < n16; i += NT) cp_async16(sProg + i * 4, gprog + i * 4);
+        cp_async_wait_all();
+    }
     __syncthreads();
 
     int col = sd.k0 + 4 * t;
     if (col > (int)pl.in_w - 4) col = (int)pl.in_w - 4;        // threads past the edge re-read the last group; their H weights are 0
-    const uint8_t* __restrict__ src = job.in + (size_t)col * 4;
     const size_t stride = job.in_stride;
+    const uint8_t* __restrict__ pnext = job.in + (size_t)col * 4 + (size_t)bd.j0 * stride;
+    int jnext = bd.j0;
 
-    float acc[AV][4][CH];
+    // acc[r] belongs to the r-th oldest output row still open (relative ring: completing a row shifts it)
+    float acc[AV][NV];
 #pragma unroll
     for (int s = 0; s < AV; ++s)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int c = 0; c < CH; ++c) acc[s][i][c] = 0.0f;
+        for (int i = 0; i < NV; ++i) acc[s][i] = 0.0f;
 
-    uint4 pf[PF];
+    // Source rows in flight: two register sets of PF rows.  While set A is consumed, the PF loads of set B are
+    // outstanding (and vice versa).  All loads share one hardware scoreboard, and a scoreboard wait drains every
+    // load issued before it, so the next set is only requested after the current one has landed: the prefetch
+    // distance is PF rows of work.
+    uint4 pf[2][PF];
 #pragma unroll
     for (int d = 0; d < PF; ++d) {
-        const int j = min(bd.j0 + d, bd.j1);
-        pf[d] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)j * stride));
+        pf[0][d] = __ldcs(reinterpret_cast<const uint4*>(pnext));
+        if (jnext < bd.j1) { pnext += stride; ++jnext; }
     }
     int nrow = 0;
+    int ring_pos = 0;
+    const uint32_t lut_lane = (uint32_t)((t & 31) & (REP - 1)) * 4u;
+    const char* sTb = reinterpret_cast<const char*>(sT);
 
-    for (int jb = bd.j0; jb <= bd.j1; jb += PF) {
+    for (int c0 = 0; c0 < total_rows; c0 += kProgChunk) {
+        const int chunk = c0 / kProgChunk;
+        const uint32_t* prog = sProg + (chunk & 1) * kProgChunk * PL::kWords;
+        {   // stream the next program chunk while this one is consumed
+            const int rows_next = min(kProgChunk, total_rows - (c0 + kProgChunk));
+            if (rows_next > 0) {
+                uint32_t* dst = sProg + ((chunk + 1) & 1) * kProgChunk * PL::kWords;
+                const uint32_t* srcp = gprog + (size_t)(c0 + kProgChunk) * PL::kWords;
+                for (int i = t; i < rows_next * PL::kWords / 4; i += NT) cp_async16(dst + i * 4, srcp + i * 4);
+            }
+        }
+        const int rows_here = min(kProgChunk, total_rows - c0);
+        int r = 0;
+        // One source row (ring position D of 2*PF): LUT-convert, accumulate; at a set boundary request the next set.
+        // Returns the completion word of the row (0 = no output row completes here).
+        auto do_row = [&](auto dtag) -> uint32_t {
+            constexpr int D = decltype(dtag)::value;
+            constexpr int SET = D / PF, IDX = D % PF;
+            const uint4 raw = pf[SET][IDX];
+            if (IDX == 0) {                       // set SET has landed: request the other set
+                // pl.zero is 0 at run time; tying the address to the data just consumed keeps the compiler from
+                // issuing these loads ahead of the scoreboard wait for the current set (see the comment at pf[]).
+                const uint8_t* __restrict__ pdep = pnext + (raw.x & pl.zero);
+                pnext = pdep;
 #pragma unroll
-        for (int d = 0; d < PF; ++d) {
-            const int j = jb + d;
-            if (j <= bd.j1) {
-                const uint4 raw = pf[d];
-                {
-                    const int jn = min(j + PF, bd.j1);
-                    pf[d] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)jn * stride));
+                for (int i = 0; i < PF; ++i) {
+                    pf[SET ^ 1][i] = __ldcs(reinterpret_cast<const uint4*>(pnext));
+                    if (jnext < bd.j1) { pnext += stride; ++jnext; }
                 }
-                float wv[AV];
+            }
+            const uint32_t* rec = prog + r * PL::kWords;
+            ++r;
+            // ---- sRGB bytes -> working floats (LUT gather; replica = lane, so no bank conflicts when REP == 32)
+            float p[NV];
+            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-                for (int s = 0; s < AV; ++s) wv[s] = __ldg(pl.vw + (size_t)j * AV + s);
-                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float p[CH];
-                    p[0] = sT[w4[i] & 0xffu];
-                    p[1] = sT[(w4[i] >> 8) & 0xffu];
-                    p[2] = sT[(w4[i] >> 16) & 0xffu];
-                    if (CH == 4) {
-                        const float af = sA[w4[i] >> 24];
-                        p[0] = __fmul_rn(p[0], af); p[1] = __fmul_rn(p[1], af); p[2] = __fmul_rn(p[2], af);
-                        p[CH - 1] = af;
-                    }
-#pragma unroll
-                    for (int s = 0; s < AV; ++s)
-#pragma unroll
-                        for (int c = 0; c < CH; ++c) acc[s][i][c] = __fmaf_rn(wv[s], p[c], acc[s][i][c]);
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t v = w4[i];
+                const uint32_t ib = and_or(v * (4u * REP), 0xffu * 4u * REP, lut_lane);
+                const uint32_t ig = and_or((v >> 8) * (4u * REP), 0xffu * 4u * REP, lut_lane);
+                const uint32_t ir = and_or((v >> 16) * (4u * REP), 0xffu * 4u * REP, lut_lane);
+                p[i * CH + 0] = *reinterpret_cast<const float*>(sTb + ib);
+                p[i * CH + 1] = *reinterpret_cast<const float*>(sTb + ig);
+                p[i * CH + 2] = *reinterpret_cast<const float*>(sTb + ir);
+                if (CH == 4) {
+                    // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
+                    const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
+                    p[i * CH + 0] = __fmul_rn(p[i * CH + 0], af);
+                    p[i * CH + 1] = __fmul_rn(p[i * CH + 1], af);
+                    p[i * CH + 2] = __fmul_rn(p[i * CH + 2], af);
+                    p[i * CH + CH - 1] = af;
                 }
-                const uint32_t dn = __ldg(pl.vdone + j);
-                const int ndone = dn & 0xffu;
-                for (int e = 0; e < ndone; ++e) {
-                    const int y = (int)(dn >> 8) + e;
-                    const int slot = y % AV;
-                    float v[4][CH];
+            }
+            // ---- ring accumulate
+            if (F2) {
 #pragma unroll
-                    for (int s = 0; s < AV; ++s) {
-                        if (s == slot) {
+                for (int s = 0; s < AV; ++s) {
+                    const float2 w2 = *reinterpret_cast<const float2*>(rec + 2 * s);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                                for (int c = 0; c < CH; ++c) { v[i][c] = acc[s][i][c]; acc[s][i][c] = 0.0f; }
-                        }
+                    for (int k = 0; k < NV / 2; ++k) {
+                        const float2 r2 = __ffma2_rn(w2, make_float2(p[2 * k], p[2 * k + 1]), make_float2(acc[s][2 * k], acc[s][2 * k + 1]));
+                        acc[s][2 * k] = r2.x; acc[s][2 * k + 1] = r2.y;
                     }
-                    if (y < bd.Y0 || y >= bd.Y1) continue;            // halo rows of a neighbouring band
-                    float* pb = sPart + (size_t)(nrow & 1) * (CH * SH) * NT;
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < AV; ++s) {
+                    const float w = __uint_as_float(rec[s]);
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) acc[s][k] = __fmaf_rn(w, p[k], acc[s][k]);
+                }
+            }
+            return rec[PL::kDone];
+        };
+        // The PF ring positions are PF copies of do_row; the (much larger) completion code below exists once:
+        // a row that completes output rows breaks out of the switch, and the loop re-enters at the next ring position.
+        while (r < rows_here) {
+            uint32_t dn = 0;
+            switch (ring_pos) {
+#define IFB_ROW_CASE(D_) \
+            case D_: if (D_ < 2 * PF) { dn = do_row(std::integral_constant<int, (D_) % (2 * PF)>{}); ring_pos = ((D_) + 1) % (2 * PF); if (dn || r >= rows_here) break; }
+            IFB_ROW_CASE(0) IFB_ROW_CASE(1) IFB_ROW_CASE(2) IFB_ROW_CASE(3) IFB_ROW_CASE(4) IFB_ROW_CASE(5) IFB_ROW_CASE(6) IFB_ROW_CASE(7)
+            IFB_ROW_CASE(8) IFB_ROW_CASE(9) IFB_ROW_CASE(10) IFB_ROW_CASE(11)
+#undef IFB_ROW_CASE
+            default: ring_pos = 0; break;
+            }
+            // ---- completed output rows: always the oldest (acc[0]); then the ring shifts down
+            const int ndone = dn & 0xffu;
+            for (int e = 0; e < ndone; ++e) {
+                const int y = (int)(dn >> 8) + e;
+                if (y >= bd.Y0 && y < bd.Y1) {                        // else: halo row of a neighbouring band
+                    float* pb = sPart + (nrow & 1) * (CH * SH) * NT;
+                    const int plane0 = (int)(sMeta[t] >> 24);
 #pragma unroll
                     for (int q = 0; q < SH; ++q) {
                         int plane = plane0 + q; if (plane >= SH) plane -= SH;
+                        const float h0 = sHw[(q * 4 + 0) * NT + t], h1 = sHw[(q * 4 + 1) * NT + t];
+                        const float h2 = sHw[(q * 4 + 2) * NT + t], h3 = sHw[(q * 4 + 3) * NT + t];
 #pragma unroll
                         for (int c = 0; c < CH; ++c) {
-                            float ps = __fmaf_rn(hw[q][0], v[0][c], 0.0f);
-                            ps = __fmaf_rn(hw[q][1], v[1][c], ps);
-                            ps = __fmaf_rn(hw[q][2], v[2][c], ps);
-                            ps = __fmaf_rn(hw[q][3], v[3][c], ps);
+                            float ps = __fmaf_rn(h0, acc[0][0 * CH + c], 0.0f);
+                            ps = __fmaf_rn(h1, acc[0][1 * CH + c], ps);
+                            ps = __fmaf_rn(h2, acc[0][2 * CH + c], ps);
+                            ps = __fmaf_rn(h3, acc[0][3 * CH + c], ps);
                             pb[(c * SH + plane) * NT + t] = ps;
                         }
                     }
                     __syncthreads();
-                    if (t < NX) {
-                        const int X = sd.X0 + t;
+                    const int u = alternate ? t - (nrow & 1) * (NT / 2) : t;
+                    if (u >= 0 && u < NX) {
+                        const uint32_t meta = sMeta[u];
+                        const int X = sd.X0 + u;
                         const int plane = X % SH;
-                        const int tg0 = rd & 0xffffu, ng = rd >> 16;
+                        const int tg0 = meta & 0xfffu, ng = (meta >> 12) & 0xfffu;
                         float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
                         for (int g = 0; g < ng; ++g) {
 #pragma unroll
                             for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], pb[(c * SH + plane) * NT + tg0 + g]);
@@ -337,8 +430,16 @@ __global__ void __launch_bounds__(256, (AV * 4 * CH + SH * 4 <= 84) ? 2 : 1) fus
                     }
                     ++nrow;
                 }
+#pragma unroll
+                for (int s = 0; s + 1 < AV; ++s)
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) acc[s][k] = acc[s + 1][k];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) acc[AV - 1][k] = 0.0f;
             }
         }
+        cp_async_wait_all();
+        __syncthreads();
     }
 }
 

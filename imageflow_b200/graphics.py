@@ -169,7 +169,7 @@ def device_count() -> int:
 class Batch:
     """Device-resident batch executor (ifb200_batch_*): many independent scale_and_render calls whose
     bitmaps already live in HBM of one GPU, enqueued on a CUDA stream."""
-    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS = 1, 2, 3
+    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS, OPT_KERNEL_VARIANT = 1, 2, 3, 4
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
@@ -192,21 +192,28 @@ class Batch:
             arr[i] = _desc(j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
         return arr, keep
 
-    def enqueue(self, descs, stream: int = 0, keep=None) -> None:
+    STREAM_OWN = C.c_void_p(-1)
+
+    @classmethod
+    def _stream(cls, stream):
+        """None -> the batch's own stream (IFB200_STREAM_OWN); an int is a cudaStream_t (0 = legacy default stream)."""
+        return cls.STREAM_OWN if stream is None else C.c_void_p(stream)
+
+    def enqueue(self, descs, stream=None, keep=None) -> None:
         if keep:
             self._keep.append(keep)
         buf = C.create_string_buffer(512)
-        _check(lib().ifb200_batch_enqueue(self._h, descs, len(descs), C.c_void_p(stream) if stream else None, buf, 512), buf)
+        _check(lib().ifb200_batch_enqueue(self._h, descs, len(descs), self._stream(stream), buf, 512), buf)
 
-    def scale_and_render_many(self, jobs, stream: int = 0) -> None:
+    def scale_and_render_many(self, jobs, stream=None) -> None:
         descs, keep = self.make_descs(jobs)
         self.enqueue(descs, stream, keep)
 
-    def color_matrix(self, dev_ptr: int, w: int, h: int, stride: int, m, stream: int = 0) -> None:
+    def color_matrix(self, dev_ptr: int, w: int, h: int, stride: int, m, stream=None) -> None:
         mm = np.ascontiguousarray(m, np.float32).reshape(25)
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_color_matrix(self._h, dev_ptr, w, h, stride, mm.ctypes.data_as(C.POINTER(C.c_float)),
-                                                C.c_void_p(stream) if stream else None, buf, 512), buf)
+                                                self._stream(stream), buf, 512), buf)
 
     def sync(self) -> None:
         buf = C.create_string_buffer(512)

@@ -108,7 +108,10 @@ int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stri
 
 /* ---- device-resident batch API (the metric path; not in the reference) -----------------------
  * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
- * enqueue is asynchronous on `cuda_stream` (a cudaStream_t; NULL = the batch's own stream). */
+ * enqueue is asynchronous on `cuda_stream`, a cudaStream_t with the usual CUDA meaning (NULL = the legacy
+ * default stream); pass IFB200_STREAM_OWN to use the batch's private non-blocking stream, which is the
+ * stream ifb200_batch_sync waits on. */
+#define IFB200_STREAM_OWN ((void*)(intptr_t)-1)
 typedef struct ifb200_batch ifb200_batch;
 int  ifb200_batch_create(int device, ifb200_batch** out, char* err, size_t err_cap);
 int  ifb200_batch_enqueue(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, void* cuda_stream,
@@ -120,8 +123,11 @@ void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */
 enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
-    IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size (multiple of 32)                           */
-    IFB200_OPT_MIN_CTAS = 3            /* split images into row bands until the grid has this many CTAs   */
+    IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size: 128 or 256 (strip = 4x that many columns) */
+    IFB200_OPT_MIN_CTAS = 3,           /* split images into row bands until the grid has this many CTAs   */
+    IFB200_OPT_KERNEL_VARIANT = 4      /* A/B timing of fused-kernel variants (bit0: scalar FFMA instead of
+                                          FFMA2, bit1: unreplicated LUT); variants missing from the build
+                                          silently fall back to the generic pair; results are bit-identical */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */

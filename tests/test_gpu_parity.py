@@ -106,7 +106,7 @@ def test_fused_kernel_is_the_one_that_runs(ifb, torch_mod):
     assert fused == 0
 
 
-@pytest.mark.parametrize("nt,min_ctas", [(128, 1), (256, 1), (256, 4096), (64, 64)])
+@pytest.mark.parametrize("nt,min_ctas", [(128, 1), (256, 1), (256, 4096), (128, 64)])
 def test_fused_decompositions_agree(ifb, torch_mod, nt, min_ctas):
     """strip width and row-band count must not change a single bit."""
     inp = util.noise(1280, 720, seed=7, alpha_mode="mixed")
