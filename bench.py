@@ -56,7 +56,6 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--nt", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=-1, help="IFB200_OPT_KERNEL_VARIANT (dev builds)")
     return ap.parse_args()
 
 
@@ -235,8 +234,6 @@ def main():
     batch = ifb.Batch(local)
     if args.nt:
         batch.set_option(ifb.Batch.OPT_THREADS_PER_CTA, args.nt)
-    if args.variant >= 0:
-        batch.set_option(ifb.Batch.OPT_KERNEL_VARIANT, args.variant)
     params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))
     jobs = [(ifb.BitmapWindow.from_torch(inp[i], alpha_meaningful=bool(alpha)),
              ifb.BitmapWindow.from_torch(out[i], compose=ifb.BitmapCompositing(wl["compose"])), params, cm) for i in range(B)]
@@ -279,7 +276,8 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = e0.elapsed_time(e1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in k_ev]))
+    step_ms = [a.elapsed_time(b) for a, b in k_ev]
+    kern_ms = float(np.mean(step_ms))
     launches = batch.kernel_launches - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -293,7 +291,8 @@ def main():
     achieved = alg / (kern_ms / 1e3) / 1e9
     tap_flops = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_min": float(np.min(step_ms)),
+                "kernel_ms_all": [round(x, 4) for x in step_ms], "algorithmic_bytes_per_launch": alg,
                 "fused_jobs": batch.fused_jobs, "generic_jobs": batch.generic_jobs}
     tfile = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tfile):

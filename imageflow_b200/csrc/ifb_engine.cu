@@ -108,7 +108,7 @@ struct Plan {
     bool fused_ok = false; std::string fused_reason;
     int av = 0, sh = 0;
     std::vector<uint32_t> vdone_host;
-    std::unique_ptr<DevVec<uint32_t>> vprog[2];        // [f2]
+    std::unique_ptr<DevVec<uint32_t>> vprog;
     std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
 };
 
@@ -155,11 +155,12 @@ void build_fused_v(Plan& p) {
     p.fused_ok = true;
 }
 
-// per-source-row program: ring-slot weights (float bits, duplicated pairs when f2) then the completion word
-const uint32_t* fused_vprog(Plan& p, bool f2) {
-    auto& slot = p.vprog[f2 ? 1 : 0];
+// per-source-row program: weights of the open output rows, oldest first (float bits, duplicated pairs), then the completion word
+const uint32_t* fused_vprog(Plan& p) {
+    auto& slot = p.vprog;
     if (slot) return slot->p;
-    const int nw = f2 ? 2 * p.av : p.av;
+    const bool f2 = true;                 // weights are stored as (w,w) pairs for FFMA2
+    const int nw = 2 * p.av;
     const int words = (nw + 1 + 3) / 4 * 4;
     std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
     const auto& a = p.wv;
@@ -269,19 +270,11 @@ const BandDev* fused_bands(Plan& p, FusedVariantTables& ft, int nb) {
 // ------------------------------------------------------------------------------------------------
 // fused kernel dispatch table
 using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
-struct FusedEntry { int av, sh, ch, rep; bool f2; int nt; FusedFn fn; };
-#define IFB_FUSED_V(AV_, SH_, CH_, REP_, F2_) \
-    {AV_, SH_, CH_, REP_, F2_, 256, fused_down_kernel<AV_, SH_, CH_, kPrefetch, REP_, F2_, 256>}, \
-    {AV_, SH_, CH_, REP_, F2_, 128, fused_down_kernel<AV_, SH_, CH_, kPrefetch, REP_, F2_, 128>}
-#ifdef IFB_ALL_VARIANTS      /* development builds: every (LUT replication, FFMA2) combination for A/B timing */
-#define IFB_FUSED(AV_, SH_) \
-    IFB_FUSED_V(AV_, SH_, 3, 32, true), IFB_FUSED_V(AV_, SH_, 4, 32, true), IFB_FUSED_V(AV_, SH_, 3, 32, false), IFB_FUSED_V(AV_, SH_, 4, 32, false), \
-    IFB_FUSED_V(AV_, SH_, 3, 1, true), IFB_FUSED_V(AV_, SH_, 4, 1, true), IFB_FUSED_V(AV_, SH_, 3, 1, false), IFB_FUSED_V(AV_, SH_, 4, 1, false)
-#else
-#define IFB_FUSED(AV_, SH_) IFB_FUSED_V(AV_, SH_, 3, 32, true), IFB_FUSED_V(AV_, SH_, 4, 32, true)
-#endif
+struct FusedEntry { int av, sh, ch, nt; FusedFn fn; size_t smem; };
+#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
+#define IFB_FUSED(AV_, SH_) IFB_FUSED_1(AV_, SH_, 3, 256), IFB_FUSED_1(AV_, SH_, 4, 256), IFB_FUSED_1(AV_, SH_, 3, 128), IFB_FUSED_1(AV_, SH_, 4, 128)
 const FusedEntry kFused[] = {
-#ifdef IFB_FEW_SHAPES
+#ifdef IFB_FEW_SHAPES      /* development builds: only the shapes the 4K->512 benchmarks use */
     IFB_FUSED(4, 5), IFB_FUSED(6, 7),
 #else
     IFB_FUSED(2, 3), IFB_FUSED(2, 5), IFB_FUSED(2, 6), IFB_FUSED(2, 7), IFB_FUSED(2, 8),
@@ -289,13 +282,9 @@ const FusedEntry kFused[] = {
     IFB_FUSED(6, 3), IFB_FUSED(6, 5), IFB_FUSED(6, 6), IFB_FUSED(6, 7), IFB_FUSED(6, 8),
 #endif
 };
-FusedFn find_fused(int av, int sh, int ch, int rep, bool f2, int nt) {
-    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch && e.rep == rep && e.f2 == f2 && e.nt == nt) return e.fn;
+const FusedEntry* find_fused(int av, int sh, int ch, int nt) {
+    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch && e.nt == nt) return &e;
     return nullptr;
-}
-size_t fused_smem_bytes(int av, int sh, int ch, int rep, bool f2, int nt) {
-    const int nw = f2 ? 2 * av : av, words = (nw + 1 + 3) / 4 * 4;
-    return sizeof(float) * ((size_t)256 * rep + (size_t)2 * kProgChunk * words + (size_t)sh * 4 * nt + (size_t)2 * ch * sh * nt + (size_t)nt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,7 +302,7 @@ struct ifb200_batch {
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
-    bool force_generic = false; int nt = 256; int min_ctas = 296; int lut_rep = 32; bool f2 = true;
+    bool force_generic = false; int nt = 256; int min_ctas = 296;
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0;
 
@@ -414,7 +403,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         const ifb200_resample_desc& d = descs[i];
         bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
         const int ch = d.alpha_meaningful ? 4 : 3;
-        if (fused && !find_fused(p.av, p.sh, ch, b->lut_rep, b->f2, b->nt)) fused = false;
+        if (fused && !find_fused(p.av, p.sh, ch, b->nt)) fused = false;
         Group* g = nullptr;
         for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.fused == fused) { g = &gg; break; }
         if (!g) { groups.push_back(Group{&p, ch, fused, {}}); g = &groups.back(); }
@@ -447,10 +436,11 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             FusedPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
             pl.n_strips = ft.n_strips; pl.n_bands = nb;
-            pl.vprog = fused_vprog(p, b->f2); pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
+            pl.vprog = fused_vprog(p); pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
             pl.hw = ft.hw.p; pl.hxa = ft.hxa.p; pl.hrd = ft.hrd.p;
-            FusedFn fn = find_fused(p.av, p.sh, g.ch, b->lut_rep, b->f2, b->nt);
-            const size_t smem = fused_smem_bytes(p.av, p.sh, g.ch, b->lut_rep, b->f2, b->nt);
+            const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
+            FusedFn fn = fe->fn;
+            const size_t smem = fe->smem;
             CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (size_t off = 0; off < nj; off += 65535) {
                 const size_t cnt = std::min<size_t>(65535, nj - off);
@@ -652,9 +642,6 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     case IFB200_OPT_MIN_CTAS:
         if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
         b->min_ctas = (int)value; return IFB200_OK;
-    case IFB200_OPT_KERNEL_VARIANT:
-        if (value < 0 || value > 3) return IFB200_ERR_INVALID_ARGUMENT;
-        b->f2 = (value & 1) == 0; b->lut_rep = (value & 2) ? 1 : 32; return IFB200_OK;
     default: return IFB200_ERR_INVALID_ARGUMENT;
     }
 }

@@ -48,13 +48,13 @@ struct FusedPlanDev {
     uint32_t in_w, in_h, out_w, out_h;
     int n_strips, n_bands;
     uint32_t zero;              // always 0 (run-time constant used to order loads after a scoreboard wait)
-    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weights of the open output rows, oldest first (float bits;
-                                //   duplicated pairs for the FFMA2 variant), then ((first completed y << 8) | count)
+    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weights of the open output rows, oldest first (float bits,
+                                //   each duplicated into a pair for FFMA2), then ((first completed y << 8) | count)
     const StripDev* strips;
     const BandDev* bands;
     const float* hw;            // [strip][SH][4][NT]
     const int* hxa;             // [strip][NT] first output column touched by thread t's 4 columns
-    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 16)
+    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12)
 };
 
 // ---------------------------------------------------------------- scalar helpers
@@ -213,16 +213,18 @@ __global__ void __launch_bounds__(256) color_matrix_kernel(uint8_t* __restrict__
 //               accumulators (one per output row whose window covers the current source row).  The
 //               per-row "program" (ring weights + which output rows complete) is streamed through a
 //               double-buffered shared-memory chunk with cp.async.
-//   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its H weights
-//               into <= SH per-output partial sums and parks them in shared memory; after one
-//               __syncthreads thread u sums the partials of output column X0+u in ascending order,
-//               runs the store epilogue and writes one coalesced BGRA8 row segment.
+//   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its H weights into <= SH
+//               per-output partial sums and parks them in shared memory; after one __syncthreads thread u sums
+//               the partials of output column X0+u in ascending order, runs the store epilogue and writes one
+//               coalesced BGRA8 row segment.  Partials are double-buffered and consecutive completions use
+//               alternating halves of the CTA, so one barrier per output row suffices.
 // Every source pixel is read from HBM once (plus strip/band halos), converted once, and the
 // V-filtered intermediate never leaves the SM.
-constexpr int kProgChunk = 64;                       // source rows per program chunk
+constexpr int kProgChunk = 32;                       // source rows per program chunk
+constexpr int kLutBytes = 256 * 256;                 // LUT region: 256 rows of 256 B (see below)
 
-template <int AV, bool F2> struct ProgLayout {
-    static constexpr int kW = F2 ? 2 * AV : AV;      // weight words (duplicated pairs for FFMA2)
+template <int AV> struct ProgLayout {
+    static constexpr int kW = 2 * AV;                // weight words: (w,w) pairs, ready for FFMA2
     static constexpr int kDone = kW;                 // index of the completion word
     static constexpr int kWords = (kW + 1 + 3) / 4 * 4;
 };
@@ -231,25 +233,39 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
-// (a & mask) | c in one LOP3
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(c));
-    return d;
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int AV, int SH, int CH, int PF, int REP, bool F2, int NT>
+// Shared-memory map of the fused kernel.
+//   [0, 64 KB)   row v (256 B): bytes 0..127 = T[v] replicated for the 32 lanes, so the byte address of a lookup is
+//                (v << 8) | (lane << 2): ONE PRMT builds it from the packed pixel, and the gather is bank-conflict
+//                free for any image content.  Bytes 128..255 of the rows ("holes") hold the strip's H weights:
+//                word w of hw[SH][4][NT] lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2).
+//   then         row-program double buffer, partial sums (2 x CH x SH x NT floats), per-thread reader meta.
+template <int AV, int SH, int CH, int NT> struct FusedSmem {
+    static constexpr int kProgBytes = 2 * kProgChunk * ProgLayout<AV>::kWords * 4;
+    static constexpr int kPartBytes = 2 * CH * SH * NT * 4;
+    static constexpr int kProgOff = kLutBytes;
+    static constexpr int kPartOff = kProgOff + kProgBytes;
+    static constexpr int kMetaOff = kPartOff + kPartBytes;
+    static constexpr int kTotal = kMetaOff + NT * 4;
+    static_assert(SH * 4 * NT / 32 <= 256, "H weights must fit in the LUT holes");
+};
+
+template <int AV, int SH, int CH, int PF, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
-    using PL = ProgLayout<AV, F2>;
-    constexpr int NV = 4 * CH;                      // working floats per thread per row
-    extern __shared__ __align__(16) float smem[];
+    using PL = ProgLayout<AV>;
+    using SM = FusedSmem<AV, SH, CH, NT>;
+    constexpr int NV = 4 * CH;                      // working floats per thread per row, channel-planar: [c][pixel]
+    static_assert(2 * PF <= 12, "ring positions");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x;
-    float* sT = smem;                                // 256*REP colour transfer table, [v][replica]
-    uint32_t* sProg = reinterpret_cast<uint32_t*>(sT + 256 * REP);                    // 2 x kProgChunk x PL::kWords
-    float* sHw = reinterpret_cast<float*>(sProg + 2 * kProgChunk * PL::kWords);       // SH x 4 x NT
-    float* sPart = sHw + SH * 4 * NT;                // 2 x CH x SH x NT partial sums
-    uint32_t* sMeta = reinterpret_cast<uint32_t*>(sPart + 2 * CH * SH * NT);          // NT: reader range | first plane
+    unsigned char* sLut = smem_raw;
+    uint32_t* sProg = reinterpret_cast<uint32_t*>(smem_raw + SM::kProgOff);
+    float* sPart = reinterpret_cast<float*>(smem_raw + SM::kPartOff);
+    uint32_t* sMeta = reinterpret_cast<uint32_t*>(smem_raw + SM::kMetaOff);
+    // this thread's H weights: word (q*4+i)*NT + t of hw  ->  hole address
+    const float* sHwT = reinterpret_cast<const float*>(sLut + ((t >> 5) << 8) + 128 + ((t & 31) << 2));
+    constexpr int kHwStep = (NT / 32) * 256 / 4;     // floats between consecutive (q,i) entries of one thread
 
     const JobDev& job = jobs[blockIdx.y];
     const int strip = blockIdx.x % pl.n_strips;
@@ -259,13 +275,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
 
     {
         const float* __restrict__ T = (job.flags & JF_LINEAR) ? tb.t_lin : tb.t_srgb;
-        for (int i = t; i < 256 * REP; i += NT) sT[i] = __ldg(T + i / REP);
-        for (int i = t; i < SH * 4 * NT; i += NT) sHw[i] = __ldg(pl.hw + (size_t)strip * SH * 4 * NT + i);
+        for (int i = t; i < 256 * 32; i += NT)
+            *reinterpret_cast<float*>(sLut + ((i >> 5) << 8) + ((i & 31) << 2)) = __ldg(T + (i >> 5));
+        for (int w = t; w < SH * 4 * NT; w += NT)
+            *reinterpret_cast<float*>(sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2)) = __ldg(pl.hw + (size_t)strip * SH * 4 * NT + w);
     }
     sMeta[t] = __ldg(pl.hrd + strip * NT + t) | ((uint32_t)(__ldg(pl.hxa + strip * NT + t) % SH) << 24);
     // outputs of this strip are finished by alternating halves of the CTA when they fit in one half
     const int NX = sd.X1 - sd.X0;
     const bool alternate = NX <= NT / 2;
+    const int my_half = t / (NT / 2);
 
     // program chunk 0
     const uint32_t* __restrict__ gprog = pl.vprog + (size_t)bd.j0 * PL::kWords;
@@ -302,8 +321,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     }
     int nrow = 0;
     int ring_pos = 0;
-    const uint32_t lut_lane = (uint32_t)((t & 31) & (REP - 1)) * 4u;
-    const char* sTb = reinterpret_cast<const char*>(sT);
+    const uint32_t lane4 = (uint32_t)(t & 31) * 4u;
 
     for (int c0 = 0; c0 < total_rows; c0 += kProgChunk) {
         const int chunk = c0 / kProgChunk;
@@ -337,50 +355,38 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             }
             const uint32_t* rec = prog + r * PL::kWords;
             ++r;
-            // ---- sRGB bytes -> working floats (LUT gather; replica = lane, so no bank conflicts when REP == 32)
+            // ---- sRGB bytes -> working floats: address = (byte << 8) | (lane << 2), one PRMT per lookup
             float p[NV];
             const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t v = w4[i];
-                const uint32_t ib = and_or(v * (4u * REP), 0xffu * 4u * REP, lut_lane);
-                const uint32_t ig = and_or((v >> 8) * (4u * REP), 0xffu * 4u * REP, lut_lane);
-                const uint32_t ir = and_or((v >> 16) * (4u * REP), 0xffu * 4u * REP, lut_lane);
-                p[i * CH + 0] = *reinterpret_cast<const float*>(sTb + ib);
-                p[i * CH + 1] = *reinterpret_cast<const float*>(sTb + ig);
-                p[i * CH + 2] = *reinterpret_cast<const float*>(sTb + ir);
+                p[0 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6504));
+                p[1 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6514));
+                p[2 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6524));
                 if (CH == 4) {
                     // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
                     const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
-                    p[i * CH + 0] = __fmul_rn(p[i * CH + 0], af);
-                    p[i * CH + 1] = __fmul_rn(p[i * CH + 1], af);
-                    p[i * CH + 2] = __fmul_rn(p[i * CH + 2], af);
-                    p[i * CH + CH - 1] = af;
+                    p[0 * 4 + i] = __fmul_rn(p[0 * 4 + i], af);
+                    p[1 * 4 + i] = __fmul_rn(p[1 * 4 + i], af);
+                    p[2 * 4 + i] = __fmul_rn(p[2 * 4 + i], af);
+                    p[(CH - 1) * 4 + i] = af;
                 }
             }
-            // ---- ring accumulate
-            if (F2) {
+            // ---- ring accumulate (packed fp32 FMA: two IEEE fmaf per instruction)
 #pragma unroll
-                for (int s = 0; s < AV; ++s) {
-                    const float2 w2 = *reinterpret_cast<const float2*>(rec + 2 * s);
+            for (int s = 0; s < AV; ++s) {
+                const float2 w2 = *reinterpret_cast<const float2*>(rec + 2 * s);
 #pragma unroll
-                    for (int k = 0; k < NV / 2; ++k) {
-                        const float2 r2 = __ffma2_rn(w2, make_float2(p[2 * k], p[2 * k + 1]), make_float2(acc[s][2 * k], acc[s][2 * k + 1]));
-                        acc[s][2 * k] = r2.x; acc[s][2 * k + 1] = r2.y;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int s = 0; s < AV; ++s) {
-                    const float w = __uint_as_float(rec[s]);
-#pragma unroll
-                    for (int k = 0; k < NV; ++k) acc[s][k] = __fmaf_rn(w, p[k], acc[s][k]);
+                for (int k = 0; k < NV / 2; ++k) {
+                    const float2 r2 = __ffma2_rn(w2, make_float2(p[2 * k], p[2 * k + 1]), make_float2(acc[s][2 * k], acc[s][2 * k + 1]));
+                    acc[s][2 * k] = r2.x; acc[s][2 * k + 1] = r2.y;
                 }
             }
             return rec[PL::kDone];
         };
-        // The PF ring positions are PF copies of do_row; the (much larger) completion code below exists once:
-        // a row that completes output rows breaks out of the switch, and the loop re-enters at the next ring position.
+        // The 2*PF ring positions are copies of do_row; the completion code below exists once: a row that completes
+        // output rows breaks out of the switch, and the loop re-enters at the next ring position.
         while (r < rows_here) {
             uint32_t dn = 0;
             switch (ring_pos) {
@@ -396,34 +402,39 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             for (int e = 0; e < ndone; ++e) {
                 const int y = (int)(dn >> 8) + e;
                 if (y >= bd.Y0 && y < bd.Y1) {                        // else: halo row of a neighbouring band
-                    float* pb = sPart + (nrow & 1) * (CH * SH) * NT;
-                    const int plane0 = (int)(sMeta[t] >> 24);
+                    const int par = nrow & 1;
+                    float* pb = sPart + par * (CH * SH) * NT;
+                    {
+                        int poff = (int)(sMeta[t] >> 24) * NT + t;    // plane (X mod SH) of this thread's first output
 #pragma unroll
-                    for (int q = 0; q < SH; ++q) {
-                        int plane = plane0 + q; if (plane >= SH) plane -= SH;
-                        const float h0 = sHw[(q * 4 + 0) * NT + t], h1 = sHw[(q * 4 + 1) * NT + t];
-                        const float h2 = sHw[(q * 4 + 2) * NT + t], h3 = sHw[(q * 4 + 3) * NT + t];
+                        for (int q = 0; q < SH; ++q) {
+                            const float h0 = sHwT[(q * 4 + 0) * kHwStep], h1 = sHwT[(q * 4 + 1) * kHwStep];
+                            const float h2 = sHwT[(q * 4 + 2) * kHwStep], h3 = sHwT[(q * 4 + 3) * kHwStep];
 #pragma unroll
-                        for (int c = 0; c < CH; ++c) {
-                            float ps = __fmaf_rn(h0, acc[0][0 * CH + c], 0.0f);
-                            ps = __fmaf_rn(h1, acc[0][1 * CH + c], ps);
-                            ps = __fmaf_rn(h2, acc[0][2 * CH + c], ps);
-                            ps = __fmaf_rn(h3, acc[0][3 * CH + c], ps);
-                            pb[(c * SH + plane) * NT + t] = ps;
+                            for (int c = 0; c < CH; ++c) {
+                                float ps = __fmaf_rn(h0, acc[0][c * 4 + 0], 0.0f);
+                                ps = __fmaf_rn(h1, acc[0][c * 4 + 1], ps);
+                                ps = __fmaf_rn(h2, acc[0][c * 4 + 2], ps);
+                                ps = __fmaf_rn(h3, acc[0][c * 4 + 3], ps);
+                                pb[c * SH * NT + poff] = ps;
+                            }
+                            poff += NT;
+                            if (poff >= SH * NT) poff -= SH * NT;
                         }
                     }
                     __syncthreads();
-                    const int u = alternate ? t - (nrow & 1) * (NT / 2) : t;
-                    if (u >= 0 && u < NX) {
+                    const int u = alternate ? t - par * (NT / 2) : t;
+                    if (u >= 0 && u < NX && (!alternate || my_half == par)) {
                         const uint32_t meta = sMeta[u];
                         const int X = sd.X0 + u;
                         const int plane = X % SH;
                         const int tg0 = meta & 0xfffu, ng = (meta >> 12) & 0xfffu;
+                        const float* pr = pb + plane * NT + tg0;
                         float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
                         for (int g = 0; g < ng; ++g) {
 #pragma unroll
-                            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], pb[(c * SH + plane) * NT + tg0 + g]);
+                            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], pr[c * SH * NT + g]);
                         }
                         uint8_t* dst = job.out + (size_t)y * job.out_stride + (size_t)X * 4;
                         *reinterpret_cast<uint32_t*>(dst) = finish_pixel(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, job, tb, dst);

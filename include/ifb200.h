@@ -124,10 +124,7 @@ void ifb200_batch_destroy(ifb200_batch* b);
 enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
     IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size: 128 or 256 (strip = 4x that many columns) */
-    IFB200_OPT_MIN_CTAS = 3,           /* split images into row bands until the grid has this many CTAs   */
-    IFB200_OPT_KERNEL_VARIANT = 4      /* A/B timing of fused-kernel variants (bit0: scalar FFMA instead of
-                                          FFMA2, bit1: unreplicated LUT); variants missing from the build
-                                          silently fall back to the generic pair; results are bit-identical */
+    IFB200_OPT_MIN_CTAS = 3            /* split images into row bands until the grid has this many CTAs   */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */
