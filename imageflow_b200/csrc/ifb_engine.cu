@@ -497,12 +497,26 @@ void color_matrix_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t 
     CUDA_OK(cudaFreeAsync(dm, st));
 }
 
-// per-thread context for the host-buffer drop-in calls
+// per-thread context for the host-buffer drop-in calls: a small pipeline of streams, each with its own
+// device staging for one input window and one destination rect, so that the upload of call i+1 overlaps the
+// kernel of call i and the download of call i-1 when several calls are issued through the batched entry point.
+constexpr int kHostSlots = 3;
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
+};
 struct HostCtx {
     ifb200_batch* batch = nullptr;
-    uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
+    HostSlot slot[kHostSlots];
     ~HostCtx() {
-        if (batch) { cudaSetDevice(batch->device); if (d_in) cudaFree(d_in); if (d_cv) cudaFree(d_cv); delete batch; }
+        if (!batch) return;
+        cudaSetDevice(batch->device);
+        for (auto& s : slot) {
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_cv) cudaFree(s.d_cv);
+        }
+        delete batch;
     }
 };
 thread_local HostCtx t_ctx;
@@ -529,12 +543,14 @@ HostCtx& host_ctx() {
         int dev = 0;
         if (const char* s = getenv("IFB200_DEVICE")) dev = atoi(s);
         t_ctx.batch = create_batch(dev);
+        for (auto& sl : t_ctx.slot) CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     }
     return t_ctx;
 }
 
-void ensure(uint8_t*& p, size_t& cap, size_t need) {
+void ensure(uint8_t*& p, size_t& cap, size_t need, cudaStream_t st) {
     if (cap >= need) return;
+    CUDA_OK(cudaStreamSynchronize(st));           // nothing may still be using the old buffer
     if (p) CUDA_OK(cudaFree(p));
     p = nullptr; cap = 0;
     CUDA_OK(cudaMalloc(&p, need));
@@ -650,31 +666,54 @@ uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b) { return b ? b->fused_jo
 uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b) { return b ? b->generic_jobs : 0; }
 
 // ---- drop-in calls with HOST buffers -----------------------------------------------------------
+namespace {
+// one host-buffer job on pipeline slot `sl` (asynchronous; caller synchronises the slot's stream)
+void host_job_async(HostCtx& c, HostSlot& sl, const ifb200_resample_desc& d) {
+    ifb200_batch* b = c.batch;
+    cudaStream_t st = sl.stream;
+    // device images: input window with a 64-byte padded pitch; destination rect only
+    const size_t in_pitch = ((size_t)d.in_w * 4 + 63) / 64 * 64;
+    const size_t cv_pitch = ((size_t)d.w * 4 + 63) / 64 * 64;
+    ensure(sl.d_in, sl.cap_in, in_pitch * d.in_h, st);
+    ensure(sl.d_cv, sl.cap_cv, cv_pitch * d.h, st);
+    CUDA_OK(cudaMemcpy2DAsync(sl.d_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h, cudaMemcpyHostToDevice, st));
+    uint8_t* host_rect = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
+    if (d.compose == IFB200_BLEND_WITH_SELF)        // the composite reads the canvas (scaling.rs:271-283)
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h, cudaMemcpyHostToDevice, st));
+    ifb200_resample_desc dd = d;
+    dd.in = sl.d_in; dd.in_stride = (uint32_t)in_pitch;
+    dd.canvas = sl.d_cv; dd.cv_w = d.w; dd.cv_h = d.h; dd.cv_stride = (uint32_t)cv_pitch; dd.x = 0; dd.y = 0;
+    enqueue_locked(b, &dd, 1, st);
+    CUDA_OK(cudaMemcpy2DAsync(host_rect, d.cv_stride, sl.d_cv, cv_pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, st));
+}
+}  // namespace
+
 int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!desc) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null descriptor");
         validate(*desc);
         HostCtx& c = host_ctx();
-        ifb200_batch* b = c.batch;
-        std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
-        cudaStream_t st = b->own_stream;
-        const ifb200_resample_desc& d = *desc;
-        // device images: input window with a 16-byte aligned pitch; destination rect only
-        const size_t in_pitch = ((size_t)d.in_w * 4 + 63) / 64 * 64;
-        const size_t cv_pitch = ((size_t)d.w * 4 + 63) / 64 * 64;
-        ensure(c.d_in, c.cap_in, in_pitch * d.in_h);
-        ensure(c.d_cv, c.cap_cv, cv_pitch * d.h);
-        CUDA_OK(cudaMemcpy2DAsync(c.d_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h, cudaMemcpyHostToDevice, st));
-        uint8_t* host_rect = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
-        if (d.compose == IFB200_BLEND_WITH_SELF)        // the composite reads the canvas (scaling.rs:271-283)
-            CUDA_OK(cudaMemcpy2DAsync(c.d_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h, cudaMemcpyHostToDevice, st));
-        ifb200_resample_desc dd = d;
-        dd.in = c.d_in; dd.in_stride = (uint32_t)in_pitch;
-        dd.canvas = c.d_cv; dd.cv_w = d.w; dd.cv_h = d.h; dd.cv_stride = (uint32_t)cv_pitch; dd.x = 0; dd.y = 0;
-        enqueue_locked(b, &dd, 1, st);
-        CUDA_OK(cudaMemcpy2DAsync(host_rect, d.cv_stride, c.d_cv, cv_pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaStreamSynchronize(st));
+        std::lock_guard<std::mutex> lk(c.batch->mu);
+        CUDA_OK(cudaSetDevice(c.batch->device));
+        host_job_async(c, c.slot[0], *desc);
+        CUDA_OK(cudaStreamSynchronize(c.slot[0].stream));
+    });
+}
+
+int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!descs && n) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null descriptor array");
+        for (size_t i = 0; i < n; ++i) validate(descs[i]);      // all-or-nothing argument errors, before any pixel moves
+        HostCtx& c = host_ctx();
+        std::lock_guard<std::mutex> lk(c.batch->mu);
+        CUDA_OK(cudaSetDevice(c.batch->device));
+        try {
+            for (size_t i = 0; i < n; ++i) host_job_async(c, c.slot[i % kHostSlots], descs[i]);
+        } catch (...) {
+            for (auto& sl : c.slot) cudaStreamSynchronize(sl.stream);
+            throw;
+        }
+        for (auto& sl : c.slot) CUDA_OK(cudaStreamSynchronize(sl.stream));
     });
 }
 
@@ -687,12 +726,13 @@ int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stri
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
         CUDA_OK(cudaSetDevice(b->device));
-        cudaStream_t st = b->own_stream;
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
-        ensure(c.d_cv, c.cap_cv, pitch * h);
-        CUDA_OK(cudaMemcpy2DAsync(c.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
-        color_matrix_locked(b, c.d_cv, w, h, (uint32_t)pitch, m, st);
-        CUDA_OK(cudaMemcpy2DAsync(px, stride, c.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
+        ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        color_matrix_locked(b, sl.d_cv, w, h, (uint32_t)pitch, m, st);
+        CUDA_OK(cudaMemcpy2DAsync(px, stride, sl.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
     });
 }

@@ -130,6 +130,18 @@ def scale_and_render(inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRend
     _check(lib().ifb200_scale_and_render(C.byref(d), buf, 512), buf)
 
 
+def scale_and_render_many(jobs) -> None:
+    """n independent scale_and_render calls with HOST bitmaps, pipelined inside the library
+    (jobs: iterable of (input, canvas, params[, color_matrix]))."""
+    jobs = list(jobs)
+    arr = (ResampleDesc * len(jobs))()
+    keep = []
+    for i, j in enumerate(jobs):
+        arr[i] = _desc(j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_scale_and_render_many(arr, len(jobs), buf, 512), buf)
+
+
 def window_bgra32_apply_color_matrix(window: BitmapWindow, m) -> None:
     """graphics/color_matrix.rs:5-28, in place on a HOST window; m is [[f32;5];5]."""
     mm = np.ascontiguousarray(m, np.float32).reshape(25)

@@ -102,6 +102,10 @@ int  ifb200_color_filter_matrix(int which, float p, float out[25]);
  * Replaces the bodies of scaling.rs:93-251 (resize_to_canvas / resize_with_matte /
  * resize_and_composite).  err (may be NULL) receives a NUL-terminated message on failure. */
 int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t err_cap);
+/* The same for n independent calls (e.g. the DrawImageExact nodes of one graph, or export_4_sizes): identical
+ * results, but uploads, kernels and downloads of consecutive jobs are pipelined on several CUDA streams.
+ * Jobs must not alias each other's canvases.  Argument errors are reported before any job runs. */
+int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, char* err, size_t err_cap);
 /* Replaces color_matrix.rs:5-28 (in place). */
 int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float m[25],
                               char* err, size_t err_cap);

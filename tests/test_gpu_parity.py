@@ -237,3 +237,90 @@ def test_batch_of_mixed_jobs(ifb, torch_mod):
         assert util.diff_stats(tc.cpu().numpy(), exp)[0] == 0
     assert b.fused_jobs + b.generic_jobs == 12
     b.close()
+
+
+def test_host_many_pipelined_matches_oracle(ifb):
+    """ifb200_scale_and_render_many: several host-buffer jobs of different geometry, pipelined on 3 streams."""
+    jobs, exps = [], []
+    for i, (iw, ih, ow, oh, comp, alpha) in enumerate([(640, 480, 200, 150, 0, False), (800, 600, 400, 300, 1, True), (1024, 768, 256, 192, 2, True),
+                                                        (333, 222, 111, 74, 0, True), (1280, 720, 320, 180, 0, False), (64, 64, 128, 128, 0, True),
+                                                        (1920, 1080, 512, 288, 1, True)]):
+        inp = util.padded(util.noise(iw, ih, seed=300 + i, alpha_mode="mixed" if alpha else "opaque"))
+        cv0 = util.noise(ow, oh, seed=400 + i, alpha_mode="mixed")
+        exp = cv0.copy()
+        oracle.scale_and_render(inp, exp, filter=2, alpha_meaningful=alpha, compose=comp, matte=(10, 20, 30, 255))
+        got = util.padded(cv0)
+        jobs.append((ifb.BitmapWindow.from_numpy(inp, alpha_meaningful=alpha),
+                     ifb.BitmapWindow.from_numpy(got, compose=ifb.BitmapCompositing(comp), matte_bgra=(10, 20, 30, 255)),
+                     ifb.ScaleAndRenderParams(w=ow, h=oh)))
+        exps.append((got, exp))
+    ifb.scale_and_render_many(jobs)
+    for got, exp in exps:
+        assert util.diff_stats(got, exp)[0] == 0
+    # argument errors are reported before anything runs
+    bad = jobs + [(jobs[0][0], jobs[0][1], ifb.ScaleAndRenderParams(x=9999, w=10, h=10))]
+    with pytest.raises(ifb.FlowError) as e:
+        ifb.scale_and_render_many(bad)
+    assert e.value.kind == ifb.ErrorKind.InvalidArgument
+
+
+FULL = [
+    # BASELINE.json configs at full size: (name, in_w, in_h, out_w, out_h, filter, alpha, compose, sharpen, colour matrix, n images, n oracle images)
+    ("c2_robidoux", 3840, 2160, 512, 512, 2, False, 0, 0.0, None, 6, 2),
+    ("c2_lanczos3", 3840, 2160, 512, 512, 6, False, 0, 0.0, None, 4, 1),
+    ("c2_robidoux_alpha", 3840, 2160, 512, 512, 2, True, 0, 0.0, None, 4, 1),
+    ("c3_8k_sharpen", 7680, 4320, 1920, 1080, 2, False, 0, 50.0, None, 2, 1),
+    ("c4_up_sepia_over", 1920, 1080, 3840, 2160, 14, True, 1, 0.0, 0, 2, 1),
+]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=lambda c: c[0])
+def test_full_size_configs(ifb, torch_mod, cfg):
+    """BASELINE.json's shapes at full size: (1) the fused kernel and the generic two-kernel path -- independent code
+    paths -- must agree bit for bit on every image (a checksum of checksums over the batch), (2) the first images are
+    also checked against the CPU oracle, (3) opaque inputs give A = 255 everywhere."""
+    torch = torch_mod
+    from imageflow_b200 import synth
+    name, iw, ih, ow, oh, flt, alpha, comp, sharpen, cmw, n, n_or = cfg
+    cm = ifb.color_filter_matrix(cmw) if cmw is not None else None
+    ins = [synth.noise_torch(iw, ih, seed=500 + i, alpha_mode="mixed" if alpha else "opaque") for i in range(n)]
+    cv0 = [synth.noise_torch(ow, oh, seed=600 + i, alpha_mode="mixed") for i in range(n)]
+    outs = {}
+    for force in (0, 1):
+        b = ifb.Batch(0)
+        b.set_option(ifb.Batch.OPT_FORCE_GENERIC, force)
+        cvs = [c.clone() for c in cv0]
+        p = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=sharpen, interpolation_filter=ifb.Filter(flt))
+        b.scale_and_render_many([(ifb.BitmapWindow.from_torch(ins[i], alpha_meaningful=alpha),
+                                  ifb.BitmapWindow.from_torch(cvs[i], compose=ifb.BitmapCompositing(comp)), p, cm) for i in range(n)],
+                                stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs[force] = cvs
+        if force == 0 and ow <= iw:
+            assert b.fused_jobs == n, "down-scales of the benchmark shapes must take the fused kernel"
+        b.close()
+    sums = [[int(c.to(torch.int64).sum().item()) for c in outs[f]] for f in (0, 1)]
+    assert sums[0] == sums[1]
+    for i in range(n):
+        assert torch.equal(outs[0][i], outs[1][i])
+        if not alpha and comp == 0:
+            assert bool((outs[0][i][..., 3] == 255).all())
+    for i in range(n_or):
+        exp = cv0[i].cpu().numpy().copy()
+        oracle.scale_and_render(ins[i].cpu().numpy(), exp, filter=flt, sharpen=sharpen, alpha_meaningful=alpha, compose=comp, color_matrix=cm)
+        assert util.diff_stats(outs[0][i].cpu().numpy(), exp)[0] == 0
+
+
+def test_flat_colour_is_preserved_at_full_size(ifb, torch_mod):
+    """size-independent property: a constant opaque frame stays that colour exactly (weights sum to 1 within the LUT's reach)."""
+    torch = torch_mod
+    inp = torch.empty((2160, 3840, 4), dtype=torch.uint8, device="cuda")
+    inp[...] = torch.tensor([37, 150, 251, 255], dtype=torch.uint8, device="cuda")
+    out = torch.zeros((512, 512, 4), dtype=torch.uint8, device="cuda")
+    b = ifb.Batch(0)
+    b.scale_and_render_many([(ifb.BitmapWindow.from_torch(inp), ifb.BitmapWindow.from_torch(out), ifb.ScaleAndRenderParams(w=512, h=512))],
+                            stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    d = (out.to(torch.int16) - torch.tensor([37, 150, 251, 255], dtype=torch.int16, device="cuda")).abs().max().item()
+    assert d <= 1
+    b.close()
