@@ -74,11 +74,15 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def mark(self):
+        """samples taken from now on belong to the timed region"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -99,7 +103,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in self.rows[max(0, self.first - 1):]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 8:
                 continue
@@ -132,9 +136,14 @@ def cpu_oracle_run(wl, n_images, threads, content, alpha, keep_outputs=False):
     ins, outs, descs = [], [], (oracle.Desc * n_images)()
     cm = oracle.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
     keep = []
+    distinct = min(n_images, max(2, min(16, n_images)))      # generating frames in numpy is slow: cycle through a few
     for i in range(n_images):
-        a = synth.noise_np(iw, ih, seed=i, alpha_mode="mixed" if alpha else "opaque") if content == "noise" else synth.gradient_np(iw, ih)
-        c = synth.noise_np(ow, oh, seed=100000 + i, alpha_mode="mixed") if wl["compose"] == 1 else np.zeros((oh, ow, 4), np.uint8)
+        if i < distinct:
+            a = synth.noise_np(iw, ih, seed=i, alpha_mode="mixed" if alpha else "opaque") if content == "noise" else synth.gradient_np(iw, ih)
+        else:
+            a = ins[i % distinct]
+        c = synth.noise_np(ow, oh, seed=100000 + i, alpha_mode="mixed") if (wl["compose"] == 1 and i < distinct) else \
+            (outs[i % distinct].copy() if wl["compose"] == 1 else np.zeros((oh, ow, 4), np.uint8))
         ins.append(a); outs.append(c)
         descs[i] = oracle.make_desc(a, c, filter=wl["filter"], sharpen=wl["sharpen"], linear=True, alpha_meaningful=bool(alpha),
                                     compose=wl["compose"], color_matrix=cm, keep=keep)
@@ -156,10 +165,10 @@ def run_reference(args, wl, rank, world):
     alpha = wl["alpha"] if args.alpha < 0 else args.alpha
     iw, ih = wl["in_wh"]
     # size the bounded sample: one probe image per thread, then scale to ~cpu_seconds / (steps+warmup)
-    dt, _ = cpu_oracle_run(wl, threads, threads, args.content, alpha)
-    per_img = dt / threads * threads / max(threads, 1)
-    budget = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    n = int(max(threads, min(256, round(budget / max(dt, 1e-3) * threads))))
+    cpu_oracle_run(wl, threads, threads, args.content, alpha)                     # warm-up (tables, page faults)
+    dt, _ = cpu_oracle_run(wl, 2 * threads, threads, args.content, alpha)
+    budget = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
+    n = int(max(2 * threads, min(4096, round(budget / max(dt, 1e-3) * 2 * threads))))
     for _ in range(args.warmup):
         cpu_oracle_run(wl, n, threads, args.content, alpha)
     t = 0.0
@@ -250,6 +259,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started before the warm-up so that nvidia-smi's start-up cost is not in the timed region
     t_w = time.perf_counter()
     n_w = 0
     while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:     # >= 3 steps and >= 0.5 s: clocks ramp up
@@ -259,9 +271,8 @@ def main():
             torch.cuda.synchronize()
     barrier()
     launches0 = batch.kernel_launches
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -323,8 +334,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle
         threads = oracle.lib().ifo_max_threads()
-        dt, _ = cpu_oracle_run(wl, threads, threads, args.content, alpha)
-        n = int(max(threads, min(512, round(args.cpu_seconds / max(dt, 1e-3) * threads))))
+        cpu_oracle_run(wl, threads, threads, args.content, alpha)                 # warm-up (tables, page faults)
+        dt, _ = cpu_oracle_run(wl, 2 * threads, threads, args.content, alpha)
+        n = int(max(2 * threads, min(4096, round(args.cpu_seconds / max(dt, 1e-3) * 2 * threads))))
         dt, _ = cpu_oracle_run(wl, n, threads, args.content, alpha)
         cpu_baseline = {"value": n * iw * ih / 1e6 / dt, "unit": "Mpx/s", "cores": threads, "kind": "port",
                         "sample": f"{n} frames of {iw}x{ih} ({dt:.1f} s), oracle/ifb_oracle.c OpenMP over images"}
