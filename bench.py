@@ -118,6 +118,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler instead)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def algorithmic_bytes_per_image(wl):
     iw, ih = wl["in_wh"]; ow, oh = wl["out_wh"]
     b = iw * ih * 4 + ow * oh * 4                    # SURVEY.md §8(d): read input once + write output once
@@ -161,7 +169,7 @@ def run_reference(args, wl, rank, world):
         return
     import oracle
     oracle.build()
-    threads = oracle.lib().ifo_max_threads()
+    threads = host_threads()
     alpha = wl["alpha"] if args.alpha < 0 else args.alpha
     iw, ih = wl["in_wh"]
     # size the bounded sample: one probe image per thread, then scale to ~cpu_seconds / (steps+warmup)
@@ -333,7 +341,7 @@ def main():
         check = {"images": n_chk, "max_abs_delta_vs_oracle": mx}
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle
-        threads = oracle.lib().ifo_max_threads()
+        threads = host_threads()
         cpu_oracle_run(wl, threads, threads, args.content, alpha)                 # warm-up (tables, page faults)
         dt, _ = cpu_oracle_run(wl, 2 * threads, threads, args.content, alpha)
         n = int(max(2 * threads, min(4096, round(args.cpu_seconds / max(dt, 1e-3) * 2 * threads))))
