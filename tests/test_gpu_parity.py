@@ -324,3 +324,18 @@ def test_flat_colour_is_preserved_at_full_size(ifb, torch_mod):
     d = (out.to(torch.int16) - torch.tensor([37, 150, 251, 255], dtype=torch.int16, device="cuda")).abs().max().item()
     assert d <= 1
     b.close()
+
+
+def test_mixed_thumbnail_workload_runner(ifb):
+    """configs[4] at toy scale: export_4_sizes cascades of mixed frame sizes, every step checked against the oracle."""
+    import json
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "mixed_workload.py"), "--images", "40", "--check", "6"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["parity_check"] == {"chains": 6, "max_abs_delta_vs_oracle": 0}
+    assert d["resamples"] > 40 and d["fused_jobs_rank0"] + d["generic_jobs_rank0"] == d["resamples"]

@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: the mixed thumbnail workload (export_4_sizes cascade, imageflow_tool self_test.rs:184-198)
+on N GPUs of one box.  Images: long edge log-uniform 256..7680 (seeded), aspect from {1:1,4:3,3:2,16:9}; every image
+is constrained within 1600, the result within 1200 and 800, and the 1200 result within 400 (no up-scaling; nodes that
+would not change the size delete themselves).  Chains are binned over ranks by greedy LPT on input pixels; there is no
+collective on the data path.  Prints one JSON line (rank 0).
+
+  python tools/mixed_workload.py --images 2000            # 1 GPU
+  python -m torch.distributed.run --nproc-per-node 8 ... tools/mixed_workload.py --images 10000
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make_images(n, seed=1234):
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n):
+        le = int(round(256 * (7680 / 256) ** rng.random()))
+        aw, ah = rng.choice([(1, 1), (4, 3), (3, 2), (16, 9)])
+        w, h = le, max(16, le * ah // aw)
+        if rng.random() < 0.25:
+            w, h = h, w                      # some portrait frames
+        out.append((w // 4 * 4 if w >= 8 else w, h))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=2000)
+    ap.add_argument("--chunk-gb", type=float, default=48.0)
+    ap.add_argument("--check", type=int, default=2, help="chains checked against the CPU oracle on rank 0")
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import imageflow_b200 as ifb
+    from imageflow_b200 import sharding, synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    imgs = make_images(args.images)
+    chains = [sharding.export_4_sizes_chain(w, h) for (w, h) in imgs]
+    costs = [sum(a[0] * a[1] for a, _ in ch) or 1 for ch in chains]
+    bins = sharding.shard_lpt(costs, world)
+    mine = bins[rank]
+    batch = ifb.Batch(local)
+    stream = torch.cuda.current_stream().cuda_stream
+    px_done = 0
+    jobs_done = 0
+    t_total = 0.0
+    checked = None
+    # process my chains in chunks that fit in memory
+    i = 0
+    while i < len(mine):
+        chunk, nbytes = [], 0
+        while i < len(mine) and (not chunk or nbytes < args.chunk_gb * 1e9):
+            idx = mine[i]; w, h = imgs[idx]
+            nbytes += w * h * 4 * 1.6
+            chunk.append(idx); i += 1
+        srcs = {idx: synth.noise_torch(imgs[idx][0], imgs[idx][1], seed=idx, device=dev) for idx in chunk}
+        # materialise every size of every chain; a chain's later steps read earlier results, so run level by level
+        results = {}
+        levels = [[], [], []]                # level 0: src->1600 ; level 1: 1600->1200, 1600->800 ; level 2: 1200->400
+        for idx in chunk:
+            for (src, dst) in chains[idx]:
+                key_src = (idx, src); key_dst = (idx, dst)
+                if key_dst not in results:
+                    results[key_dst] = torch.empty((dst[1], dst[0], 4), dtype=torch.uint8, device=dev)
+                lvl = 0 if src == imgs[idx] else (2 if dst[0] <= 400 and dst[1] <= 400 and src != imgs[idx] and max(src) <= 1200 else 1)
+                levels[lvl].append((idx, src, dst))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for lvl in levels:
+            if not lvl:
+                continue
+            jobs = []
+            for (idx, src, dst) in lvl:
+                tin = srcs[idx] if src == imgs[idx] else results[(idx, src)]
+                jobs.append((ifb.BitmapWindow.from_torch(tin), ifb.BitmapWindow.from_torch(results[(idx, dst)]),
+                             ifb.ScaleAndRenderParams(w=dst[0], h=dst[1], interpolation_filter=ifb.Filter.Robidoux)))
+                px_done += src[0] * src[1]
+            batch.scale_and_render_many(jobs, stream=stream)     # same stream: level k+1 reads what level k wrote
+            jobs_done += len(jobs)
+        e1.record()
+        torch.cuda.synchronize()
+        t_total += e0.elapsed_time(e1)
+        if rank == 0 and checked is None and args.check:
+            import oracle
+            mx = 0
+            for idx in chunk[:args.check]:
+                cur = {imgs[idx]: srcs[idx].cpu().numpy()}
+                for (src, dst) in chains[idx]:
+                    out = np.zeros((dst[1], dst[0], 4), np.uint8)
+                    oracle.scale_and_render(cur[src], out, filter=2)
+                    cur[dst] = out
+                    mx = max(mx, int(np.abs(out.astype(np.int16) - results[(idx, dst)].cpu().numpy().astype(np.int16)).max()))
+            checked = {"chains": args.check, "max_abs_delta_vs_oracle": mx}
+        del srcs, results
+        torch.cuda.empty_cache()
+    tot_px, max_ms = sharding.aggregate(px_done, t_total, device=dev)
+    tot_jobs, _ = sharding.aggregate(jobs_done, 0.0, device=dev)
+    if rank == 0:
+        print(json.dumps({"workload": "c5_mixed_thumbnails_export_4_sizes", "images": args.images, "n_gpus": world, "resamples": int(tot_jobs),
+                          "input_mpx": tot_px / 1e6, "ms": max_ms, "value": tot_px / 1e6 / (max_ms / 1e3), "unit": "Mpx/s (input pixels of every resample)",
+                          "lpt_imbalance": sharding.lpt_imbalance(costs, bins), "fused_jobs_rank0": batch.fused_jobs, "generic_jobs_rank0": batch.generic_jobs,
+                          "parity_check": checked}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
