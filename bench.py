@@ -312,7 +312,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_min": float(np.min(step_ms)),
                 "kernel_ms_all": [round(x, 4) for x in step_ms], "algorithmic_bytes_per_launch": alg,
-                "fused_jobs": batch.fused_jobs, "generic_jobs": batch.generic_jobs}
+                "fused_jobs": batch.fused_jobs, "generic_jobs": batch.generic_jobs, "tile_jobs": batch.tile_jobs}
     tfile = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tfile):
         try:

@@ -15,7 +15,7 @@ SYMBOLS = [
     "ifb200_scale_and_render", "ifb200_scale_and_render_many", "ifb200_color_matrix_bgra8",
     "ifb200_batch_create", "ifb200_batch_enqueue", "ifb200_batch_color_matrix", "ifb200_batch_sync",
     "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches",
-    "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs",
+    "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs",
 ]
 
 
@@ -74,7 +74,7 @@ def lib() -> C.CDLL:
     L.ifb200_batch_destroy.restype = None
     L.ifb200_batch_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     L.ifb200_batch_set_option.restype = C.c_int
-    for f in ("ifb200_batch_kernel_launches", "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs"):
+    for f in ("ifb200_batch_kernel_launches", "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs"):
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = C.c_uint64
     _lib = L

@@ -104,6 +104,8 @@ struct Plan {
     uint32_t in_w, in_h, out_w, out_h;
     ifb::AxisWeights wv, wh;
     AxisOnDev dv, dh;
+    // tile kernel (small windows: up-scales, 1:1, mild down-scales)
+    bool tile_ok = false; TilePlanDev tile{};
     // fused
     bool fused_ok = false; std::string fused_reason;
     int av = 0, sh = 0;
@@ -126,7 +128,7 @@ int pick(const int* choices, int n, int need) {
 void build_fused_v(Plan& p) {
     const auto& a = p.wv;
     if (!monotone(a) || !monotone(p.wh)) { p.fused_reason = "non-monotone windows"; return; }
-    if (p.in_w % 4 != 0 || p.in_w < 4) { p.fused_reason = "in_w not a multiple of 4"; return; }
+    if (p.in_w < 4) { p.fused_reason = "in_w < 4"; return; }
     // ring depth: smallest A with left[y+A] > right[y] for all y
     int need = 1;
     for (;; ++need) {
@@ -138,7 +140,7 @@ void build_fused_v(Plan& p) {
     p.av = pick(kAvChoices, (int)(sizeof kAvChoices / sizeof *kAvChoices), need);
     if (!p.av) { p.fused_reason = "vertical ring depth " + std::to_string(need) + " > 6"; return; }
     // horizontal slots per aligned group of 4 source columns
-    std::vector<int> cnt(p.in_w / 4 + 1, 0);
+    std::vector<int> cnt(p.in_w / 4 + 2, 0);
     for (uint32_t X = 0; X < p.wh.out_size; ++X)
         for (uint32_t g = p.wh.left[X] / 4; g <= p.wh.right[X] / 4; ++g) cnt[g]++;
     int hneed = *std::max_element(cnt.begin(), cnt.end());
@@ -153,6 +155,26 @@ void build_fused_v(Plan& p) {
     }
     p.vdone_host = std::move(vdone);
     p.fused_ok = true;
+}
+
+// tile kernel: 64 x 16 output pixels per CTA; usable when the source extent of every tile fits in shared memory
+void build_tile(Plan& p) {
+    if (!monotone(p.wv) || !monotone(p.wh)) return;
+    TilePlanDev t{};
+    t.in_w = p.in_w; t.in_h = p.in_h; t.out_w = p.out_w; t.out_h = p.out_h;
+    t.tow = 64; t.toh = 16;
+    t.tiles_x = (int)((p.out_w + t.tow - 1) / t.tow); t.tiles_y = (int)((p.out_h + t.toh - 1) / t.toh);
+    for (int tx = 0; tx < t.tiles_x; ++tx) {
+        const uint32_t X0 = tx * t.tow, X1 = std::min<uint32_t>(X0 + t.tow, p.out_w);
+        t.max_ic = std::max<int>(t.max_ic, (int)(p.wh.right[X1 - 1] - p.wh.left[X0] + 1));
+    }
+    for (int ty = 0; ty < t.tiles_y; ++ty) {
+        const uint32_t Y0 = ty * t.toh, Y1 = std::min<uint32_t>(Y0 + t.toh, p.out_h);
+        t.max_ir = std::max<int>(t.max_ir, (int)(p.wv.right[Y1 - 1] - p.wv.left[Y0] + 1));
+    }
+    const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
+    if (smem > 96 * 1024) return;                        // large windows: the ring kernel or the generic pair
+    p.tile = t; p.tile_ok = true;
 }
 
 // per-source-row program: weights of the open output rows, oldest first (float bits, duplicated pairs), then the completion word
@@ -304,7 +326,7 @@ struct ifb200_batch {
     // options
     bool force_generic = false; int nt = 256; int min_ctas = 296;
     // counters
-    uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0;
+    uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
 
     ~ifb200_batch() {
         cudaSetDevice(device);
@@ -343,6 +365,7 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
         p->dv.upload(p->wv); p->dh.upload(p->wh);
         build_fused_v(*p);
+        build_tile(*p);
         Plan& ref = *p;
         plans[k] = std::move(p);
         return ref;
@@ -395,18 +418,24 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     host_tables();
     CUDA_OK(cudaSetDevice(b->device));
     // group jobs by (plan, kernel class)
-    struct Group { Plan* plan; int ch; bool fused; std::vector<size_t> idx; };
+    struct Group { Plan* plan; int ch; int kind; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
         validate(descs[i]);
         Plan& p = b->plan_for(descs[i]);
         const ifb200_resample_desc& d = descs[i];
-        bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
+        // 16-byte row loads: aligned base and pitch, and the pitch must cover the last (possibly partial) group of 4 pixels
+        bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0) &&
+                     (d.in_stride >= ((uint64_t)d.in_w * 4 + 15) / 16 * 16);
         const int ch = d.alpha_meaningful ? 4 : 3;
         if (fused && !find_fused(p.av, p.sh, ch, b->nt)) fused = false;
+        // the ring kernel streams every source row once and wins whenever rows outnumber outputs (down-scales);
+        // for up-scales / 1:1 the tile kernel does less work per source pixel
+        const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || (p.out_h >= p.in_h && p.out_w >= p.in_w));
+        const int kind = prefer_tile ? 2 : (fused ? 1 : 0);
         Group* g = nullptr;
-        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.fused == fused) { g = &gg; break; }
-        if (!g) { groups.push_back(Group{&p, ch, fused, {}}); g = &groups.back(); }
+        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind) { g = &gg; break; }
+        if (!g) { groups.push_back(Group{&p, ch, kind, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
     // job array -> device (pinned staging, stream ordered)
@@ -428,7 +457,19 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         Plan& p = *g.plan;
         const JobDev* jobs = dj + gstart[gi];
         const size_t nj = g.idx.size();
-        if (g.fused) {
+        if (g.kind == 2) {
+            const TilePlanDev& t = p.tile;
+            const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
+            CUDA_OK(cudaFuncSetAttribute((const void*)fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            for (size_t off = 0; off < nj; off += 65535) {
+                const size_t cnt = std::min<size_t>(65535, nj - off);
+                dim3 grid((unsigned)(t.tiles_x * t.tiles_y), (unsigned)cnt);
+                fused_tile_kernel<<<grid, 256, smem, st>>>(jobs + off, b->tables, p.dv.view(), p.dh.view(), t);
+                CUDA_OK(cudaGetLastError());
+                b->launches++;
+            }
+            b->tile_jobs += nj;
+        } else if (g.kind == 1) {
             FusedVariantTables& ft = fused_tables(p, b->nt);
             int nb = 1;
             const size_t base = nj * ft.n_strips;
@@ -664,6 +705,7 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b) { return b ? b->launches : 0; }
 uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b) { return b ? b->fused_jobs : 0; }
 uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b) { return b ? b->generic_jobs : 0; }
+uint64_t ifb200_batch_tile_jobs(const ifb200_batch* b) { return b ? b->tile_jobs : 0; }
 
 // ---- drop-in calls with HOST buffers -----------------------------------------------------------
 namespace {

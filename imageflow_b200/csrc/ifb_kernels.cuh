@@ -179,6 +179,82 @@ __global__ void __launch_bounds__(128) hpass_generic_kernel(const JobDev* __rest
     *reinterpret_cast<uint32_t*>(dst) = finish_pixel(f0, f1, f2, f3, job, tb, dst);
 }
 
+// ---------------------------------------------------------------- tile kernel (up-scales, 1:1, mild down-scales)
+// One CTA = (job, TOW x TOH tile of output pixels).  The few source pixels the tile needs are converted once into a
+// shared-memory float4 tile, the V pass writes a second shared-memory tile [TOH][source columns], the H pass reads
+// it; nothing but the source pixels and the destination pixels touches HBM.  Same arithmetic, same bits as the
+// other kernels (V chain ascending; H per aligned group of 4 source columns, partials added ascending).
+struct TilePlanDev {
+    uint32_t in_w, in_h, out_w, out_h;
+    int tow, toh;               // tile size in output pixels
+    int tiles_x, tiles_y;
+    int max_ic, max_ir;         // largest source extent of any tile (shared-memory tile dimensions)
+};
+
+__global__ void __launch_bounds__(256) fused_tile_kernel(const JobDev* __restrict__ jobs, Tables tb, AxisDev av, AxisDev ah, TilePlanDev pl) {
+    extern __shared__ __align__(16) float4 tsm[];
+    float4* sIn = tsm;                                   // [max_ir][max_ic]
+    float4* sV = tsm + (size_t)pl.max_ir * pl.max_ic;    // [toh][max_ic]
+    const JobDev& job = jobs[blockIdx.y];
+    const int tx = blockIdx.x % pl.tiles_x, ty = blockIdx.x / pl.tiles_x;
+    const int X0 = tx * pl.tow, X1 = min(X0 + pl.tow, (int)pl.out_w);
+    const int Y0 = ty * pl.toh, Y1 = min(Y0 + pl.toh, (int)pl.out_h);
+    const int c0 = (int)__ldg(ah.left + X0), c1 = (int)__ldg(ah.right + (X1 - 1));
+    const int r0 = (int)__ldg(av.left + Y0), r1 = (int)__ldg(av.right + (Y1 - 1));
+    const int ic = c1 - c0 + 1, ir = r1 - r0 + 1, pitch = pl.max_ic;
+    const bool am = job.flags & JF_ALPHA;
+    const float* __restrict__ T = (job.flags & JF_LINEAR) ? tb.t_lin : tb.t_srgb;
+    // ---- A: source tile -> working floats
+    for (int i = threadIdx.x; i < ir * ic; i += blockDim.x) {
+        const int r = i / ic, c = i - r * ic;
+        const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(job.in + (size_t)(r0 + r) * job.in_stride) + (c0 + c));
+        float pb = __ldg(T + (px & 0xffu)), pg = __ldg(T + ((px >> 8) & 0xffu)), pr = __ldg(T + ((px >> 16) & 0xffu)), pa = 0.0f;
+        if (am) {
+            pa = __fmul_rn(__uint2float_rn(px >> 24), 1.0f / 255.0f);
+            pb = __fmul_rn(pb, pa); pg = __fmul_rn(pg, pa); pr = __fmul_rn(pr, pa);
+        }
+        sIn[r * pitch + c] = make_float4(pb, pg, pr, pa);
+    }
+    __syncthreads();
+    // ---- B: V pass for the tile's output rows over its source columns
+    const int nrows = Y1 - Y0;
+    for (int i = threadIdx.x; i < nrows * ic; i += blockDim.x) {
+        const int yl = i / ic, c = i - yl * ic;
+        const uint32_t l = __ldg(av.left + Y0 + yl), r = __ldg(av.right + Y0 + yl);
+        const float* __restrict__ w = av.w + __ldg(av.off + Y0 + yl);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (uint32_t j = l; j <= r; ++j) {
+            const float wt = __ldg(w + (j - l));
+            const float4 v = sIn[(int)(j - r0) * pitch + c];
+            a0 = __fmaf_rn(wt, v.x, a0); a1 = __fmaf_rn(wt, v.y, a1); a2 = __fmaf_rn(wt, v.z, a2); a3 = __fmaf_rn(wt, v.w, a3);
+        }
+        sV[yl * pitch + c] = make_float4(a0, a1, a2, a3);
+    }
+    __syncthreads();
+    // ---- C: H pass + store epilogue
+    const int ncols = X1 - X0;
+    for (int i = threadIdx.x; i < nrows * ncols; i += blockDim.x) {
+        const int yl = i / ncols, xl = i - yl * ncols;
+        const int X = X0 + xl;
+        const uint32_t l = __ldg(ah.left + X), r = __ldg(ah.right + X);
+        const float* __restrict__ w = ah.w + __ldg(ah.off + X);
+        const float4* __restrict__ row = sV + yl * pitch - c0;
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+        for (uint32_t g = l >> 2; g <= (r >> 2); ++g) {
+            const uint32_t k0 = max(g * 4u, l), k1 = min(g * 4u + 3u, r);
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+            for (uint32_t k = k0; k <= k1; ++k) {
+                const float wt = __ldg(w + (k - l));
+                const float4 v = row[k];
+                p0 = __fmaf_rn(wt, v.x, p0); p1 = __fmaf_rn(wt, v.y, p1); p2 = __fmaf_rn(wt, v.z, p2); p3 = __fmaf_rn(wt, v.w, p3);
+            }
+            f0 = __fadd_rn(f0, p0); f1 = __fadd_rn(f1, p1); f2 = __fadd_rn(f2, p2); f3 = __fadd_rn(f3, p3);
+        }
+        uint8_t* dst = job.out + (size_t)(Y0 + yl) * job.out_stride + (size_t)X * 4;
+        *reinterpret_cast<uint32_t*>(dst) = finish_pixel(f0, f1, f2, f3, job, tb, dst);
+    }
+}
+
 // ---------------------------------------------------------------- standalone colour matrix (color_matrix.rs:5-28)
 __global__ void __launch_bounds__(256) color_matrix_kernel(uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
                                                            const float* __restrict__ m20) {
@@ -297,7 +373,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     __syncthreads();
 
     int col = sd.k0 + 4 * t;
-    if (col > (int)pl.in_w - 4) col = (int)pl.in_w - 4;        // threads past the edge re-read the last group; their H weights are 0
+    // threads past the edge re-read the last aligned group (its tail may be row padding); their H weights are 0
+    if (col > (int)((pl.in_w - 1) & ~3u)) col = (int)((pl.in_w - 1) & ~3u);
     const size_t stride = job.in_stride;
     const uint8_t* __restrict__ pnext = job.in + (size_t)col * 4 + (size_t)bd.j0 * stride;
     int jnext = bd.j0;

@@ -244,6 +244,10 @@ class Batch:
     def generic_jobs(self) -> int:
         return lib().ifb200_batch_generic_jobs(self._h)
 
+    @property
+    def tile_jobs(self) -> int:
+        return lib().ifb200_batch_tile_jobs(self._h)
+
     def close(self) -> None:
         if self._h:
             lib().ifb200_batch_destroy(self._h)

@@ -134,6 +134,7 @@ int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */
 uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b);        /* jobs that took the fused kernel */
 uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b);      /* jobs that took the generic pair */
+uint64_t ifb200_batch_tile_jobs(const ifb200_batch* b);         /* jobs that took the tile kernel (up-scales, 1:1) */
 
 #ifdef __cplusplus
 }

@@ -235,7 +235,7 @@ def test_batch_of_mixed_jobs(ifb, torch_mod):
     torch.cuda.synchronize()
     for tc, exp in expects:
         assert util.diff_stats(tc.cpu().numpy(), exp)[0] == 0
-    assert b.fused_jobs + b.generic_jobs == 12
+    assert b.fused_jobs + b.generic_jobs + b.tile_jobs == 12
     b.close()
 
 
@@ -298,6 +298,8 @@ def test_full_size_configs(ifb, torch_mod, cfg):
         outs[force] = cvs
         if force == 0 and ow <= iw:
             assert b.fused_jobs == n, "down-scales of the benchmark shapes must take the fused kernel"
+        if force == 0 and ow > iw:
+            assert b.tile_jobs == n, "up-scales must take the tile kernel"
         b.close()
     sums = [[int(c.to(torch.int64).sum().item()) for c in outs[f]] for f in (0, 1)]
     assert sums[0] == sums[1]
@@ -338,4 +340,4 @@ def test_mixed_thumbnail_workload_runner(ifb):
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["parity_check"] == {"chains": 6, "max_abs_delta_vs_oracle": 0}
-    assert d["resamples"] > 40 and d["fused_jobs_rank0"] + d["generic_jobs_rank0"] == d["resamples"]
+    assert d["resamples"] > 40 and d["fused_jobs_rank0"] + d["generic_jobs_rank0"] + d["tile_jobs_rank0"] == d["resamples"]

@@ -28,7 +28,7 @@ def make_images(n, seed=1234):
         w, h = le, max(16, le * ah // aw)
         if rng.random() < 0.25:
             w, h = h, w                      # some portrait frames
-        out.append((w // 4 * 4 if w >= 8 else w, h))
+        out.append((w, h))
     return out
 
 
@@ -68,15 +68,22 @@ def main():
             idx = mine[i]; w, h = imgs[idx]
             nbytes += w * h * 4 * 1.6
             chunk.append(idx); i += 1
-        srcs = {idx: synth.noise_torch(imgs[idx][0], imgs[idx][1], seed=idx, device=dev) for idx in chunk}
+        srcs = {}
+        for idx in chunk:
+            w, h = imgs[idx]
+            pitch = (w * 4 + 63) // 64 * 64
+            v = torch.zeros((h, pitch), dtype=torch.uint8, device=dev).as_strided((h, w, 4), (pitch, 4, 1))
+            synth.noise_torch(w, h, seed=idx, device=dev, out=v)
+            srcs[idx] = v
         # materialise every size of every chain; a chain's later steps read earlier results, so run level by level
         results = {}
         levels = [[], [], []]                # level 0: src->1600 ; level 1: 1600->1200, 1600->800 ; level 2: 1200->400
         for idx in chunk:
             for (src, dst) in chains[idx]:
                 key_src = (idx, src); key_dst = (idx, dst)
-                if key_dst not in results:
-                    results[key_dst] = torch.empty((dst[1], dst[0], 4), dtype=torch.uint8, device=dev)
+                if key_dst not in results:            # 64-byte padded pitch, like Bitmap::create_u8 (bitmaps.rs:803-804)
+                    pitch = (dst[0] * 4 + 63) // 64 * 64
+                    results[key_dst] = torch.empty((dst[1], pitch), dtype=torch.uint8, device=dev).as_strided((dst[1], dst[0], 4), (pitch, 4, 1))
                 lvl = 0 if src == imgs[idx] else (2 if dst[0] <= 400 and dst[1] <= 400 and src != imgs[idx] and max(src) <= 1200 else 1)
                 levels[lvl].append((idx, src, dst))
         torch.cuda.synchronize()
@@ -102,12 +109,12 @@ def main():
             import oracle
             mx = 0
             for idx in chunk[:args.check]:
-                cur = {imgs[idx]: srcs[idx].cpu().numpy()}
+                cur = {imgs[idx]: srcs[idx].contiguous().cpu().numpy()}
                 for (src, dst) in chains[idx]:
                     out = np.zeros((dst[1], dst[0], 4), np.uint8)
                     oracle.scale_and_render(cur[src], out, filter=2)
                     cur[dst] = out
-                    mx = max(mx, int(np.abs(out.astype(np.int16) - results[(idx, dst)].cpu().numpy().astype(np.int16)).max()))
+                    mx = max(mx, int(np.abs(out.astype(np.int16) - results[(idx, dst)].contiguous().cpu().numpy().astype(np.int16)).max()))
             checked = {"chains": args.check, "max_abs_delta_vs_oracle": mx}
         del srcs, results
         torch.cuda.empty_cache()
@@ -116,7 +123,7 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": "c5_mixed_thumbnails_export_4_sizes", "images": args.images, "n_gpus": world, "resamples": int(tot_jobs),
                           "input_mpx": tot_px / 1e6, "ms": max_ms, "value": tot_px / 1e6 / (max_ms / 1e3), "unit": "Mpx/s (input pixels of every resample)",
-                          "lpt_imbalance": sharding.lpt_imbalance(costs, bins), "fused_jobs_rank0": batch.fused_jobs, "generic_jobs_rank0": batch.generic_jobs,
+                          "lpt_imbalance": sharding.lpt_imbalance(costs, bins), "fused_jobs_rank0": batch.fused_jobs, "generic_jobs_rank0": batch.generic_jobs, "tile_jobs_rank0": batch.tile_jobs,
                           "parity_check": checked}))
     if world > 1:
         dist.destroy_process_group()
