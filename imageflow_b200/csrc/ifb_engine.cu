@@ -177,12 +177,11 @@ void build_tile(Plan& p) {
     p.tile = t; p.tile_ok = true;
 }
 
-// per-source-row program: weights of the open output rows, oldest first (float bits, duplicated pairs), then the completion word
+// per-source-row program: weights of the open output rows, oldest first (float bits), then the completion word
 const uint32_t* fused_vprog(Plan& p) {
     auto& slot = p.vprog;
     if (slot) return slot->p;
-    const bool f2 = true;                 // weights are stored as (w,w) pairs for FFMA2
-    const int nw = 2 * p.av;
+    const int nw = p.av;
     const int words = (nw + 1 + 3) / 4 * 4;
     std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
     const auto& a = p.wv;
@@ -196,7 +195,7 @@ const uint32_t* fused_vprog(Plan& p) {
             if (s >= (uint32_t)p.av) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: ring slot %u >= %d", s, p.av);
             uint32_t bits; memcpy(&bits, &w[j - a.left[y]], 4);
             uint32_t* rec = prog.data() + (size_t)j * words;
-            if (f2) { rec[2 * s] = bits; rec[2 * s + 1] = bits; } else rec[s] = bits;
+            rec[s] = bits;
         }
     }
     for (uint32_t j = 0; j < p.in_h; ++j) prog[(size_t)j * words + nw] = p.vdone_host[j];
@@ -257,15 +256,19 @@ FusedVariantTables& fused_tables(Plan& p, int nt) {
                 const float* w = h.w.data() + h.offset[X];
                 for (uint32_t i = 0; i < 4; ++i) {
                     const uint32_t k = c0 + i;
-                    if (k >= h.left[X] && k <= h.right[X])
-                        hw[(((size_t)s * SH + q) * 4 + i) * nt + t] = w[k - h.left[X]];
+                    if (k < h.left[X] || k > h.right[X]) continue;
+                    // outputs (q, q+1) are interleaved as float2; an odd last output follows as plain floats
+                    const size_t base = (size_t)s * SH * 4 * nt;
+                    const size_t idx = (q / 2 < (uint32_t)SH / 2) ? 2 * ((size_t)((q / 2) * 4 + i) * nt + t) + (q & 1)
+                                                                  : (size_t)(SH / 2) * 8 * nt + (size_t)i * nt + t;
+                    hw[base + idx] = w[k - h.left[X]];
                 }
             }
         }
         for (uint32_t X = sd.X0; X < (uint32_t)sd.X1; ++X) {
             const uint32_t tg0 = h.left[X] / 4 - sd.k0 / 4, ng = h.right[X] / 4 - h.left[X] / 4 + 1;
             if (tg0 + ng > (uint32_t)nt || ng >= 4096u) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: reader range outside strip");
-            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12);
+            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12) | ((X % (uint32_t)SH) << 28);
         }
     }
     ft->strips.upload(strips); ft->hw.upload(hw); ft->hxa.upload(hxa); ft->hrd.upload(hrd);

@@ -52,9 +52,9 @@ struct FusedPlanDev {
                                 //   each duplicated into a pair for FFMA2), then ((first completed y << 8) | count)
     const StripDev* strips;
     const BandDev* bands;
-    const float* hw;            // [strip][SH][4][NT]
+    const float* hw;            // [strip][SH*4*NT]: pairs (q,q+1) as float2 at 2*((qp*4+i)*NT+t), odd last q as floats after them
     const int* hxa;             // [strip][NT] first output column touched by thread t's 4 columns
-    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12)
+    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12) | ((X mod SH) << 28)
 };
 
 // ---------------------------------------------------------------- scalar helpers
@@ -300,7 +300,7 @@ constexpr int kProgChunk = 32;                       // source rows per program 
 constexpr int kLutBytes = 256 * 256;                 // LUT region: 256 rows of 256 B (see below)
 
 template <int AV> struct ProgLayout {
-    static constexpr int kW = 2 * AV;                // weight words: (w,w) pairs, ready for FFMA2
+    static constexpr int kW = AV;                    // weight words (FFMA2 takes the weight as a broadcast scalar operand)
     static constexpr int kDone = kW;                 // index of the completion word
     static constexpr int kWords = (kW + 1 + 3) / 4 * 4;
 };
@@ -315,7 +315,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   [0, 64 KB)   row v (256 B): bytes 0..127 = T[v] replicated for the 32 lanes, so the byte address of a lookup is
 //                (v << 8) | (lane << 2): ONE PRMT builds it from the packed pixel, and the gather is bank-conflict
 //                free for any image content.  Bytes 128..255 of the rows ("holes") hold the strip's H weights:
-//                word w of hw[SH][4][NT] lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2).
+//                word w of the H-weight block (see the completion code) lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2).
 //   then         row-program double buffer, partial sums (2 x CH x SH x NT floats), per-thread reader meta.
 template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kProgBytes = 2 * kProgChunk * ProgLayout<AV>::kWords * 4;
@@ -326,6 +326,11 @@ template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kTotal = kMetaOff + NT * 4;
     static_assert(SH * 4 * NT / 32 <= 256, "H weights must fit in the LUT holes");
 };
+
+// address of word w of the data parked in the LUT holes
+__device__ __forceinline__ const unsigned char* hole_ptr(const unsigned char* sLut, int w) {
+    return sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2);
+}
 
 template <int AV, int SH, int CH, int PF, int NT>
 __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
@@ -339,9 +344,6 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     uint32_t* sProg = reinterpret_cast<uint32_t*>(smem_raw + SM::kProgOff);
     float* sPart = reinterpret_cast<float*>(smem_raw + SM::kPartOff);
     uint32_t* sMeta = reinterpret_cast<uint32_t*>(smem_raw + SM::kMetaOff);
-    // this thread's H weights: word (q*4+i)*NT + t of hw  ->  hole address
-    const float* sHwT = reinterpret_cast<const float*>(sLut + ((t >> 5) << 8) + 128 + ((t & 31) << 2));
-    constexpr int kHwStep = (NT / 32) * 256 / 4;     // floats between consecutive (q,i) entries of one thread
 
     const JobDev& job = jobs[blockIdx.y];
     const int strip = blockIdx.x % pl.n_strips;
@@ -453,7 +455,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             // ---- ring accumulate (packed fp32 FMA: two IEEE fmaf per instruction)
 #pragma unroll
             for (int s = 0; s < AV; ++s) {
-                const float2 w2 = *reinterpret_cast<const float2*>(rec + 2 * s);
+                const float ws = __uint_as_float(rec[s]);
+                const float2 w2 = make_float2(ws, ws);          // becomes a scalar (.F32) operand of FFMA2
 #pragma unroll
                 for (int k = 0; k < NV / 2; ++k) {
                     const float2 r2 = __ffma2_rn(w2, make_float2(p[2 * k], p[2 * k + 1]), make_float2(acc[s][2 * k], acc[s][2 * k + 1]));
@@ -482,21 +485,38 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                     const int par = nrow & 1;
                     float* pb = sPart + par * (CH * SH) * NT;
                     {
-                        int poff = (int)(sMeta[t] >> 24) * NT + t;    // plane (X mod SH) of this thread's first output
+                        // H weights of this thread: output pairs (q, q+1) as float2 at word 2*((qp*4+i)*NT + t), the odd
+                        // last output as floats after them; FFMA2 takes the V value as a broadcast scalar operand.
+                        int poff = (int)((sMeta[t] >> 24) & 7u) * NT + t;   // plane (X mod SH) of this thread's first output
+                        auto next_plane = [&]() { poff += NT; if (poff >= SH * NT) poff -= SH * NT; };
 #pragma unroll
-                        for (int q = 0; q < SH; ++q) {
-                            const float h0 = sHwT[(q * 4 + 0) * kHwStep], h1 = sHwT[(q * 4 + 1) * kHwStep];
-                            const float h2 = sHwT[(q * 4 + 2) * kHwStep], h3 = sHwT[(q * 4 + 3) * kHwStep];
+                        for (int qp = 0; qp < SH / 2; ++qp) {
+                            float2 h[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) h[i] = *reinterpret_cast<const float2*>(hole_ptr(sLut, 2 * ((qp * 4 + i) * NT + t)));
+                            const int p0 = poff; next_plane();
+                            const int p1 = poff; next_plane();
 #pragma unroll
                             for (int c = 0; c < CH; ++c) {
-                                float ps = __fmaf_rn(h0, acc[0][c * 4 + 0], 0.0f);
-                                ps = __fmaf_rn(h1, acc[0][c * 4 + 1], ps);
-                                ps = __fmaf_rn(h2, acc[0][c * 4 + 2], ps);
-                                ps = __fmaf_rn(h3, acc[0][c * 4 + 3], ps);
+                                float2 ps = make_float2(0.0f, 0.0f);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) { const float v = acc[0][c * 4 + i]; ps = __ffma2_rn(h[i], make_float2(v, v), ps); }
+                                pb[c * SH * NT + p0] = ps.x;
+                                pb[c * SH * NT + p1] = ps.y;
+                            }
+                        }
+                        if (SH & 1) {
+                            float h[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) h[i] = *reinterpret_cast<const float*>(hole_ptr(sLut, (SH / 2) * 8 * NT + i * NT + t));
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) {
+                                float ps = __fmaf_rn(h[0], acc[0][c * 4 + 0], 0.0f);
+                                ps = __fmaf_rn(h[1], acc[0][c * 4 + 1], ps);
+                                ps = __fmaf_rn(h[2], acc[0][c * 4 + 2], ps);
+                                ps = __fmaf_rn(h[3], acc[0][c * 4 + 3], ps);
                                 pb[c * SH * NT + poff] = ps;
                             }
-                            poff += NT;
-                            if (poff >= SH * NT) poff -= SH * NT;
                         }
                     }
                     __syncthreads();
@@ -504,7 +524,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                     if (u >= 0 && u < NX && (!alternate || my_half == par)) {
                         const uint32_t meta = sMeta[u];
                         const int X = sd.X0 + u;
-                        const int plane = X % SH;
+                        const int plane = (int)(meta >> 28);                // X mod SH, precomputed on the host
                         const int tg0 = meta & 0xfffu, ng = (meta >> 12) & 0xfffu;
                         const float* pr = pb + plane * NT + tg0;
                         float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
