@@ -8,13 +8,13 @@ Host-side mirror of the reference seam (paths relative to the imageflow checkout
 All arithmetic runs in hand-written sm_100a kernels inside libifb200.so (include/ifb200.h);
 this package only marshals arguments.  Nothing here imports the CPU oracle.
 """
-from .graphics import (Batch, BitmapCompositing, BitmapWindow, ErrorKind, Filter, FlowError, ScaleAndRenderParams,
+from .graphics import (Batch, apply_matte, BitmapCompositing, BitmapWindow, ErrorKind, Filter, FlowError, ScaleAndRenderParams,
                        WorkingFloatspace, color_filter_matrix, device_count, populate_weights, scale_and_render, scale_and_render_many,
                        window_bgra32_apply_color_matrix)
 from ._lib import LIB_PATH, ResampleDesc, lib
 
 __all__ = [
-    "Batch", "BitmapCompositing", "BitmapWindow", "ErrorKind", "Filter", "FlowError", "ScaleAndRenderParams",
+    "Batch", "apply_matte", "BitmapCompositing", "BitmapWindow", "ErrorKind", "Filter", "FlowError", "ScaleAndRenderParams",
     "WorkingFloatspace", "color_filter_matrix", "device_count", "populate_weights", "scale_and_render", "scale_and_render_many",
     "window_bgra32_apply_color_matrix", "LIB_PATH", "ResampleDesc", "lib",
 ]

@@ -541,6 +541,20 @@ void color_matrix_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t 
     CUDA_OK(cudaFreeAsync(dm, st));
 }
 
+void apply_matte_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t* matte, cudaStream_t st) {
+    if (!dev_px || !matte) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+    if (w == 0 || h == 0) return;
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+    const uint64_t total = (uint64_t)w * h;
+    if (total > 0xffffffffull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap too large");
+    CUDA_OK(cudaSetDevice(b->device));
+    const uint32_t m = (uint32_t)matte[0] | ((uint32_t)matte[1] << 8) | ((uint32_t)matte[2] << 16) | ((uint32_t)matte[3] << 24);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148ull * 16);
+    apply_matte_kernel<<<blocks, 256, 0, st>>>(dev_px, w, h, stride, m, b->tables);
+    CUDA_OK(cudaGetLastError());
+    b->launches++;
+}
+
 // per-thread context for the host-buffer drop-in calls: a small pipeline of streams, each with its own
 // device staging for one input window and one destination rect, so that the upload of call i+1 overlaps the
 // kernel of call i and the download of call i-1 when several calls are issued through the batched entry point.
@@ -678,6 +692,16 @@ int ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint
     });
 }
 
+int ifb200_batch_apply_matte(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t matte_bgra[4],
+                             int alpha_meaningful, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        if (!alpha_meaningful) return;                       // blend.rs:10-13: nothing to do unless alpha is meaningful
+        std::lock_guard<std::mutex> lk(b->mu);
+        apply_matte_locked(b, dev_px, w, h, stride, matte_bgra, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+
 int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
@@ -759,6 +783,27 @@ int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, ch
             throw;
         }
         for (auto& sl : c.slot) CUDA_OK(cudaStreamSynchronize(sl.stream));
+    });
+}
+
+int ifb200_apply_matte_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t matte_bgra[4], int alpha_meaningful,
+                             char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!px || !matte_bgra) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (!alpha_meaningful || w == 0 || h == 0) return;   // blend.rs:10-13
+        if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
+        ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        apply_matte_locked(b, sl.d_cv, w, h, (uint32_t)pitch, matte_bgra, st);
+        CUDA_OK(cudaMemcpy2DAsync(px, stride, sl.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
     });
 }
 

@@ -280,6 +280,33 @@ __global__ void __launch_bounds__(256) color_matrix_kernel(uint8_t* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- apply_matte (graphics/blend.rs:6-59)
+// Encoder-side flatten over a solid colour, in place, linear light.
+__global__ void __launch_bounds__(256) apply_matte_kernel(uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
+                                                          uint32_t matte_bgra, Tables tb) {
+    const float a2f = 1.0f / 255.0f;
+    const float ma = __fmul_rn((float)(matte_bgra >> 24), a2f);
+    const float mb = __ldg(tb.t_lin + (matte_bgra & 0xffu)), mg = __ldg(tb.t_lin + ((matte_bgra >> 8) & 0xffu)), mr = __ldg(tb.t_lin + ((matte_bgra >> 16) & 0xffu));
+    const uint32_t total = w * h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t y = i / w, x = i - y * w;
+        uint32_t* p = reinterpret_cast<uint32_t*>(px + (size_t)y * stride) + x;
+        const uint32_t v = *p;
+        const uint32_t pa = v >> 24;
+        if (pa == 0u) { *p = matte_bgra; continue; }
+        if (pa == 255u) continue;
+        const float paf = __fmul_rn((float)(int)pa, a2f);
+        const float m_a = __fmul_rn(__fsub_rn(1.0f, paf), ma);
+        const float fa = __fadd_rn(m_a, paf);
+        auto ch = [&](uint32_t byte, float m) {
+            const float lin = __fdiv_rn(__fadd_rn(__fmul_rn(__ldg(tb.t_lin + byte), paf), __fmul_rn(m, m_a)), fa);
+            return lut_encode(tb.lut16k, lin);
+        };
+        const uint32_t nb = ch(v & 0xffu, mb), ng = ch((v >> 8) & 0xffu, mg), nr = ch((v >> 16) & 0xffu, mr);
+        *p = nb | (ng << 8) | (nr << 16) | (uchar_clamp_ff(__fmul_rn(255.0f, fa)) << 24);
+    }
+}
+
 // ---------------------------------------------------------------- fused down-scale kernel
 // One CTA = (job, strip of output columns, band of output rows).  Thread t owns source columns
 // k0+4t .. k0+4t+3 for the whole band:

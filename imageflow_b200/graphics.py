@@ -150,6 +150,13 @@ def window_bgra32_apply_color_matrix(window: BitmapWindow, m) -> None:
                                             mm.ctypes.data_as(C.POINTER(C.c_float)), buf, 512), buf)
 
 
+def apply_matte(window: BitmapWindow, matte_bgra) -> None:
+    """graphics/blend.rs:6-59 (Bitmap::apply_matte), in place on a HOST window."""
+    mm = (C.c_uint8 * 4)(*matte_bgra)
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_apply_matte_bgra8(window.ptr, window.w, window.h, window.stride, mm, int(bool(window.alpha_meaningful)), buf, 512), buf)
+
+
 def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
     """flow/nodes/color.rs:86-225 presets (0 sepia ... 9 saturation)."""
     m = np.zeros(25, np.float32)

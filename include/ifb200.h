@@ -110,6 +110,11 @@ int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, ch
 int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float m[25],
                               char* err, size_t err_cap);
 
+/* Replaces Bitmap::apply_matte (graphics/blend.rs:6-59), the encoder-side flatten over a solid colour (in place,
+ * linear light).  No-op unless alpha is meaningful (blend.rs:10-13).  [SURVEY.md section 8(f), item 2] */
+int ifb200_apply_matte_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t matte_bgra[4],
+                             int alpha_meaningful, char* err, size_t err_cap);
+
 /* ---- device-resident batch API (the metric path; not in the reference) -----------------------
  * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
  * enqueue is asynchronous on `cuda_stream`, a cudaStream_t with the usual CUDA meaning (NULL = the legacy
@@ -122,6 +127,8 @@ int  ifb200_batch_enqueue(ifb200_batch* b, const ifb200_resample_desc* descs, si
                           char* err, size_t err_cap);
 int  ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
                                const float m[25], void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_apply_matte(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
+                              const uint8_t matte_bgra[4], int alpha_meaningful, void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
 void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */

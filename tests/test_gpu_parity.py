@@ -341,3 +341,17 @@ def test_mixed_thumbnail_workload_runner(ifb):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["parity_check"] == {"chains": 6, "max_abs_delta_vs_oracle": 0}
     assert d["resamples"] > 40 and d["fused_jobs_rank0"] + d["generic_jobs_rank0"] + d["tile_jobs_rank0"] == d["resamples"]
+
+
+def test_apply_matte_matches_oracle(ifb):
+    """SURVEY section 8(f) item 2: Bitmap::apply_matte (blend.rs:6-59) on the GPU, bit-exact vs the oracle."""
+    px0 = util.noise(301, 97, seed=21, alpha_mode="mixed")
+    for matte in ((255, 255, 255, 255), (10, 200, 30, 255), (0, 0, 0, 128)):
+        exp = px0.copy()
+        oracle.apply_matte(exp, matte)
+        got = util.padded(px0)
+        ifb.apply_matte(ifb.BitmapWindow.from_numpy(got, alpha_meaningful=True), matte)
+        assert util.diff_stats(got, exp)[0] == 0
+    same = util.padded(px0)
+    ifb.apply_matte(ifb.BitmapWindow.from_numpy(same, alpha_meaningful=False), (1, 2, 3, 255))     # blend.rs:10-13
+    assert np.array_equal(same, px0)
