@@ -324,6 +324,7 @@ struct ifb200_batch {
     DevVec<float> t_lin, t_srgb; DevVec<uint8_t> lut16k;
     Tables tables{};
     using Key = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t>;
+    static constexpr size_t kMaxPlans = 4096;
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
@@ -420,6 +421,10 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     if (n == 0) return;
     host_tables();
     CUDA_OK(cudaSetDevice(b->device));
+    if (b->plans.size() + n > ifb200_batch::kMaxPlans) {   // bound the cache (mixed workloads: thousands of geometries);
+        CUDA_OK(cudaDeviceSynchronize());                  // done before any Plan* of this call is taken; kernels in flight
+        b->plans.clear();                                  // may still read the old tables, hence the synchronise
+    }
     // group jobs by (plan, kernel class)
     struct Group { Plan* plan; int ch; int kind; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
     std::vector<Group> groups;
