@@ -295,8 +295,9 @@ const BandDev* fused_bands(Plan& p, FusedVariantTables& ft, int nb) {
 // ------------------------------------------------------------------------------------------------
 // fused kernel dispatch table
 using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
-struct FusedEntry { int av, sh, ch, nt; FusedFn fn; size_t smem; };
-#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
+struct FusedEntry { int av, sh, ch, nt; FusedFn fn, fn_simple; size_t smem; };
+#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_, false>, \
+                                         fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_, true>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
 #define IFB_FUSED(AV_, SH_) IFB_FUSED_1(AV_, SH_, 3, 256), IFB_FUSED_1(AV_, SH_, 4, 256), IFB_FUSED_1(AV_, SH_, 3, 128), IFB_FUSED_1(AV_, SH_, 4, 128)
 const FusedEntry kFused[] = {
 #ifdef IFB_FEW_SHAPES      /* development builds: only the shapes the 4K->512 benchmarks use */
@@ -426,7 +427,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         b->plans.clear();                                  // may still read the old tables, hence the synchronise
     }
     // group jobs by (plan, kernel class)
-    struct Group { Plan* plan; int ch; int kind; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
+    struct Group { Plan* plan; int ch; int kind; bool simple; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
         validate(descs[i]);
@@ -441,9 +442,10 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         // for up-scales / 1:1 the tile kernel does less work per source pixel
         const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || (p.out_h >= p.in_h && p.out_w >= p.in_w));
         const int kind = prefer_tile ? 2 : (fused ? 1 : 0);
+        const bool simple = d.compose == IFB200_REPLACE_SELF && !d.color_matrix;   // store epilogue without composite / matrix code
         Group* g = nullptr;
-        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind) { g = &gg; break; }
-        if (!g) { groups.push_back(Group{&p, ch, kind, {}}); g = &groups.back(); }
+        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind && gg.simple == simple) { g = &gg; break; }
+        if (!g) { groups.push_back(Group{&p, ch, kind, simple, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
     // job array -> device (pinned staging, stream ordered)
@@ -488,7 +490,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             pl.vprog = fused_vprog(p); pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
             pl.hw = ft.hw.p; pl.hxa = ft.hxa.p; pl.hrd = ft.hrd.p;
             const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
-            FusedFn fn = fe->fn;
+            FusedFn fn = g.simple ? fe->fn_simple : fe->fn;
             const size_t smem = fe->smem;
             CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (size_t off = 0; off < nj; off += 65535) {

@@ -78,11 +78,14 @@ __device__ __forceinline__ uint32_t encode(bool linear, const uint8_t* __restric
 
 // Store epilogue for one destination pixel. F = premultiplied working-space (b,g,r,a).
 // `dst` is read only for BlendWithSelf.  Returns packed BGRA8.
+// SIMPLE = true: the caller guarantees compose == ReplaceSelf and no colour matrix (the common thumbnail case);
+// the composite / matte / matrix code is then not even compiled into the kernel.
+template <bool SIMPLE = false>
 __device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, float a, const JobDev& job,
                                                  const Tables& tb, const uint8_t* dst) {
     const bool linear = job.flags & JF_LINEAR;
     const bool am = job.flags & JF_ALPHA;
-    const uint32_t compose = (job.flags >> JF_COMPOSE_SHIFT) & 3u;
+    const uint32_t compose = SIMPLE ? 0u : (job.flags >> JF_COMPOSE_SHIFT) & 3u;
     uint32_t ob, og, orr, oa;
     if (compose == 1u) {                                   // BlendWithSelf: scaling.rs:254-287
         if (a > 0.994f || !am) {
@@ -112,7 +115,7 @@ __device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, floa
         ob = encode(linear, tb.lut16k, b); og = encode(linear, tb.lut16k, g); orr = encode(linear, tb.lut16k, r);
         oa = uchar_clamp_ff(__fmul_rn(a, 255.0f));
     }
-    if (job.flags & JF_CM) {                               // color_matrix.rs:5-28, on sRGB bytes
+    if (!SIMPLE && (job.flags & JF_CM)) {                  // color_matrix.rs:5-28, on sRGB bytes
         const float fr = (float)orr, fg = (float)og, fb = (float)ob, fa = (float)oa;
         const float* m = job.cm;
         auto row = [&](int c) {
@@ -359,7 +362,7 @@ __device__ __forceinline__ const unsigned char* hole_ptr(const unsigned char* sL
     return sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2);
 }
 
-template <int AV, int SH, int CH, int PF, int NT>
+template <int AV, int SH, int CH, int PF, int NT, bool SIMPLE>
 __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
     using PL = ProgLayout<AV>;
     using SM = FusedSmem<AV, SH, CH, NT>;
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                             for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], pr[c * SH * NT + g]);
                         }
                         uint8_t* dst = job.out + (size_t)y * job.out_stride + (size_t)X * 4;
-                        *reinterpret_cast<uint32_t*>(dst) = finish_pixel(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, job, tb, dst);
+                        *reinterpret_cast<uint32_t*>(dst) = finish_pixel<SIMPLE>(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, job, tb, dst);
                     }
                     ++nrow;
                 }
