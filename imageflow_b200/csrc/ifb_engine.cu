@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -79,10 +81,36 @@ struct DevVec {
     DevVec& operator=(const DevVec&) = delete;
 };
 
+// Several host arrays packed into ONE device allocation and ONE asynchronous copy (through pinned staging) on the
+// stream that is about to use them.  Streams other than the uploading one wait on `ready` (see use_on()).
+struct DevBlob {
+    uint8_t* p = nullptr;
+    std::vector<uint8_t> host;
+    cudaEvent_t ready = nullptr; bool done = false; cudaStream_t up_stream = nullptr;
+    size_t add(const void* src, size_t bytes) {
+        const size_t off = (host.size() + 255) / 256 * 256;
+        host.resize(off + bytes);
+        if (bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+    template <class T> size_t add(const std::vector<T>& v) { return add(v.data(), v.size() * sizeof(T)); }
+    void commit(ifb200_batch* b, cudaStream_t st);
+    void use_on(cudaStream_t st) {
+        if (done || st == up_stream) return;
+        if (cudaEventQuery(ready) == cudaSuccess) { done = true; return; }
+        CUDA_OK(cudaStreamWaitEvent(st, ready, 0));
+    }
+    template <class T> const T* at(size_t off) const { return reinterpret_cast<const T*>(p + off); }
+    ~DevBlob() { if (ready) cudaEventDestroy(ready); if (p) cudaFree(p); }
+    DevBlob() = default;
+    DevBlob(const DevBlob&) = delete;
+    DevBlob& operator=(const DevBlob&) = delete;
+};
+
 struct AxisOnDev {
-    DevVec<uint32_t> left, right, off; DevVec<float> w;
-    void upload(const ifb::AxisWeights& a) { left.upload(a.left); right.upload(a.right); off.upload(a.offset); w.upload(a.w); }
-    AxisDev view() const { return AxisDev{left.p, right.p, off.p, w.p}; }
+    size_t o_left = 0, o_right = 0, o_off = 0, o_w = 0;
+    void add_to(DevBlob& blob, const ifb::AxisWeights& a) { o_left = blob.add(a.left); o_right = blob.add(a.right); o_off = blob.add(a.offset); o_w = blob.add(a.w); }
+    AxisDev view(const DevBlob& blob) const { return AxisDev{blob.at<uint32_t>(o_left), blob.at<uint32_t>(o_right), blob.at<uint32_t>(o_off), blob.at<float>(o_w)}; }
 };
 
 // Supported (AV, SH) instantiations of the fused kernel.
@@ -95,22 +123,21 @@ constexpr int kPrefetch = IFB_PF;   // rows per prefetch set (two sets in regist
 
 struct FusedVariantTables {      // depends on NT (strips) and band count
     int nt = 0, n_strips = 0;
-    DevVec<StripDev> strips;
-    DevVec<float> hw; DevVec<int> hxa; DevVec<uint32_t> hrd;
-    std::map<int, std::unique_ptr<DevVec<BandDev>>> bands;   // by band count
+    DevBlob blob;                       // strips, hw, hxa, hrd, the row program and the band tables, one allocation
+    size_t o_strips = 0, o_hw = 0, o_hxa = 0, o_hrd = 0, o_vprog[2] = {0, 0};
+    std::map<int, size_t> o_bands;      // by band count (a fixed set, chosen when the tables are built)
 };
 
 struct Plan {
     uint32_t in_w, in_h, out_w, out_h;
     ifb::AxisWeights wv, wh;
-    AxisOnDev dv, dh;
+    AxisOnDev dv, dh; std::unique_ptr<DevBlob> axes;   // CSR windows on the device: only the tile kernel and the generic pair read them
     // tile kernel (small windows: up-scales, 1:1, mild down-scales)
     bool tile_ok = false; TilePlanDev tile{};
     // fused
     bool fused_ok = false; std::string fused_reason;
     int av = 0, sh = 0;
     std::vector<uint32_t> vdone_host;
-    std::unique_ptr<DevVec<uint32_t>> vprog;
     std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
 };
 
@@ -178,9 +205,7 @@ void build_tile(Plan& p) {
 }
 
 // per-source-row program: weights of the open output rows, oldest first (float bits), then the completion word
-const uint32_t* fused_vprog(Plan& p) {
-    auto& slot = p.vprog;
-    if (slot) return slot->p;
+std::vector<uint32_t> fused_vprog_host(const Plan& p) {
     const int nw = p.av;
     const int words = (nw + 1 + 3) / 4 * 4;
     std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
@@ -194,19 +219,15 @@ const uint32_t* fused_vprog(Plan& p) {
             const uint32_t s = y - done_before[j];
             if (s >= (uint32_t)p.av) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: ring slot %u >= %d", s, p.av);
             uint32_t bits; memcpy(&bits, &w[j - a.left[y]], 4);
-            uint32_t* rec = prog.data() + (size_t)j * words;
-            rec[s] = bits;
+            prog[(size_t)j * words + s] = bits;
         }
     }
     for (uint32_t j = 0; j < p.in_h; ++j) prog[(size_t)j * words + nw] = p.vdone_host[j];
-    slot = std::make_unique<DevVec<uint32_t>>();
-    slot->upload(prog);
-    return slot->p;
+    return prog;
 }
 
-FusedVariantTables& fused_tables(Plan& p, int nt) {
-    auto it = p.by_nt.find(nt);
-    if (it != p.by_nt.end()) return *it->second;
+// host half: strips, H-weight block, reader meta, row program and band tables, staged in ft->blob.host (no CUDA calls)
+std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
     auto ft = std::make_unique<FusedVariantTables>();
     ft->nt = nt;
     const auto& h = p.wh;
@@ -271,25 +292,38 @@ FusedVariantTables& fused_tables(Plan& p, int nt) {
             hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12) | ((X % (uint32_t)SH) << 28);
         }
     }
-    ft->strips.upload(strips); ft->hw.upload(hw); ft->hxa.upload(hxa); ft->hrd.upload(hrd);
-    auto& ref = *ft;
-    p.by_nt[nt] = std::move(ft);
-    return ref;
+    // everything the kernel reads for this (plan, CTA size) goes into one allocation and one asynchronous copy
+    ft->o_strips = ft->blob.add(strips); ft->o_hw = ft->blob.add(hw); ft->o_hxa = ft->blob.add(hxa); ft->o_hrd = ft->blob.add(hrd);
+    ft->o_vprog[0] = ft->blob.add(fused_vprog_host(p));
+    for (int nb = 1; ; nb *= 2) {                        // band tables for power-of-two band counts
+        const int use = std::min<int>(nb, (int)std::max<uint32_t>(1u, p.out_h / 8u));
+        if (!ft->o_bands.count(use)) {
+            std::vector<BandDev> bv;
+            for (int i = 0; i < use; ++i) {
+                const int Y0 = (int)((int64_t)p.out_h * i / use), Y1 = (int)((int64_t)p.out_h * (i + 1) / use);
+                bv.push_back(BandDev{Y0, Y1, (int)p.wv.left[Y0], (int)p.wv.right[Y1 - 1]});
+            }
+            ft->o_bands[use] = ft->blob.add(bv);
+        }
+        if (use < nb || nb >= 4096) break;
+    }
+    return ft;
 }
 
-const BandDev* fused_bands(Plan& p, FusedVariantTables& ft, int nb) {
-    auto it = ft.bands.find(nb);
-    if (it != ft.bands.end()) return it->second->p;
-    std::vector<BandDev> b;
-    for (int i = 0; i < nb; ++i) {
-        int Y0 = (int)((int64_t)p.out_h * i / nb), Y1 = (int)((int64_t)p.out_h * (i + 1) / nb);
-        b.push_back(BandDev{Y0, Y1, (int)p.wv.left[Y0], (int)p.wv.right[Y1 - 1]});
-    }
-    auto dv = std::make_unique<DevVec<BandDev>>();
-    dv->upload(b);
-    const BandDev* r = dv->p;
-    ft.bands[nb] = std::move(dv);
-    return r;
+// device half: one allocation + one asynchronous copy on the first use; later uses only order their stream after it
+FusedVariantTables& fused_tables(ifb200_batch* bt, cudaStream_t st, Plan& p, int nt) {
+    auto it = p.by_nt.find(nt);
+    if (it == p.by_nt.end()) it = p.by_nt.emplace(nt, fused_tables_host(p, nt)).first;
+    FusedVariantTables& ft = *it->second;
+    if (!ft.blob.p) ft.blob.commit(bt, st); else ft.blob.use_on(st);
+    return ft;
+}
+
+// smallest prepared band count >= want
+int pick_bands(const FusedVariantTables& ft, int want) {
+    int best = ft.o_bands.rbegin()->first;
+    for (const auto& kv : ft.o_bands) if (kv.first >= want) { best = kv.first; break; }
+    return best;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,12 +389,15 @@ struct ifb200_batch {
         return s.p;
     }
 
-    Plan& plan_for(const ifb200_resample_desc& d) {
-        uint32_t sbits; float sp = d.sharpen_percent > 0.0f ? d.sharpen_percent : 0.0f;
+    static Key key_of(const ifb200_resample_desc& d) {
+        uint32_t sbits; const float sp = d.sharpen_percent > 0.0f ? d.sharpen_percent : 0.0f;
         memcpy(&sbits, &sp, 4);
-        Key k{d.in_w, d.in_h, d.w, d.h, d.filter, sbits};
-        auto it = plans.find(k);
-        if (it != plans.end()) return *it->second;
+        return Key{d.in_w, d.in_h, d.w, d.h, d.filter, sbits};
+    }
+    // Everything of a plan that needs no CUDA call (weights exactly as weights.rs, kernel tables staged for upload);
+    // thread-safe, so that an enqueue with many new geometries builds its plans on several host threads.
+    static std::unique_ptr<Plan> build_plan_host(const ifb200_resample_desc& d, int nt) {
+        const float sp = d.sharpen_percent > 0.0f ? d.sharpen_percent : 0.0f;
         auto p = std::make_unique<Plan>();
         p->in_w = d.in_w; p->in_h = d.in_h; p->out_w = d.w; p->out_h = d.h;
         const ifb::Lobe lobe = sp > 0.0f ? ifb::Lobe::SharpenPercent : ifb::Lobe::Natural;   // scaling.rs:104-106
@@ -368,16 +405,76 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "vertical weights failed: %s", ifb200_status_name(rc));
         rc = ifb::compute_axis_weights(d.filter, 1.0, lobe, sp, d.w, d.in_w, p->wh);
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
-        p->dv.upload(p->wv); p->dh.upload(p->wh);
         build_fused_v(*p);
         build_tile(*p);
-        Plan& ref = *p;
-        plans[k] = std::move(p);
+        if (p->fused_ok && !(p->tile_ok && p->out_h >= p->in_h && p->out_w >= p->in_w))
+            p->by_nt.emplace(nt, fused_tables_host(*p, nt));
+        return p;
+    }
+    Plan& plan_for(const ifb200_resample_desc& d) {
+        const Key k = key_of(d);
+        auto it = plans.find(k);
+        if (it != plans.end()) return *it->second;
+        Plan& ref = *(plans[k] = build_plan_host(d, nt));
         return ref;
+    }
+    // build the plans this call needs and the cache lacks, in parallel
+    void prebuild_plans(const ifb200_resample_desc* descs, size_t n) {
+        std::map<Key, size_t> todo;
+        for (size_t i = 0; i < n; ++i) {
+            const Key k = key_of(descs[i]);
+            if (!plans.count(k)) todo.emplace(k, i);
+        }
+        if (todo.size() < 8) return;                      // a few plans: the serial path in plan_for() is fine
+        std::vector<std::pair<Key, size_t>> work(todo.begin(), todo.end());
+        std::vector<std::unique_ptr<Plan>> built(work.size());
+        std::vector<Err> errs(work.size(), Err{0, ""});
+        std::atomic<size_t> next{0};
+        const unsigned nthreads = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)work.size()}));
+        const int cta = nt;
+        auto worker = [&] {
+            for (size_t w; (w = next.fetch_add(1)) < work.size();) {
+                try { built[w] = build_plan_host(descs[work[w].second], cta); }
+                catch (const Err& e) { errs[w] = e; }
+                catch (...) { errs[w] = Err{IFB200_ERR_OUT_OF_MEMORY, "plan build failed"}; }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+        for (size_t w = 0; w < work.size(); ++w) {
+            if (errs[w].code) throw errs[w];
+            plans[work[w].first] = std::move(built[w]);
+        }
     }
 };
 
+void DevBlob::commit(ifb200_batch* b, cudaStream_t st) {
+    const size_t n = host.size();
+    if (!n) return;
+    CUDA_OK(cudaMalloc(&p, n));
+    cudaEvent_t ev;
+    void* pin = b->stage(n, &ev);
+    memcpy(pin, host.data(), n);
+    CUDA_OK(cudaMemcpyAsync(p, pin, n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(ev, st));                     // releases the pinned slot
+    CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(ready, st));
+    up_stream = st;
+    host.clear(); host.shrink_to_fit();
+}
+
 namespace {
+
+// CSR windows on the device (tile kernel and generic pair only)
+void ensure_axes(ifb200_batch* b, cudaStream_t st, Plan& p) {
+    if (p.axes) { p.axes->use_on(st); return; }
+    p.axes = std::make_unique<DevBlob>();
+    p.dv.add_to(*p.axes, p.wv);
+    p.dh.add_to(*p.axes, p.wh);
+    p.axes->commit(b, st);
+}
 
 void validate(const ifb200_resample_desc& d) {
     if (!d.in || !d.canvas) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
@@ -426,6 +523,8 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         CUDA_OK(cudaDeviceSynchronize());                  // done before any Plan* of this call is taken; kernels in flight
         b->plans.clear();                                  // may still read the old tables, hence the synchronise
     }
+    for (size_t i = 0; i < n; ++i) validate(descs[i]);
+    b->prebuild_plans(descs, n);
     // group jobs by (plan, kernel class)
     struct Group { Plan* plan; int ch; int kind; bool simple; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
     std::vector<Group> groups;
@@ -469,26 +568,29 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         const size_t nj = g.idx.size();
         if (g.kind == 2) {
             const TilePlanDev& t = p.tile;
+            ensure_axes(b, st, p);
             const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
             CUDA_OK(cudaFuncSetAttribute((const void*)fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             for (size_t off = 0; off < nj; off += 65535) {
                 const size_t cnt = std::min<size_t>(65535, nj - off);
                 dim3 grid((unsigned)(t.tiles_x * t.tiles_y), (unsigned)cnt);
-                fused_tile_kernel<<<grid, 256, smem, st>>>(jobs + off, b->tables, p.dv.view(), p.dh.view(), t);
+                fused_tile_kernel<<<grid, 256, smem, st>>>(jobs + off, b->tables, p.dv.view(*p.axes), p.dh.view(*p.axes), t);
                 CUDA_OK(cudaGetLastError());
                 b->launches++;
             }
             b->tile_jobs += nj;
         } else if (g.kind == 1) {
-            FusedVariantTables& ft = fused_tables(p, b->nt);
+            FusedVariantTables& ft = fused_tables(b, st, p, b->nt);
             int nb = 1;
             const size_t base = nj * ft.n_strips;
             if (base < (size_t)b->min_ctas) nb = (int)std::min<size_t>((b->min_ctas + base - 1) / base, std::max<uint32_t>(1u, p.out_h / 8u));
+            nb = pick_bands(ft, nb);
             FusedPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
             pl.n_strips = ft.n_strips; pl.n_bands = nb;
-            pl.vprog = fused_vprog(p); pl.strips = ft.strips.p; pl.bands = fused_bands(p, ft, nb);
-            pl.hw = ft.hw.p; pl.hxa = ft.hxa.p; pl.hrd = ft.hrd.p;
+            pl.vprog = ft.blob.at<uint32_t>(ft.o_vprog[0]); pl.strips = ft.blob.at<StripDev>(ft.o_strips);
+            pl.bands = ft.blob.at<BandDev>(ft.o_bands.at(nb));
+            pl.hw = ft.blob.at<float>(ft.o_hw); pl.hxa = ft.blob.at<int>(ft.o_hxa); pl.hrd = ft.blob.at<uint32_t>(ft.o_hrd);
             const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
             FusedFn fn = g.simple ? fe->fn_simple : fe->fn;
             const size_t smem = fe->smem;
@@ -505,15 +607,16 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             // generic pair; bound the float4 intermediate to ~1 GiB per chunk
             const size_t per = (size_t)p.out_h * p.in_w * sizeof(float4);
             const size_t chunk = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nj, 65535), ((size_t)1 << 30) / std::max<size_t>(per, 1)));
+            ensure_axes(b, st, p);
             float4* inter = nullptr;
             CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&inter), per * chunk, st));
             for (size_t off = 0; off < nj; off += chunk) {
                 const size_t cnt = std::min(chunk, nj - off);
                 dim3 gv((p.in_w + 127) / 128, p.out_h, (unsigned)cnt);
-                vpass_generic_kernel<<<gv, 128, 0, st>>>(jobs + off, b->tables, p.dv.view(), p.in_w, p.out_h, inter);
+                vpass_generic_kernel<<<gv, 128, 0, st>>>(jobs + off, b->tables, p.dv.view(*p.axes), p.in_w, p.out_h, inter);
                 CUDA_OK(cudaGetLastError());
                 dim3 gh((p.out_w + 127) / 128, p.out_h, (unsigned)cnt);
-                hpass_generic_kernel<<<gh, 128, 0, st>>>(jobs + off, b->tables, p.dh.view(), p.in_w, p.out_w, p.out_h, inter);
+                hpass_generic_kernel<<<gh, 128, 0, st>>>(jobs + off, b->tables, p.dh.view(*p.axes), p.in_w, p.out_w, p.out_h, inter);
                 CUDA_OK(cudaGetLastError());
                 b->launches += 2;
             }

@@ -56,6 +56,16 @@ def main():
     mine = bins[rank]
     batch = ifb.Batch(local)
     stream = torch.cuda.current_stream().cuda_stream
+    # warm-up outside the timed region: loads the kernel variants (CUDA loads modules lazily), the pinned staging pool and
+    # the stream-ordered allocator; uses geometries that do not occur in the workload, so no plan is pre-built
+    wjobs, wkeep = [], []
+    for (w, h, ow, oh) in [(1031, 777, 257, 193), (517, 389, 511, 385), (2053, 1031, 255, 129), (259, 263, 521, 529)]:
+        a = synth.noise_torch(w, h, seed=1, device=dev); o = torch.empty((oh, ow, 4), dtype=torch.uint8, device=dev)
+        wkeep += [a, o]
+        wjobs.append((ifb.BitmapWindow.from_torch(a), ifb.BitmapWindow.from_torch(o), ifb.ScaleAndRenderParams(w=ow, h=oh)))
+    batch.scale_and_render_many(wjobs * 3, stream=stream)
+    torch.cuda.synchronize()
+    del wkeep
     px_done = 0
     jobs_done = 0
     t_total = 0.0
