@@ -101,7 +101,7 @@ struct DevBlob {
         CUDA_OK(cudaStreamWaitEvent(st, ready, 0));
     }
     template <class T> const T* at(size_t off) const { return reinterpret_cast<const T*>(p + off); }
-    ~DevBlob() { if (ready) cudaEventDestroy(ready); if (p) cudaFree(p); }
+    ~DevBlob() { if (ready) cudaEventDestroy(ready); }     // the memory belongs to the batch's table arena
     DevBlob() = default;
     DevBlob(const DevBlob&) = delete;
     DevBlob& operator=(const DevBlob&) = delete;
@@ -370,8 +370,29 @@ struct ifb200_batch {
     ~ifb200_batch() {
         cudaSetDevice(device);
         for (auto& s : pinned) { if (s.ev) cudaEventDestroy(s.ev); if (s.p) cudaFreeHost(s.p); }
-        plans.clear();
+        drop_plans();
         if (own_stream) cudaStreamDestroy(own_stream);
+    }
+
+    // Bump allocator for plan tables: thousands of small tables cost one cudaMalloc per 32 MiB, not one each.
+    // Freed as a whole together with the plan cache.
+    std::vector<uint8_t*> arena_chunks; size_t arena_used = 0, arena_cap = 0;
+    uint8_t* table_alloc(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        if (arena_chunks.empty() || arena_used + bytes > arena_cap) {
+            const size_t cap = std::max<size_t>(bytes, (size_t)32 << 20);
+            uint8_t* c = nullptr;
+            CUDA_OK(cudaMalloc(&c, cap));
+            arena_chunks.push_back(c); arena_used = 0; arena_cap = cap;
+        }
+        uint8_t* r = arena_chunks.back() + arena_used;
+        arena_used += bytes;
+        return r;
+    }
+    void drop_plans() {                                   // callers synchronise the device first
+        plans.clear();
+        for (uint8_t* c : arena_chunks) cudaFree(c);
+        arena_chunks.clear(); arena_used = arena_cap = 0;
     }
 
     void* stage(size_t bytes, cudaEvent_t* ev_out) {
@@ -453,7 +474,7 @@ struct ifb200_batch {
 void DevBlob::commit(ifb200_batch* b, cudaStream_t st) {
     const size_t n = host.size();
     if (!n) return;
-    CUDA_OK(cudaMalloc(&p, n));
+    p = b->table_alloc(n);
     cudaEvent_t ev;
     void* pin = b->stage(n, &ev);
     memcpy(pin, host.data(), n);
@@ -521,7 +542,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     CUDA_OK(cudaSetDevice(b->device));
     if (b->plans.size() + n > ifb200_batch::kMaxPlans) {   // bound the cache (mixed workloads: thousands of geometries);
         CUDA_OK(cudaDeviceSynchronize());                  // done before any Plan* of this call is taken; kernels in flight
-        b->plans.clear();                                  // may still read the old tables, hence the synchronise
+        b->drop_plans();                                   // may still read the old tables, hence the synchronise
     }
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
     b->prebuild_plans(descs, n);
