@@ -284,12 +284,15 @@ def main():
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    host_ms = []
     e0.record()
     for k in range(args.steps):
         if canvas0 is not None:
             out.copy_(canvas0)
         k_ev[k][0].record()
+        t_h = time.perf_counter()
         batch.enqueue(descs, stream)
+        host_ms.append((time.perf_counter() - t_h) * 1e3)
         k_ev[k][1].record()
     e1.record()
     barrier()
@@ -311,7 +314,7 @@ def main():
     tap_flops = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_min": float(np.min(step_ms)),
-                "kernel_ms_all": [round(x, 4) for x in step_ms], "algorithmic_bytes_per_launch": alg,
+                "kernel_ms_all": [round(x, 4) for x in step_ms], "host_enqueue_ms": [round(x, 3) for x in host_ms], "algorithmic_bytes_per_launch": alg,
                 "fused_jobs": batch.fused_jobs, "generic_jobs": batch.generic_jobs, "tile_jobs": batch.tile_jobs}
     tfile = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tfile):

@@ -116,15 +116,20 @@ struct AxisOnDev {
 // Supported (AV, SH) instantiations of the fused kernel.
 constexpr int kAvChoices[] = {2, 4, 6};
 constexpr int kShChoices[] = {3, 5, 6, 7, 8};
-#ifndef IFB_PF
-#define IFB_PF 3
+// Rows per prefetch set (two sets in registers): as deep as the register budget of the variant allows (128 registers per
+// thread at two 256-thread CTAs per SM; the ring takes AV * 4 * CH of them).
+constexpr int prefetch_rows(int av, int ch) {
+#ifdef IFB_PF
+    return IFB_PF;
+#else
+    return ch == 3 ? (av <= 2 ? 6 : av <= 4 ? 5 : 3) : (av <= 2 ? 6 : av <= 4 ? 3 : 2);
 #endif
-constexpr int kPrefetch = IFB_PF;   // rows per prefetch set (two sets in registers)
+}
 
 struct FusedVariantTables {      // depends on NT (strips) and band count
     int nt = 0, n_strips = 0;
-    DevBlob blob;                       // strips, hw, hxa, hrd, the row program and the band tables, one allocation
-    size_t o_strips = 0, o_hw = 0, o_hxa = 0, o_hrd = 0, o_vprog[2] = {0, 0};
+    DevBlob blob;                       // strips, hw, hrd, the row program and the band tables, one allocation
+    size_t o_strips = 0, o_hw = 0, o_hrd = 0, o_vprog[2] = {0, 0};
     std::map<int, size_t> o_bands;      // by band count (a fixed set, chosen when the tables are built)
 };
 
@@ -178,7 +183,7 @@ void build_fused_v(Plan& p) {
     for (uint32_t y = 0; y < a.out_size; ++y) {
         uint32_t& d = vdone[a.right[y]];
         if ((d & 0xffu) == 0) d = (y << 8) | 1u; else d += 1u;
-        if ((d & 0xffu) == 0xffu) { p.fused_reason = "too many rows complete at once"; return; }
+        if ((d & 0xffu) > 15u) { p.fused_reason = "too many rows complete at once"; return; }
     }
     p.vdone_host = std::move(vdone);
     p.fused_ok = true;
@@ -204,25 +209,24 @@ void build_tile(Plan& p) {
     p.tile = t; p.tile_ok = true;
 }
 
-// per-source-row program: weights of the open output rows, oldest first (float bits), then the completion word
+// per-source-row program: weight (float bits) per ring slot -- output row y owns slot y mod AV while its window is
+// open (build_fused_v guarantees at most AV consecutive rows are open at once) -- then the completion word
 std::vector<uint32_t> fused_vprog_host(const Plan& p) {
-    const int nw = p.av;
-    const int words = (nw + 1 + 3) / 4 * 4;
+    const uint32_t nw = (uint32_t)p.av;
+    const uint32_t words = (nw + 1 + 3) / 4 * 4;
     std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
     const auto& a = p.wv;
-    // relative ring: at source row j slot r holds output row (number of rows completed before j) + r
-    std::vector<uint32_t> done_before(p.in_h + 1, 0u);
-    for (uint32_t j = 0; j < p.in_h; ++j) done_before[j + 1] = done_before[j] + (p.vdone_host[j] & 0xffu);
     for (uint32_t y = 0; y < a.out_size; ++y) {
         const float* w = a.w.data() + a.offset[y];
         for (uint32_t j = a.left[y]; j <= a.right[y]; ++j) {
-            const uint32_t s = y - done_before[j];
-            if (s >= (uint32_t)p.av) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: ring slot %u >= %d", s, p.av);
             uint32_t bits; memcpy(&bits, &w[j - a.left[y]], 4);
-            prog[(size_t)j * words + s] = bits;
+            prog[(size_t)j * words + y % nw] = bits;
         }
     }
-    for (uint32_t j = 0; j < p.in_h; ++j) prog[(size_t)j * words + nw] = p.vdone_host[j];
+    for (uint32_t j = 0; j < p.in_h; ++j) {
+        const uint32_t d = p.vdone_host[j];
+        if (d & 0xffu) prog[(size_t)j * words + nw] = (d & ~0xffu) | (((d >> 8) % nw) << 4) | (d & 0xfu);
+    }
     return prog;
 }
 
@@ -260,7 +264,6 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
     ft->n_strips = (int)ns;
     const int SH = p.sh;
     std::vector<float> hw((size_t)ns * SH * 4 * nt, 0.0f);
-    std::vector<int> hxa((size_t)ns * nt, 0);
     std::vector<uint32_t> hrd((size_t)ns * nt, 0u);
     for (uint32_t s = 0; s < ns; ++s) {
         const StripDev& sd = strips[s];
@@ -271,17 +274,17 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
             uint32_t Xa = Xlo, n = 0;
             for (uint32_t X = Xlo; X < (uint32_t)sd.X1 && h.left[X] <= c1; ++X) ++n;
             if (n > (uint32_t)SH) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: %u outputs in one column group > SH=%d", n, SH);
-            hxa[(size_t)s * nt + t] = (int)(n ? Xa : 0);
             for (uint32_t q = 0; q < n; ++q) {
                 const uint32_t X = Xa + q;
                 const float* w = h.w.data() + h.offset[X];
                 for (uint32_t i = 0; i < 4; ++i) {
                     const uint32_t k = c0 + i;
                     if (k < h.left[X] || k > h.right[X]) continue;
-                    // outputs (q, q+1) are interleaved as float2; an odd last output follows as plain floats
+                    // by partial plane pl = X mod SH: planes (2k, 2k+1) interleaved as float2, an odd last plane as two float2
                     const size_t base = (size_t)s * SH * 4 * nt;
-                    const size_t idx = (q / 2 < (uint32_t)SH / 2) ? 2 * ((size_t)((q / 2) * 4 + i) * nt + t) + (q & 1)
-                                                                  : (size_t)(SH / 2) * 8 * nt + (size_t)i * nt + t;
+                    const uint32_t pl = X % (uint32_t)SH;
+                    const size_t idx = (pl / 2 < (uint32_t)SH / 2) ? 2 * ((size_t)((pl / 2) * 4 + i) * nt + t) + (pl & 1)
+                                                                   : 2 * ((size_t)((SH / 2) * 4 + i / 2) * nt + t) + (i & 1);
                     hw[base + idx] = w[k - h.left[X]];
                 }
             }
@@ -293,7 +296,7 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
         }
     }
     // everything the kernel reads for this (plan, CTA size) goes into one allocation and one asynchronous copy
-    ft->o_strips = ft->blob.add(strips); ft->o_hw = ft->blob.add(hw); ft->o_hxa = ft->blob.add(hxa); ft->o_hrd = ft->blob.add(hrd);
+    ft->o_strips = ft->blob.add(strips); ft->o_hw = ft->blob.add(hw); ft->o_hrd = ft->blob.add(hrd);
     ft->o_vprog[0] = ft->blob.add(fused_vprog_host(p));
     for (int nb = 1; ; nb *= 2) {                        // band tables for power-of-two band counts
         const int use = std::min<int>(nb, (int)std::max<uint32_t>(1u, p.out_h / 8u));
@@ -330,8 +333,8 @@ int pick_bands(const FusedVariantTables& ft, int want) {
 // fused kernel dispatch table
 using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
 struct FusedEntry { int av, sh, ch, nt; FusedFn fn, fn_simple; size_t smem; };
-#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_, false>, \
-                                         fused_down_kernel<AV_, SH_, CH_, kPrefetch, NT_, true>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
+#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, false>, \
+                                         fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, true>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
 #define IFB_FUSED(AV_, SH_) IFB_FUSED_1(AV_, SH_, 3, 256), IFB_FUSED_1(AV_, SH_, 4, 256), IFB_FUSED_1(AV_, SH_, 3, 128), IFB_FUSED_1(AV_, SH_, 4, 128)
 const FusedEntry kFused[] = {
 #ifdef IFB_FEW_SHAPES      /* development builds: only the shapes the 4K->512 benchmarks use */
@@ -364,6 +367,7 @@ struct ifb200_batch {
     std::vector<PinnedSlot> pinned;
     // options
     bool force_generic = false; int nt = 256; int min_ctas = 296;
+    bool ring_ok = true;     // the shared window is laid out as the ring kernel's LUT gather assumes (smem_base_probe_kernel)
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
 
@@ -442,9 +446,18 @@ struct ifb200_batch {
     // build the plans this call needs and the cache lacks, in parallel
     void prebuild_plans(const ifb200_resample_desc* descs, size_t n) {
         std::map<Key, size_t> todo;
-        for (size_t i = 0; i < n; ++i) {
-            const Key k = key_of(descs[i]);
-            if (!plans.count(k)) todo.emplace(k, i);
+        auto collect = [&] {
+            todo.clear();
+            for (size_t i = 0; i < n; ++i) {
+                const Key k = key_of(descs[i]);
+                if (!plans.count(k)) todo.emplace(k, i);
+            }
+        };
+        collect();
+        if (!plans.empty() && plans.size() + todo.size() > kMaxPlans) {   // bound the cache (mixed workloads: thousands of
+            CUDA_OK(cudaDeviceSynchronize());                             // geometries); done before any Plan* of this call is
+            drop_plans();                                                 // taken; kernels in flight may still read the old
+            collect();                                                    // tables, hence the synchronise
         }
         if (todo.size() < 8) return;                      // a few plans: the serial path in plan_for() is fine
         std::vector<std::pair<Key, size_t>> work(todo.begin(), todo.end());
@@ -540,10 +553,6 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     if (n == 0) return;
     host_tables();
     CUDA_OK(cudaSetDevice(b->device));
-    if (b->plans.size() + n > ifb200_batch::kMaxPlans) {   // bound the cache (mixed workloads: thousands of geometries);
-        CUDA_OK(cudaDeviceSynchronize());                  // done before any Plan* of this call is taken; kernels in flight
-        b->drop_plans();                                   // may still read the old tables, hence the synchronise
-    }
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
     b->prebuild_plans(descs, n);
     // group jobs by (plan, kernel class)
@@ -554,7 +563,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         Plan& p = b->plan_for(descs[i]);
         const ifb200_resample_desc& d = descs[i];
         // 16-byte row loads: aligned base and pitch, and the pitch must cover the last (possibly partial) group of 4 pixels
-        bool fused = p.fused_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0) &&
+        bool fused = p.fused_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0) &&
                      (d.in_stride >= ((uint64_t)d.in_w * 4 + 15) / 16 * 16);
         const int ch = d.alpha_meaningful ? 4 : 3;
         if (fused && !find_fused(p.av, p.sh, ch, b->nt)) fused = false;
@@ -611,7 +620,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             pl.n_strips = ft.n_strips; pl.n_bands = nb;
             pl.vprog = ft.blob.at<uint32_t>(ft.o_vprog[0]); pl.strips = ft.blob.at<StripDev>(ft.o_strips);
             pl.bands = ft.blob.at<BandDev>(ft.o_bands.at(nb));
-            pl.hw = ft.blob.at<float>(ft.o_hw); pl.hxa = ft.blob.at<int>(ft.o_hxa); pl.hrd = ft.blob.at<uint32_t>(ft.o_hrd);
+            pl.hw = ft.blob.at<float>(ft.o_hw); pl.hrd = ft.blob.at<uint32_t>(ft.o_hrd);
             const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
             FusedFn fn = g.simple ? fe->fn_simple : fe->fn;
             const size_t smem = fe->smem;
@@ -720,10 +729,28 @@ ifb200_batch* create_batch(int device) {
     std::unique_ptr<ifb200_batch> b(new ifb200_batch());
     b->device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    {   // job arrays and the generic path's intermediates come from the stream-ordered pool: keep its memory across
+        // synchronisation points (the default threshold of 0 returns it to the OS at every synchronise, and the next
+        // call pays tens of milliseconds to get it back)
+        cudaMemPool_t pool;
+        CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     std::vector<float> tl(256), ts(256); std::vector<uint8_t> lut(16384);
     ifb::byte_to_float_table(true, tl.data()); ifb::byte_to_float_table(false, ts.data()); ifb::linear_to_srgb_table(lut.data());
     b->t_lin.upload(tl); b->t_srgb.upload(ts); b->lut16k.upload(lut);
     b->tables = Tables{b->t_lin.p, b->t_srgb.p, b->lut16k.p};
+    {   // the ring kernel folds the shared-window offset of dynamic shared memory into its LUT gather: verify it once
+        DevVec<uint32_t> probe; probe.upload(std::vector<uint32_t>(1, 0xffffffffu));
+        CUDA_OK(cudaFuncSetAttribute((const void*)smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        smem_base_probe_kernel<<<1, 32, 100 * 1024, b->own_stream>>>(probe.p);
+        CUDA_OK(cudaGetLastError());
+        uint32_t got = 0;
+        CUDA_OK(cudaMemcpyAsync(&got, probe.p, 4, cudaMemcpyDeviceToHost, b->own_stream));
+        CUDA_OK(cudaStreamSynchronize(b->own_stream));
+        b->ring_ok = (got & 0xffffu) == kSmemWindowBase;
+    }
     return b.release();
 }
 

@@ -48,12 +48,12 @@ struct FusedPlanDev {
     uint32_t in_w, in_h, out_w, out_h;
     int n_strips, n_bands;
     uint32_t zero;              // always 0 (run-time constant used to order loads after a scoreboard wait)
-    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weights of the open output rows, oldest first (float bits,
-                                //   each duplicated into a pair for FFMA2), then ((first completed y << 8) | count)
+    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weight (float bits) of the output row in each ring slot (row y lives in
+                                //   slot y mod AV), then ((first completed y << 8) | (its slot << 4) | count)
     const StripDev* strips;
     const BandDev* bands;
-    const float* hw;            // [strip][SH*4*NT]: pairs (q,q+1) as float2 at 2*((qp*4+i)*NT+t), odd last q as floats after them
-    const int* hxa;             // [strip][NT] first output column touched by thread t's 4 columns
+    const float* hw;            // [strip][SH*4*NT]: H weights of thread t by partial plane p = output column mod SH and own column i:
+                                //   p < 2*(SH/2): word 2*(((p/2)*4+i)*NT+t) + (p&1); odd last plane: word 2*(((SH/2)*4+i/2)*NT+t) + (i&1)
     const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12) | ((X mod SH) << 28)
 };
 
@@ -81,11 +81,11 @@ __device__ __forceinline__ uint32_t encode(bool linear, const uint8_t* __restric
 // SIMPLE = true: the caller guarantees compose == ReplaceSelf and no colour matrix (the common thumbnail case);
 // the composite / matte / matrix code is then not even compiled into the kernel.
 template <bool SIMPLE = false>
-__device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, float a, const JobDev& job,
+__device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, float a, const uint32_t flags, const JobDev& job,
                                                  const Tables& tb, const uint8_t* dst) {
-    const bool linear = job.flags & JF_LINEAR;
-    const bool am = job.flags & JF_ALPHA;
-    const uint32_t compose = SIMPLE ? 0u : (job.flags >> JF_COMPOSE_SHIFT) & 3u;
+    const bool linear = flags & JF_LINEAR;
+    const bool am = flags & JF_ALPHA;
+    const uint32_t compose = SIMPLE ? 0u : (flags >> JF_COMPOSE_SHIFT) & 3u;
     uint32_t ob, og, orr, oa;
     if (compose == 1u) {                                   // BlendWithSelf: scaling.rs:254-287
         if (a > 0.994f || !am) {
@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, floa
         ob = encode(linear, tb.lut16k, b); og = encode(linear, tb.lut16k, g); orr = encode(linear, tb.lut16k, r);
         oa = uchar_clamp_ff(__fmul_rn(a, 255.0f));
     }
-    if (!SIMPLE && (job.flags & JF_CM)) {                  // color_matrix.rs:5-28, on sRGB bytes
+    if (!SIMPLE && (flags & JF_CM)) {                  // color_matrix.rs:5-28, on sRGB bytes
         const float fr = (float)orr, fg = (float)og, fb = (float)ob, fa = (float)oa;
         const float* m = job.cm;
         auto row = [&](int c) {
@@ -128,6 +128,10 @@ __device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, floa
         orr = row(0); og = row(1); ob = row(2); oa = row(3);
     }
     return ob | (og << 8) | (orr << 16) | (oa << 24);
+}
+template <bool SIMPLE = false>
+__device__ __forceinline__ uint32_t finish_pixel(float b, float g, float r, float a, const JobDev& job, const Tables& tb, const uint8_t* dst) {
+    return finish_pixel<SIMPLE>(b, g, r, a, job.flags, job, tb, dst);
 }
 
 // ---------------------------------------------------------------- generic two-kernel path
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(256) apply_matte_kernel(uint8_t* __restrict__ 
 //   pass 1 (V): streams source rows top to bottom straight from HBM into registers (one 16-byte load
 //               per row, PF rows in flight per thread), converts through a bank-conflict-free
 //               (lane-replicated) shared-memory LUT once, and accumulates into a ring of AV register
-//               accumulators (one per output row whose window covers the current source row).  The
-//               per-row "program" (ring weights + which output rows complete) is streamed through a
+//               accumulators: output row y lives in slot y mod AV for as long as its window is open.  The
+//               per-row "program" (slot weights + which output rows complete) is streamed through a
 //               double-buffered shared-memory chunk with cp.async.
 //   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its H weights into <= SH
 //               per-output partial sums and parks them in shared memory; after one __syncthreads thread u sums
@@ -326,12 +330,19 @@ __global__ void __launch_bounds__(256) apply_matte_kernel(uint8_t* __restrict__ 
 //               alternating halves of the CTA, so one barrier per output row suffices.
 // Every source pixel is read from HBM once (plus strip/band halos), converted once, and the
 // V-filtered intermediate never leaves the SM.
+//
+// Shared memory is addressed through explicit ld/st.shared with 32-bit window addresses held in registers: every
+// hot-loop access is `[register + immediate]`, nothing is recomputed per row.
 constexpr int kProgChunk = 32;                       // source rows per program chunk
 constexpr int kLutBytes = 256 * 256;                 // LUT region: 256 rows of 256 B (see below)
+// Offset of a CTA's dynamic shared memory inside the shared window (1 KB is reserved by the system on sm_90+).  The LUT
+// gather folds it into the immediate field of the load; the engine checks it with smem_base_probe_kernel before it
+// ever launches a fused kernel, and uses the other kernels if a driver should lay shared memory out differently.
+constexpr uint32_t kSmemWindowBase = 0x400u;
 
 template <int AV> struct ProgLayout {
-    static constexpr int kW = AV;                    // weight words (FFMA2 takes the weight as a broadcast scalar operand)
-    static constexpr int kDone = kW;                 // index of the completion word
+    static constexpr int kW = AV;                    // weight words, by ring slot (FFMA2 takes the weight as a broadcast scalar operand)
+    static constexpr int kDone = kW;                 // index of the completion word: (first completed y << 8) | (its slot << 4) | count
     static constexpr int kWords = (kW + 1 + 3) / 4 * 4;
 };
 
@@ -341,39 +352,56 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// A value the compiler must keep in a register (it cannot re-derive it, so it cannot rematerialise it per use).
+__device__ __forceinline__ uint32_t pinned_reg(uint32_t x) { uint32_t y; asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint64_t pinned_reg64(uint64_t x) { uint64_t y; asm volatile("mov.b64 %0, %1;" : "=l"(y) : "l"(x)); return y; }
+// read-only-after-setup table gather (may be scheduled freely: its operands depend on the pixel just loaded)
+__device__ __forceinline__ float lds_table(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+__global__ void smem_base_probe_kernel(uint32_t* out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(smem_raw);
+}
+
 // Shared-memory map of the fused kernel.
 //   [0, 64 KB)   row v (256 B): bytes 0..127 = T[v] replicated for the 32 lanes, so the byte address of a lookup is
 //                (v << 8) | (lane << 2): ONE PRMT builds it from the packed pixel, and the gather is bank-conflict
 //                free for any image content.  Bytes 128..255 of the rows ("holes") hold the strip's H weights:
-//                word w of the H-weight block (see the completion code) lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2).
-//   then         row-program double buffer, partial sums (2 x CH x SH x NT floats), per-thread reader meta.
+//                word w of the H-weight block (see FusedPlanDev::hw) lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2),
+//                which puts pair k of thread t at hole_base(t) + k * 16 * NT.
+//   then         row-program double buffer, partial sums (2 x CH x SH x NT floats).
 template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kProgBytes = 2 * kProgChunk * ProgLayout<AV>::kWords * 4;
-    static constexpr int kPartBytes = 2 * CH * SH * NT * 4;
+    static constexpr int kPartBuf = CH * SH * NT * 4;           // one partial-sum buffer
     static constexpr int kProgOff = kLutBytes;
     static constexpr int kPartOff = kProgOff + kProgBytes;
-    static constexpr int kMetaOff = kPartOff + kPartBytes;
-    static constexpr int kTotal = kMetaOff + NT * 4;
-    static_assert(SH * 4 * NT / 32 <= 256, "H weights must fit in the LUT holes");
+    static constexpr int kTotal = kPartOff + 2 * kPartBuf;
+    static constexpr int kHwPairs = (SH / 2) * 4 + (SH & 1) * 2; // float2 pairs of H weights per thread
+    static_assert(kHwPairs * 2 * NT / 32 <= 256, "H weights must fit in the LUT holes");
 };
-
-// address of word w of the data parked in the LUT holes
-__device__ __forceinline__ const unsigned char* hole_ptr(const unsigned char* sLut, int w) {
-    return sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2);
-}
 
 template <int AV, int SH, int CH, int PF, int NT, bool SIMPLE>
 __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
     using PL = ProgLayout<AV>;
     using SM = FusedSmem<AV, SH, CH, NT>;
     constexpr int NV = 4 * CH;                      // working floats per thread per row, channel-planar: [c][pixel]
+    constexpr int kRec = PL::kWords * 4;            // bytes per program record
     static_assert(2 * PF <= 12, "ring positions");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x;
     unsigned char* sLut = smem_raw;
     uint32_t* sProg = reinterpret_cast<uint32_t*>(smem_raw + SM::kProgOff);
-    float* sPart = reinterpret_cast<float*>(smem_raw + SM::kPartOff);
-    uint32_t* sMeta = reinterpret_cast<uint32_t*>(smem_raw + SM::kMetaOff);
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    if ((sb & 0xffffu) != kSmemWindowBase) __trap();      // never taken: the engine probes the layout before using this kernel
 
     const JobDev& job = jobs[blockIdx.y];
     const int strip = blockIdx.x % pl.n_strips;
@@ -385,14 +413,27 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
         const float* __restrict__ T = (job.flags & JF_LINEAR) ? tb.t_lin : tb.t_srgb;
         for (int i = t; i < 256 * 32; i += NT)
             *reinterpret_cast<float*>(sLut + ((i >> 5) << 8) + ((i & 31) << 2)) = __ldg(T + (i >> 5));
-        for (int w = t; w < SH * 4 * NT; w += NT)
+        for (int w = t; w < SM::kHwPairs * 2 * NT; w += NT)
             *reinterpret_cast<float*>(sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2)) = __ldg(pl.hw + (size_t)strip * SH * 4 * NT + w);
     }
-    sMeta[t] = __ldg(pl.hrd + strip * NT + t) | ((uint32_t)(__ldg(pl.hxa + strip * NT + t) % SH) << 24);
+    // ---- per-thread constants, pinned in registers
     // outputs of this strip are finished by alternating halves of the CTA when they fit in one half
     const int NX = sd.X1 - sd.X0;
     const bool alternate = NX <= NT / 2;
     const int my_half = t / (NT / 2);
+    const int u = alternate ? t - my_half * (NT / 2) : t;             // output column of the strip this thread finishes
+    // bit p of fin: this thread finishes the rows emitted into partial buffer p
+    const uint32_t fin = u < NX ? (alternate ? (1u << my_half) : 3u) : 0u;
+    const uint32_t rmeta = __ldg(pl.hrd + strip * NT + (u < NX ? u : 0));
+    // partial (c, plane, thread) is the float at kPartOff + buffer * kPartBuf + ((c * SH + plane) * NT + thread) * 4
+    const uint32_t rd_base = sb + SM::kPartOff + ((rmeta >> 28) * NT + (rmeta & 0xfffu)) * 4u;
+    const uint32_t rd_groups = (rmeta >> 12) & 0xfffu;
+    const uint32_t wr_base = sb + SM::kPartOff + (uint32_t)t * 4u;
+    const uint32_t hw_base = sb + (((uint32_t)t >> 4) << 8) + 128u + (((uint32_t)t & 15u) << 3);
+    const uint32_t lane4 = pinned_reg(((uint32_t)(t & 31) * 4u) | ((sb >> 16) << 8));   // PRMT operand: low byte + window bits 16..31
+    const uint32_t flags = job.flags;
+    uint8_t* const out_col = job.out + (size_t)(sd.X0 + u) * 4;
+    const uint32_t out_stride = job.out_stride;
 
     // program chunk 0
     const uint32_t* __restrict__ gprog = pl.vprog + (size_t)bd.j0 * PL::kWords;
@@ -409,9 +450,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     if (col > (int)((pl.in_w - 1) & ~3u)) col = (int)((pl.in_w - 1) & ~3u);
     const size_t stride = job.in_stride;
     const uint8_t* __restrict__ pnext = job.in + (size_t)col * 4 + (size_t)bd.j0 * stride;
-    int jnext = bd.j0;
+    int left = total_rows;                          // source rows not requested yet, counting the one pnext points at (>= 1)
 
-    // acc[r] belongs to the r-th oldest output row still open (relative ring: completing a row shifts it)
+    // acc[s]: output row y with y mod AV == s, while its window is open
     float acc[AV][NV];
 #pragma unroll
     for (int s = 0; s < AV; ++s)
@@ -421,20 +462,27 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     // Source rows in flight: two register sets of PF rows.  While set A is consumed, the PF loads of set B are
     // outstanding (and vice versa).  All loads share one hardware scoreboard, and a scoreboard wait drains every
     // load issued before it, so the next set is only requested after the current one has landed: the prefetch
-    // distance is PF rows of work.
+    // distance is PF rows of work.  Past the last row of the band the last row is requested again (never consumed).
     uint4 pf[2][PF];
+    auto request_set = [&](uint4 (&dst)[PF]) {
+        if (left > PF) {
 #pragma unroll
-    for (int d = 0; d < PF; ++d) {
-        pf[0][d] = __ldcs(reinterpret_cast<const uint4*>(pnext));
-        if (jnext < bd.j1) { pnext += stride; ++jnext; }
-    }
-    int nrow = 0;
+            for (int i = 0; i < PF; ++i) { dst[i] = __ldcs(reinterpret_cast<const uint4*>(pnext)); pnext += stride; }
+            left -= PF;
+        } else {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                dst[i] = __ldcs(reinterpret_cast<const uint4*>(pnext));
+                if (left > 1) { pnext += stride; --left; }
+            }
+        }
+    };
+    request_set(pf[0]);
     int ring_pos = 0;
-    const uint32_t lane4 = (uint32_t)(t & 31) * 4u;
+    uint32_t par = 0;                               // partial buffer of the next emitted row
 
     for (int c0 = 0; c0 < total_rows; c0 += kProgChunk) {
         const int chunk = c0 / kProgChunk;
-        const uint32_t* prog = sProg + (chunk & 1) * kProgChunk * PL::kWords;
         {   // stream the next program chunk while this one is consumed
             const int rows_next = min(kProgChunk, total_rows - (c0 + kProgChunk));
             if (rows_next > 0) {
@@ -443,8 +491,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                 for (int i = t; i < rows_next * PL::kWords / 4; i += NT) cp_async16(dst + i * 4, srcp + i * 4);
             }
         }
-        const int rows_here = min(kProgChunk, total_rows - c0);
-        int r = 0;
+        uint32_t pa = sb + SM::kProgOff + (uint32_t)(chunk & 1) * (kProgChunk * kRec);      // next program record
+        const uint32_t pa_end = pa + (uint32_t)min(kProgChunk, total_rows - c0) * kRec;
         // One source row (ring position D of 2*PF): LUT-convert, accumulate; at a set boundary request the next set.
         // Returns the completion word of the row (0 = no output row completes here).
         auto do_row = [&](auto dtag) -> uint32_t {
@@ -454,25 +502,29 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             if (IDX == 0) {                       // set SET has landed: request the other set
                 // pl.zero is 0 at run time; tying the address to the data just consumed keeps the compiler from
                 // issuing these loads ahead of the scoreboard wait for the current set (see the comment at pf[]).
-                const uint8_t* __restrict__ pdep = pnext + (raw.x & pl.zero);
-                pnext = pdep;
-#pragma unroll
-                for (int i = 0; i < PF; ++i) {
-                    pf[SET ^ 1][i] = __ldcs(reinterpret_cast<const uint4*>(pnext));
-                    if (jnext < bd.j1) { pnext += stride; ++jnext; }
-                }
+                pnext = pnext + (raw.x & pl.zero);
+                request_set(pf[SET ^ 1]);
             }
-            const uint32_t* rec = prog + r * PL::kWords;
-            ++r;
-            // ---- sRGB bytes -> working floats: address = (byte << 8) | (lane << 2), one PRMT per lookup
+            // ---- program record: AV slot weights, then the completion word
+            uint32_t rec[PL::kWords];
+            {
+                const uint4 q = lds_u32x4(pa);
+                rec[0] = q.x; rec[1] = q.y; rec[2] = q.z; rec[3] = q.w;
+                if (PL::kWords > 4) {
+                    if (AV + 1 - 4 == 1) rec[4] = lds_u32(pa + 16);
+                    else { const uint4 q2 = lds_u32x4(pa + 16); rec[4] = q2.x; rec[5] = q2.y; rec[6] = q2.z; rec[7] = q2.w; }
+                }
+                pa += kRec;
+            }
+            // ---- sRGB bytes -> working floats: window address = (byte << 8) | (lane << 2), one PRMT per lookup
             float p[NV];
             const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint32_t v = w4[i];
-                p[0 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6504));
-                p[1 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6514));
-                p[2 * 4 + i] = *reinterpret_cast<const float*>(sLut + __byte_perm(v, lane4, 0x6524));
+                p[0 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6504) + kSmemWindowBase);
+                p[1 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6514) + kSmemWindowBase);
+                p[2 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6524) + kSmemWindowBase);
                 if (CH == 4) {
                     // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
                     const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
@@ -497,83 +549,98 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
         };
         // The 2*PF ring positions are copies of do_row; the completion code below exists once: a row that completes
         // output rows breaks out of the switch, and the loop re-enters at the next ring position.
-        while (r < rows_here) {
+        while (pa != pa_end) {
             uint32_t dn = 0;
             switch (ring_pos) {
 #define IFB_ROW_CASE(D_) \
-            case D_: if (D_ < 2 * PF) { dn = do_row(std::integral_constant<int, (D_) % (2 * PF)>{}); ring_pos = ((D_) + 1) % (2 * PF); if (dn || r >= rows_here) break; }
+            case D_: if (D_ < 2 * PF) { dn = do_row(std::integral_constant<int, (D_) % (2 * PF)>{}); ring_pos = ((D_) + 1) % (2 * PF); if (dn || pa == pa_end) break; }
             IFB_ROW_CASE(0) IFB_ROW_CASE(1) IFB_ROW_CASE(2) IFB_ROW_CASE(3) IFB_ROW_CASE(4) IFB_ROW_CASE(5) IFB_ROW_CASE(6) IFB_ROW_CASE(7)
             IFB_ROW_CASE(8) IFB_ROW_CASE(9) IFB_ROW_CASE(10) IFB_ROW_CASE(11)
 #undef IFB_ROW_CASE
             default: ring_pos = 0; break;
             }
-            // ---- completed output rows: always the oldest (acc[0]); then the ring shifts down
-            const int ndone = dn & 0xffu;
-            for (int e = 0; e < ndone; ++e) {
-                const int y = (int)(dn >> 8) + e;
-                if (y >= bd.Y0 && y < bd.Y1) {                        // else: halo row of a neighbouring band
-                    const int par = nrow & 1;
-                    float* pb = sPart + par * (CH * SH) * NT;
-                    {
-                        // H weights of this thread: output pairs (q, q+1) as float2 at word 2*((qp*4+i)*NT + t), the odd
-                        // last output as floats after them; FFMA2 takes the V value as a broadcast scalar operand.
-                        int poff = (int)((sMeta[t] >> 24) & 7u) * NT + t;   // plane (X mod SH) of this thread's first output
-                        auto next_plane = [&]() { poff += NT; if (poff >= SH * NT) poff -= SH * NT; };
+            // ---- completed output rows: consecutive y, consecutive slots
+            const int ndone = dn & 0xfu;
+            int slot = (dn >> 4) & 0xfu;
+            // H pass, first half: the finished V row (ring slot `v`) times this thread's H weights, by partial plane (output
+            // column mod SH): planes (2k, 2k+1) as float2 pairs -- FFMA2 takes the V value as a broadcast scalar operand --
+            // and an odd last plane as two float2.  One copy of this code per ring slot: the row is consumed where it lies.
+            auto emit = [&](float (&v)[NV]) {
+                const uint32_t wr = wr_base + par * SM::kPartBuf;
 #pragma unroll
-                        for (int qp = 0; qp < SH / 2; ++qp) {
-                            float2 h[4];
+                for (int qp = 0; qp < SH / 2; ++qp) {
+                    float2 h[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) h[i] = *reinterpret_cast<const float2*>(hole_ptr(sLut, 2 * ((qp * 4 + i) * NT + t)));
-                            const int p0 = poff; next_plane();
-                            const int p1 = poff; next_plane();
+                    for (int i = 0; i < 4; ++i) h[i] = lds_f32x2(hw_base + (qp * 4 + i) * 16 * NT);
 #pragma unroll
-                            for (int c = 0; c < CH; ++c) {
-                                float2 ps = make_float2(0.0f, 0.0f);
+                    for (int c = 0; c < CH; ++c) {
+                        float2 ps = make_float2(0.0f, 0.0f);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) { const float v = acc[0][c * 4 + i]; ps = __ffma2_rn(h[i], make_float2(v, v), ps); }
-                                pb[c * SH * NT + p0] = ps.x;
-                                pb[c * SH * NT + p1] = ps.y;
-                            }
-                        }
-                        if (SH & 1) {
-                            float h[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) h[i] = *reinterpret_cast<const float*>(hole_ptr(sLut, (SH / 2) * 8 * NT + i * NT + t));
-#pragma unroll
-                            for (int c = 0; c < CH; ++c) {
-                                float ps = __fmaf_rn(h[0], acc[0][c * 4 + 0], 0.0f);
-                                ps = __fmaf_rn(h[1], acc[0][c * 4 + 1], ps);
-                                ps = __fmaf_rn(h[2], acc[0][c * 4 + 2], ps);
-                                ps = __fmaf_rn(h[3], acc[0][c * 4 + 3], ps);
-                                pb[c * SH * NT + poff] = ps;
-                            }
-                        }
+                        for (int i = 0; i < 4; ++i) { const float x = v[c * 4 + i]; ps = __ffma2_rn(h[i], make_float2(x, x), ps); }
+                        sts_f32(wr + ((c * SH + 2 * qp) * NT) * 4, ps.x);
+                        sts_f32(wr + ((c * SH + 2 * qp + 1) * NT) * 4, ps.y);
                     }
-                    __syncthreads();
-                    const int u = alternate ? t - par * (NT / 2) : t;
-                    if (u >= 0 && u < NX && (!alternate || my_half == par)) {
-                        const uint32_t meta = sMeta[u];
-                        const int X = sd.X0 + u;
-                        const int plane = (int)(meta >> 28);                // X mod SH, precomputed on the host
-                        const int tg0 = meta & 0xfffu, ng = (meta >> 12) & 0xfffu;
-                        const float* pr = pb + plane * NT + tg0;
-                        float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-                        for (int g = 0; g < ng; ++g) {
+                }
+                if (SH & 1) {
+                    const float2 h01 = lds_f32x2(hw_base + ((SH / 2) * 4 + 0) * 16 * NT);
+                    const float2 h23 = lds_f32x2(hw_base + ((SH / 2) * 4 + 1) * 16 * NT);
 #pragma unroll
-                            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], pr[c * SH * NT + g]);
-                        }
-                        uint8_t* dst = job.out + (size_t)y * job.out_stride + (size_t)X * 4;
-                        *reinterpret_cast<uint32_t*>(dst) = finish_pixel<SIMPLE>(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, job, tb, dst);
+                    for (int c = 0; c < CH; ++c) {
+                        float ps = __fmaf_rn(h01.x, v[c * 4 + 0], 0.0f);
+                        ps = __fmaf_rn(h01.y, v[c * 4 + 1], ps);
+                        ps = __fmaf_rn(h23.x, v[c * 4 + 2], ps);
+                        ps = __fmaf_rn(h23.y, v[c * 4 + 3], ps);
+                        sts_f32(wr + ((c * SH + SH - 1) * NT) * 4, ps);
                     }
-                    ++nrow;
                 }
 #pragma unroll
-                for (int s = 0; s + 1 < AV; ++s)
+                for (int k = 0; k < NV; ++k) v[k] = 0.0f;             // the slot is free for output row y + AV
+            };
+            for (int e = 0; e < ndone; ++e) {
+                const int y = (int)(dn >> 8) + e;
+                const int cur = slot;
+                slot = slot + 1 == AV ? 0 : slot + 1;
+                if (y >= bd.Y0 && y < bd.Y1) {
+                    switch (cur) {
+#define IFB_SLOT_CASE(S_) case S_: if (S_ < AV) emit(acc[(S_) % AV]); break;
+                    IFB_SLOT_CASE(0) IFB_SLOT_CASE(1) IFB_SLOT_CASE(2) IFB_SLOT_CASE(3) IFB_SLOT_CASE(4) IFB_SLOT_CASE(5)
+#undef IFB_SLOT_CASE
+                    default: break;
+                    }
+                    __syncthreads();
+                    if ((fin >> par) & 1u) {
+                        uint32_t a = rd_base + par * SM::kPartBuf;
+                        float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        int n = (int)rd_groups;
+                        for (; n >= 4; n -= 4, a += 16) {
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) acc[s][k] = acc[s + 1][k];
+                            for (int g = 0; g < 4; ++g)
 #pragma unroll
-                for (int k = 0; k < NV; ++k) acc[AV - 1][k] = 0.0f;
+                                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
+                        }
+                        if (n & 2) {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
+                            a += 8;
+                        }
+                        if (n & 1) {
+#pragma unroll
+                            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT) * 4));
+                        }
+                        uint8_t* dst = out_col + (size_t)y * out_stride;
+                        *reinterpret_cast<uint32_t*>(dst) = finish_pixel<SIMPLE>(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, flags, job, tb, dst);
+                    }
+                    par ^= 1u;
+                } else {                                              // halo row of a neighbouring band: only free the slot
+                    switch (cur) {
+#define IFB_SLOT_CASE(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int k = 0; k < NV; ++k) acc[(S_) % AV][k] = 0.0f; } break;
+                    IFB_SLOT_CASE(0) IFB_SLOT_CASE(1) IFB_SLOT_CASE(2) IFB_SLOT_CASE(3) IFB_SLOT_CASE(4) IFB_SLOT_CASE(5)
+#undef IFB_SLOT_CASE
+                    default: break;
+                    }
+                }
             }
         }
         cp_async_wait_all();
