@@ -367,6 +367,21 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
+// Split barrier on a shared-memory mbarrier: a warp announces "my partials of this row are parked" without waiting
+// (arrive has release semantics), and only waits -- one completion later -- for all warps to have done so.
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t addr) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "IFB_MBAR_WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra IFB_MBAR_WAIT_%=;\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+
 __global__ void smem_base_probe_kernel(uint32_t* out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -384,7 +399,8 @@ template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kPartBuf = CH * SH * NT * 4;           // one partial-sum buffer
     static constexpr int kProgOff = kLutBytes;
     static constexpr int kPartOff = kProgOff + kProgBytes;
-    static constexpr int kTotal = kPartOff + 2 * kPartBuf;
+    static constexpr int kBarOff = kPartOff + 2 * kPartBuf;      // two 8-byte mbarriers (one per partial buffer)
+    static constexpr int kTotal = kBarOff + 16;
     static constexpr int kHwPairs = (SH / 2) * 4 + (SH & 1) * 2; // float2 pairs of H weights per thread
     static_assert(kHwPairs * 2 * NT / 32 <= 256, "H weights must fit in the LUT holes");
 };
@@ -435,6 +451,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     uint8_t* const out_col = job.out + (size_t)(sd.X0 + u) * 4;
     const uint32_t out_stride = job.out_stride;
 
+    if (t == 0) { mbar_init(sb + SM::kBarOff, NT / 32); mbar_init(sb + SM::kBarOff + 8, NT / 32); }   // one arrival per warp
     // program chunk 0
     const uint32_t* __restrict__ gprog = pl.vprog + (size_t)bd.j0 * PL::kWords;
     const int total_rows = bd.j1 - bd.j0 + 1;
@@ -479,7 +496,36 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     };
     request_set(pf[0]);
     int ring_pos = 0;
-    uint32_t par = 0;                               // partial buffer of the next emitted row
+    uint32_t buf = 0;                               // partial buffer (and mbarrier) of the next emitted row == nrow & 1
+    uint32_t nrow = 0;                              // rows emitted so far
+    int yprev = 0;                                  // the emitted row that is not finished yet (nrow > 0)
+    const uint32_t bar_base = sb + SM::kBarOff;
+
+    // H pass, second half: thread u adds the partials of output column X0+u in ascending group order, then the store epilogue
+    auto finish = [&](const int y, const uint32_t b) {
+        uint32_t a = rd_base + b * SM::kPartBuf;
+        float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        int n = (int)rd_groups;
+        for (; n >= 4; n -= 4, a += 16) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
+        }
+        if (n & 2) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
+            a += 8;
+        }
+        if (n & 1) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT) * 4));
+        }
+        uint8_t* dst = out_col + (size_t)y * out_stride;
+        *reinterpret_cast<uint32_t*>(dst) = finish_pixel<SIMPLE>(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, flags, job, tb, dst);
+    };
 
     for (int c0 = 0; c0 < total_rows; c0 += kProgChunk) {
         const int chunk = c0 / kProgChunk;
@@ -566,7 +612,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             // column mod SH): planes (2k, 2k+1) as float2 pairs -- FFMA2 takes the V value as a broadcast scalar operand --
             // and an odd last plane as two float2.  One copy of this code per ring slot: the row is consumed where it lies.
             auto emit = [&](float (&v)[NV]) {
-                const uint32_t wr = wr_base + par * SM::kPartBuf;
+                const uint32_t wr = wr_base + buf * SM::kPartBuf;
 #pragma unroll
                 for (int qp = 0; qp < SH / 2; ++qp) {
                     float2 h[4];
@@ -601,38 +647,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                 const int cur = slot;
                 slot = slot + 1 == AV ? 0 : slot + 1;
                 if (y >= bd.Y0 && y < bd.Y1) {
+                    // Finish the row emitted at the previous completion: every warp parked its partials a row ago, so the
+                    // wait rarely blocks, and warps only need to stay within one output row of each other.
+                    if (nrow) {
+                        mbar_wait(bar_base + (buf ^ 1u) * 8u, ((nrow - 1u) >> 1) & 1u);
+                        if ((fin >> (buf ^ 1u)) & 1u) finish(yprev, buf ^ 1u);
+                    }
                     switch (cur) {
 #define IFB_SLOT_CASE(S_) case S_: if (S_ < AV) emit(acc[(S_) % AV]); break;
                     IFB_SLOT_CASE(0) IFB_SLOT_CASE(1) IFB_SLOT_CASE(2) IFB_SLOT_CASE(3) IFB_SLOT_CASE(4) IFB_SLOT_CASE(5)
 #undef IFB_SLOT_CASE
                     default: break;
                     }
-                    __syncthreads();
-                    if ((fin >> par) & 1u) {
-                        uint32_t a = rd_base + par * SM::kPartBuf;
-                        float F[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                        int n = (int)rd_groups;
-                        for (; n >= 4; n -= 4, a += 16) {
-#pragma unroll
-                            for (int g = 0; g < 4; ++g)
-#pragma unroll
-                                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
-                        }
-                        if (n & 2) {
-#pragma unroll
-                            for (int g = 0; g < 2; ++g)
-#pragma unroll
-                                for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT + g) * 4));
-                            a += 8;
-                        }
-                        if (n & 1) {
-#pragma unroll
-                            for (int c = 0; c < CH; ++c) F[c] = __fadd_rn(F[c], lds_f32(a + (c * SH * NT) * 4));
-                        }
-                        uint8_t* dst = out_col + (size_t)y * out_stride;
-                        *reinterpret_cast<uint32_t*>(dst) = finish_pixel<SIMPLE>(F[0], F[1], F[2], CH == 4 ? F[3] : 0.0f, flags, job, tb, dst);
-                    }
-                    par ^= 1u;
+                    __syncwarp();
+                    if ((t & 31) == 0) mbar_arrive(bar_base + buf * 8u);
+                    yprev = y;
+                    ++nrow;
+                    buf ^= 1u;
                 } else {                                              // halo row of a neighbouring band: only free the slot
                     switch (cur) {
 #define IFB_SLOT_CASE(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int k = 0; k < NV; ++k) acc[(S_) % AV][k] = 0.0f; } break;
@@ -645,6 +676,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
         }
         cp_async_wait_all();
         __syncthreads();
+    }
+    if (nrow) {                                                       // the last emitted row of the band
+        mbar_wait(bar_base + (buf ^ 1u) * 8u, ((nrow - 1u) >> 1) & 1u);
+        if ((fin >> (buf ^ 1u)) & 1u) finish(yprev, buf ^ 1u);
     }
 }
 
