@@ -351,6 +351,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async16_to(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// TMA-style L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): no register, no scoreboard
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // A value the compiler must keep in a register (it cannot re-derive it, so it cannot rematerialise it per use).
 __device__ __forceinline__ uint32_t pinned_reg(uint32_t x) { uint32_t y; asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
@@ -393,14 +402,21 @@ __global__ void smem_base_probe_kernel(uint32_t* out) {
 //                free for any image content.  Bytes 128..255 of the rows ("holes") hold the strip's H weights:
 //                word w of the H-weight block (see FusedPlanDev::hw) lives at ((w >> 5) << 8) + 128 + ((w & 31) << 2),
 //                which puts pair k of thread t at hole_base(t) + k * 16 * NT.
-//   then         row-program double buffer, partial sums (2 x CH x SH x NT floats).
+//   then         row-program double buffer, partial sums (2 x CH x SH x NT floats), two mbarriers.
+//   then         row stages: ST x NT x 16 B, each thread's private FIFO of source rows in flight (cp.async), when it fits.
+constexpr int kSmemPerCtaFor2 = 113 * 1024;          // 228 KB per SM, 1 KB reserved per CTA: two CTAs of this size fit
 template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kProgBytes = 2 * kProgChunk * ProgLayout<AV>::kWords * 4;
     static constexpr int kPartBuf = CH * SH * NT * 4;           // one partial-sum buffer
     static constexpr int kProgOff = kLutBytes;
     static constexpr int kPartOff = kProgOff + kProgBytes;
     static constexpr int kBarOff = kPartOff + 2 * kPartBuf;      // two 8-byte mbarriers (one per partial buffer)
-    static constexpr int kTotal = kBarOff + 16;
+    static constexpr int kStageOff = kBarOff + 16;
+    static constexpr int kRowStage = NT * 16;
+    // stages that fit next to a second CTA (at least 3, at most 6), else 0: the kernel then prefetches into registers
+    static constexpr int kFit = (kSmemPerCtaFor2 - kStageOff) / kRowStage;
+    static constexpr int kStages = kFit >= 3 ? (kFit > 6 ? 6 : kFit) : 0;
+    static constexpr int kTotal = kStageOff + kStages * kRowStage;
     static constexpr int kHwPairs = (SH / 2) * 4 + (SH & 1) * 2; // float2 pairs of H weights per thread
     static_assert(kHwPairs * 2 * NT / 32 <= 256, "H weights must fit in the LUT holes");
 };
@@ -411,7 +427,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     using SM = FusedSmem<AV, SH, CH, NT>;
     constexpr int NV = 4 * CH;                      // working floats per thread per row, channel-planar: [c][pixel]
     constexpr int kRec = PL::kWords * 4;            // bytes per program record
-    static_assert(2 * PF <= 12, "ring positions");
+    constexpr int ST = SM::kStages;                 // > 0: source rows are staged through shared memory, PF is not used
+    constexpr int RING = ST > 0 ? ST : 2 * PF;      // unrolled copies of the row code
+    static_assert(RING <= 12, "ring positions");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x;
     unsigned char* sLut = smem_raw;
@@ -476,16 +494,33 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
 #pragma unroll
         for (int i = 0; i < NV; ++i) acc[s][i] = 0.0f;
 
-    // Source rows in flight: two register sets of PF rows.  While set A is consumed, the PF loads of set B are
-    // outstanding (and vice versa).  All loads share one hardware scoreboard, and a scoreboard wait drains every
-    // load issued before it, so the next set is only requested after the current one has landed: the prefetch
-    // distance is PF rows of work.  Past the last row of the band the last row is requested again (never consumed).
-    uint4 pf[2][PF];
-    auto request_set = [&](uint4 (&dst)[PF]) {
+    // bytes of a source row this CTA reads (thread 0's pointer is the start of the segment); rows are padded to 16 bytes
+    const uint32_t seg_bytes = min((uint32_t)NT * 16u, ((pl.in_w * 4u + 15u) & ~15u) - (uint32_t)sd.k0 * 4u);
+    // Source rows in flight.
+    // ST > 0: each thread owns a FIFO of ST 16-byte slots in shared memory; row i+ST-1 is requested (cp.async, L1 bypass)
+    //   when row i is consumed, and cp.async groups are counted, so ST-1 rows stay in flight per thread at no register
+    //   cost.  One thread also asks L2 for the CTA's rows ST..2ST-1 further ahead (bulk prefetch), so that the cp.async
+    //   requests are L2 hits.
+    // ST == 0 (the stages do not fit next to a second CTA): two register sets of PF rows.  While set A is consumed the PF
+    //   loads of set B are outstanding (and vice versa).  All loads share one hardware scoreboard and a scoreboard wait
+    //   drains every load issued before it, so the next set is only requested after the current one has landed.
+    // Past the last row of the band the last row is requested again (never consumed).
+    uint4 pf[2][ST > 0 ? 1 : PF];
+    const uint32_t st_base = sb + SM::kStageOff + (uint32_t)t * 16u;
+    auto request_row = [&](const int stage) {
+        cp_async16_to(st_base + stage * SM::kRowStage, pnext);
+        cp_async_commit();
+        if (left > 1) { pnext += stride; --left; }
+    };
+    auto request_set = [&](uint4 (&dst)[ST > 0 ? 1 : PF]) {
         if (left > PF) {
 #pragma unroll
             for (int i = 0; i < PF; ++i) { dst[i] = __ldcs(reinterpret_cast<const uint4*>(pnext)); pnext += stride; }
             left -= PF;
+            if (t == 0 && left >= PF) {                   // the set after this one: on its way into L2
+#pragma unroll
+                for (int i = 0; i < PF; ++i) l2_prefetch_bulk(pnext + (size_t)i * stride, seg_bytes);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < PF; ++i) {
@@ -494,7 +529,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             }
         }
     };
-    request_set(pf[0]);
+    if (ST > 0) {
+#pragma unroll
+        for (int i = 0; i + 1 < ST; ++i) request_row(i);
+    } else {
+        request_set(pf[0]);
+    }
     int ring_pos = 0;
     uint32_t buf = 0;                               // partial buffer (and mbarrier) of the next emitted row == nrow & 1
     uint32_t nrow = 0;                              // rows emitted so far
@@ -539,17 +579,28 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
         }
         uint32_t pa = sb + SM::kProgOff + (uint32_t)(chunk & 1) * (kProgChunk * kRec);      // next program record
         const uint32_t pa_end = pa + (uint32_t)min(kProgChunk, total_rows - c0) * kRec;
-        // One source row (ring position D of 2*PF): LUT-convert, accumulate; at a set boundary request the next set.
+        // One source row (ring position D of RING): fetch, LUT-convert, accumulate.
         // Returns the completion word of the row (0 = no output row completes here).
         auto do_row = [&](auto dtag) -> uint32_t {
             constexpr int D = decltype(dtag)::value;
-            constexpr int SET = D / PF, IDX = D % PF;
-            const uint4 raw = pf[SET][IDX];
-            if (IDX == 0) {                       // set SET has landed: request the other set
-                // pl.zero is 0 at run time; tying the address to the data just consumed keeps the compiler from
-                // issuing these loads ahead of the scoreboard wait for the current set (see the comment at pf[]).
-                pnext = pnext + (raw.x & pl.zero);
-                request_set(pf[SET ^ 1]);
+            uint4 raw;
+            if (ST > 0) {
+                if (D == 0 && t == 0 && left > 2 * ST) {              // L2 prefetch of the ST rows after the ST next requests
+#pragma unroll
+                    for (int i = 0; i < ST; ++i) l2_prefetch_bulk(pnext + (size_t)(ST + i) * stride, seg_bytes);
+                }
+                request_row((D + ST - 1) % (ST > 0 ? ST : 1));        // row i+ST-1 into the slot consumed one row ago
+                cp_async_wait_group<(ST > 0 ? ST - 1 : 0)>();         // all but the newest ST-1 requests have landed: row i is here
+                raw = lds_u32x4(st_base + D * SM::kRowStage);
+            } else {
+                constexpr int SET = D / PF, IDX = D % PF;
+                raw = pf[SET][IDX];
+                if (IDX == 0) {                   // set SET has landed: request the other set
+                    // pl.zero is 0 at run time; tying the address to the data just consumed keeps the compiler from
+                    // issuing these loads ahead of the scoreboard wait for the current set (see the comment at pf[]).
+                    pnext = pnext + (raw.x & pl.zero);
+                    request_set(pf[SET ^ 1]);
+                }
             }
             // ---- program record: AV slot weights, then the completion word
             uint32_t rec[PL::kWords];
@@ -593,13 +644,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
             }
             return rec[PL::kDone];
         };
-        // The 2*PF ring positions are copies of do_row; the completion code below exists once: a row that completes
+        // The RING ring positions are copies of do_row; the completion code below exists once: a row that completes
         // output rows breaks out of the switch, and the loop re-enters at the next ring position.
         while (pa != pa_end) {
             uint32_t dn = 0;
             switch (ring_pos) {
 #define IFB_ROW_CASE(D_) \
-            case D_: if (D_ < 2 * PF) { dn = do_row(std::integral_constant<int, (D_) % (2 * PF)>{}); ring_pos = ((D_) + 1) % (2 * PF); if (dn || pa == pa_end) break; }
+            case D_: if (D_ < RING) { dn = do_row(std::integral_constant<int, (D_) % RING>{}); ring_pos = ((D_) + 1) % RING; if (dn || pa == pa_end) break; }
             IFB_ROW_CASE(0) IFB_ROW_CASE(1) IFB_ROW_CASE(2) IFB_ROW_CASE(3) IFB_ROW_CASE(4) IFB_ROW_CASE(5) IFB_ROW_CASE(6) IFB_ROW_CASE(7)
             IFB_ROW_CASE(8) IFB_ROW_CASE(9) IFB_ROW_CASE(10) IFB_ROW_CASE(11)
 #undef IFB_ROW_CASE
@@ -674,7 +725,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                 }
             }
         }
-        cp_async_wait_all();
+        // the next program chunk was requested a whole chunk of rows ago: with staged rows its cp.async group is long
+        // complete (groups retire in order, wait_group<ST-1> ran every row); only its visibility to the other threads is needed
+        if (ST == 0 || c0 + kProgChunk >= total_rows) cp_async_wait_all();
         __syncthreads();
     }
     if (nrow) {                                                       // the last emitted row of the band
