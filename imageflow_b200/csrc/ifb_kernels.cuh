@@ -413,9 +413,10 @@ template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static constexpr int kBarOff = kPartOff + 2 * kPartBuf;      // two 8-byte mbarriers (one per partial buffer)
     static constexpr int kStageOff = kBarOff + 16;
     static constexpr int kRowStage = NT * 16;
-    // stages that fit next to a second CTA (at least 3, at most 6), else 0: the kernel then prefetches into registers
+    // Stages that fit next to a second CTA (at least 3, at most 6); if fewer fit the kernel prefetches into registers
+    // instead (0 stages) -- unless a second CTA does not fit anyway, then the single CTA takes 6 stages.
     static constexpr int kFit = (kSmemPerCtaFor2 - kStageOff) / kRowStage;
-    static constexpr int kStages = kFit >= 3 ? (kFit > 6 ? 6 : kFit) : 0;
+    static constexpr int kStages = kFit >= 3 ? (kFit > 6 ? 6 : kFit) : (kStageOff <= kSmemPerCtaFor2 ? 0 : 6);
     static constexpr int kTotal = kStageOff + kStages * kRowStage;
     static constexpr int kHwPairs = (SH / 2) * 4 + (SH & 1) * 2; // float2 pairs of H weights per thread
     static_assert(kHwPairs * 2 * NT / 32 <= 256, "H weights must fit in the LUT holes");
