@@ -699,6 +699,42 @@ void apply_matte_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h
 // device staging for one input window and one destination rect, so that the upload of call i+1 overlaps the
 // kernel of call i and the download of call i-1 when several calls are issued through the batched entry point.
 constexpr int kHostSlots = 3;
+// transpose.rs:95-121 + the bounds checks of transpose.rs:46-79 (strides in bytes here)
+void transpose_locked(ifb200_batch* b, const uint8_t* from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* to, uint32_t to_stride,
+                      cudaStream_t st) {
+    if (!from || !to) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
+    if (w == 0 || h == 0) return;
+    if ((from_stride & 3) || (to_stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "strides must be multiples of 4 bytes");
+    if (from_stride < w * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "from_stride(%u) < width(%u)", from_stride / 4, w);
+    if (to_stride < h * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "to_stride(%u) < height(%u)", to_stride / 4, h);
+    CUDA_OK(cudaSetDevice(b->device));
+    dim3 grid((w + 31) / 32, (h + 31) / 32);
+    if (grid.y > 65535u) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap too tall for transposition (%u rows)", h);
+    transpose_bgra8_kernel<<<grid, dim3(32, 8), 0, st>>>(from, from_stride, w, h, to, to_stride);
+    CUDA_OK(cudaGetLastError());
+    b->launches++;
+}
+void flip_locked(ifb200_batch* b, bool vertical, uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, cudaStream_t st) {
+    if (!px) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
+    if (w == 0 || h == 0) return;
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
+    const bool v4 = (w % 4 == 0) && (stride % 16 == 0) && ((uintptr_t)px % 16 == 0);       // four pixels per access
+    const uint32_t we = v4 ? w / 4 : w;
+    const uint64_t elems = vertical ? (uint64_t)(h / 2) * we : (uint64_t)(v4 ? (we + 1) / 2 : we / 2) * h;
+    if (elems == 0) return;
+    CUDA_OK(cudaSetDevice(b->device));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((elems + 255) / 256, 148u * 16u);
+    if (vertical) {
+        if (v4) flip_vertical_bgra8_kernel<uint4><<<blocks, 256, 0, st>>>(px, we, h, stride);
+        else flip_vertical_bgra8_kernel<uint32_t><<<blocks, 256, 0, st>>>(px, we, h, stride);
+    } else {
+        if (v4) flip_horizontal_bgra8_v4_kernel<<<blocks, 256, 0, st>>>(px, we, h, stride);
+        else flip_horizontal_bgra8_kernel<<<blocks, 256, 0, st>>>(px, w, h, stride);
+    }
+    CUDA_OK(cudaGetLastError());
+    b->launches++;
+}
+
 struct HostSlot {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
@@ -860,6 +896,29 @@ int ifb200_batch_apply_matte(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint3
     });
 }
 
+int ifb200_batch_transpose(ifb200_batch* b, const uint8_t* dev_from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* dev_to,
+                           uint32_t to_stride, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        transpose_locked(b, dev_from, from_stride, w, h, dev_to, to_stride, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+int ifb200_batch_flip_vertical(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        flip_locked(b, true, dev_px, w, h, stride, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+int ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        flip_locked(b, false, dev_px, w, h, stride, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+
 int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
@@ -964,6 +1023,52 @@ int ifb200_apply_matte_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t strid
         CUDA_OK(cudaStreamSynchronize(st));
     });
 }
+
+int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* to, uint32_t to_stride,
+                           char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!from || !to) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (w == 0 || h == 0) return;
+        if ((from_stride & 3) || (to_stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "strides must be multiples of 4 bytes");
+        if (from_stride < w * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "from_stride(%u) < width(%u)", from_stride / 4, w);
+        if (to_stride < h * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "to_stride(%u) < height(%u)", to_stride / 4, h);
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pin = ((size_t)w * 4 + 63) / 64 * 64, pout = ((size_t)h * 4 + 63) / 64 * 64;
+        ensure(sl.d_in, sl.cap_in, pin * h, st);
+        ensure(sl.d_cv, sl.cap_cv, pout * w, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_in, pin, from, from_stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        transpose_locked(b, sl.d_in, (uint32_t)pin, w, h, sl.d_cv, (uint32_t)pout, st);
+        CUDA_OK(cudaMemcpy2DAsync(to, to_stride, sl.d_cv, pout, (size_t)h * 4, w, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+static int flip_host(bool vertical, uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!px) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (w == 0 || h == 0) return;
+        if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
+        ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        flip_locked(b, vertical, sl.d_cv, w, h, (uint32_t)pitch, st);
+        CUDA_OK(cudaMemcpy2DAsync(px, stride, sl.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+int ifb200_flip_vertical_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t cap) { return flip_host(true, px, w, h, stride, err, cap); }
+int ifb200_flip_horizontal_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t cap) { return flip_host(false, px, w, h, stride, err, cap); }
 
 int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float m[25], char* err, size_t cap) {
     return guarded(err, cap, [&] {

@@ -314,20 +314,81 @@ __global__ void __launch_bounds__(256) apply_matte_kernel(uint8_t* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------- transpose / flips
+// Pure data movement on BGRA8 words, bound by HBM: 4 bytes read + 4 bytes written per pixel.
+// graphics/transpose.rs:95-121 (bitmap_window_transpose): to[x][y] = from[y][x].  32x32-word tiles through shared memory
+// (padded to 33 columns: conflict-free), 32x8 threads, both the reads and the writes are full 128-byte rows.
+__global__ void __launch_bounds__(256) transpose_bgra8_kernel(const uint8_t* __restrict__ from, uint32_t from_stride, uint32_t w, uint32_t h,
+                                                              uint8_t* __restrict__ to, uint32_t to_stride) {
+    __shared__ uint32_t tile[32][33];
+    const uint32_t x0 = blockIdx.x * 32u, y0 = blockIdx.y * 32u;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const uint32_t x = x0 + threadIdx.x, y = y0 + threadIdx.y + j;
+        if (x < w && y < h) tile[threadIdx.y + j][threadIdx.x] = __ldcs(reinterpret_cast<const uint32_t*>(from + (size_t)y * from_stride) + x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const uint32_t oy = x0 + threadIdx.y + j, ox = y0 + threadIdx.x;      // destination row = source column
+        if (oy < w && ox < h) __stcs(reinterpret_cast<uint32_t*>(to + (size_t)oy * to_stride) + ox, tile[threadIdx.x][threadIdx.y + j]);
+    }
+}
+// graphics/flip.rs:10-22 (flow_bitmap_bgra_flip_vertical_safe): rows y and h-1-y swap, in place; the middle row of an odd
+// height stays.  One thread per element of the top half; T = uint4 (four pixels) when rows are 16-byte aligned and the
+// width is a multiple of 4, else uint32_t.
+template <class T>
+__global__ void __launch_bounds__(256) flip_vertical_bgra8_kernel(uint8_t* __restrict__ px, uint32_t w_elems, uint32_t h, uint32_t stride) {
+    const uint32_t half = h / 2u;
+    const uint64_t total = (uint64_t)half * w_elems;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / w_elems), x = (uint32_t)(i - (uint64_t)y * w_elems);
+        T* a = reinterpret_cast<T*>(px + (size_t)y * stride) + x;
+        T* b = reinterpret_cast<T*>(px + (size_t)(h - 1u - y) * stride) + x;
+        const T va = *a, vb = *b;
+        *a = vb; *b = va;
+    }
+}
+// graphics/flip.rs:25-39 (flow_bitmap_bgra_flip_horizontal_safe): every row reversed pixel-wise, in place.
+__global__ void __launch_bounds__(256) flip_horizontal_bgra8_kernel(uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride) {
+    const uint32_t half = w / 2u;
+    const uint64_t total = (uint64_t)half * h;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / half), x = (uint32_t)(i - (uint64_t)y * half);
+        uint32_t* row = reinterpret_cast<uint32_t*>(px + (size_t)y * stride);
+        const uint32_t va = row[x], vb = row[w - 1u - x];
+        row[x] = vb; row[w - 1u - x] = va;
+    }
+}
+// the same on groups of four pixels (rows 16-byte aligned, width a multiple of 4): group g swaps with group n-1-g, each
+// reversed inside; the middle group of an odd count is reversed in place
+__global__ void __launch_bounds__(256) flip_horizontal_bgra8_v4_kernel(uint8_t* __restrict__ px, uint32_t w4, uint32_t h, uint32_t stride) {
+    const uint32_t per_row = (w4 + 1u) / 2u;
+    const uint64_t total = (uint64_t)per_row * h;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / per_row), g = (uint32_t)(i - (uint64_t)y * per_row);
+        uint4* row = reinterpret_cast<uint4*>(px + (size_t)y * stride);
+        const uint4 a = row[g], b = row[w4 - 1u - g];
+        row[g] = make_uint4(b.w, b.z, b.y, b.x);
+        row[w4 - 1u - g] = make_uint4(a.w, a.z, a.y, a.x);      // g == w4-1-g (middle group): both stores write the same value
+    }
+}
+
 // ---------------------------------------------------------------- fused down-scale kernel
 // One CTA = (job, strip of output columns, band of output rows).  Thread t owns source columns
 // k0+4t .. k0+4t+3 for the whole band:
-//   pass 1 (V): streams source rows top to bottom straight from HBM into registers (one 16-byte load
-//               per row, PF rows in flight per thread), converts through a bank-conflict-free
-//               (lane-replicated) shared-memory LUT once, and accumulates into a ring of AV register
+//   pass 1 (V): streams source rows top to bottom, 16 bytes per thread per row -- through a private shared-memory FIFO
+//               filled by cp.async where its stages fit, else into two register sets -- converts them through a
+//               bank-conflict-free (lane-replicated) shared-memory LUT once, and accumulates into a ring of AV register
 //               accumulators: output row y lives in slot y mod AV for as long as its window is open.  The
 //               per-row "program" (slot weights + which output rows complete) is streamed through a
 //               double-buffered shared-memory chunk with cp.async.
 //   pass 2 (H): when an output row completes, each thread multiplies its 4 V values by its H weights into <= SH
-//               per-output partial sums and parks them in shared memory; after one __syncthreads thread u sums
-//               the partials of output column X0+u in ascending order, runs the store epilogue and writes one
-//               coalesced BGRA8 row segment.  Partials are double-buffered and consecutive completions use
-//               alternating halves of the CTA, so one barrier per output row suffices.
+//               per-output partial sums, parks them in shared memory and arrives on an mbarrier; one completion later
+//               thread u waits for that mbarrier (normally already complete), sums the partials of output column X0+u in
+//               ascending order, runs the store epilogue and writes one coalesced BGRA8 row segment.  Partials are
+//               double-buffered and consecutive rows are finished by alternating halves of the CTA; the CTA never
+//               rendezvous per output row.
 // Every source pixel is read from HBM once (plus strip/band halos), converted once, and the
 // V-filtered intermediate never leaves the SM.
 //
@@ -363,7 +424,6 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) 
 
 // A value the compiler must keep in a register (it cannot re-derive it, so it cannot rematerialise it per use).
 __device__ __forceinline__ uint32_t pinned_reg(uint32_t x) { uint32_t y; asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
-__device__ __forceinline__ uint64_t pinned_reg64(uint64_t x) { uint64_t y; asm volatile("mov.b64 %0, %1;" : "=l"(y) : "l"(x)); return y; }
 // read-only-after-setup table gather (may be scheduled freely: its operands depend on the pixel just loaded)
 __device__ __forceinline__ float lds_table(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
@@ -451,7 +511,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
         for (int w = t; w < SM::kHwPairs * 2 * NT; w += NT)
             *reinterpret_cast<float*>(sLut + ((w >> 5) << 8) + 128 + ((w & 31) << 2)) = __ldg(pl.hw + (size_t)strip * SH * 4 * NT + w);
     }
-    // ---- per-thread constants, pinned in registers
+    // ---- per-thread constants
     // outputs of this strip are finished by alternating halves of the CTA when they fit in one half
     const int NX = sd.X1 - sd.X0;
     const bool alternate = NX <= NT / 2;

@@ -157,6 +157,30 @@ def apply_matte(window: BitmapWindow, matte_bgra) -> None:
     _check(lib().ifb200_apply_matte_bgra8(window.ptr, window.w, window.h, window.stride, mm, int(bool(window.alpha_meaningful)), buf, 512), buf)
 
 
+def bitmap_window_transpose(from_window: BitmapWindow, to_window: BitmapWindow) -> None:
+    """graphics/transpose.rs:95-121 on HOST windows: to[x][y] = from[y][x]; dimensions must be swapped, BGRA only."""
+    if from_window.w != to_window.h or from_window.h != to_window.w or from_window.pixel_layout != to_window.pixel_layout:
+        raise FlowError(ErrorKind.InvalidArgument,
+                        "For transposition, canvas and input formats must be the same and dimensions must be swapped")
+    if from_window.pixel_layout != "BGRA":
+        raise FlowError(ErrorKind.InvalidArgument, "Only BGRA layout is supported")
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_transpose_bgra8(from_window.ptr, from_window.stride, from_window.w, from_window.h,
+                                        to_window.ptr, to_window.stride, buf, 512), buf)
+
+
+def flow_bitmap_bgra_flip_vertical_safe(bitmap: BitmapWindow) -> None:
+    """graphics/flip.rs:10-22, in place on a HOST bitmap."""
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_flip_vertical_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, buf, 512), buf)
+
+
+def flow_bitmap_bgra_flip_horizontal_safe(bitmap: BitmapWindow) -> None:
+    """graphics/flip.rs:25-39, in place on a HOST bitmap."""
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_flip_horizontal_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, buf, 512), buf)
+
+
 def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
     """flow/nodes/color.rs:86-225 presets (0 sepia ... 9 saturation)."""
     m = np.zeros(25, np.float32)
@@ -233,6 +257,25 @@ class Batch:
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_color_matrix(self._h, dev_ptr, w, h, stride, mm.ctypes.data_as(C.POINTER(C.c_float)),
                                                 self._stream(stream), buf, 512), buf)
+
+    def transpose(self, from_window: BitmapWindow, to_window: BitmapWindow, stream=None) -> None:
+        """graphics/transpose.rs:95-121 on DEVICE windows (asynchronous on `stream`)."""
+        if from_window.w != to_window.h or from_window.h != to_window.w:
+            raise FlowError(ErrorKind.InvalidArgument,
+                            "For transposition, canvas and input formats must be the same and dimensions must be swapped")
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_transpose(self._h, from_window.ptr, from_window.stride, from_window.w, from_window.h,
+                                            to_window.ptr, to_window.stride, self._stream(stream), buf, 512), buf)
+
+    def flip_vertical(self, bitmap: BitmapWindow, stream=None) -> None:
+        """graphics/flip.rs:10-22 on a DEVICE bitmap, in place."""
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_flip_vertical(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, self._stream(stream), buf, 512), buf)
+
+    def flip_horizontal(self, bitmap: BitmapWindow, stream=None) -> None:
+        """graphics/flip.rs:25-39 on a DEVICE bitmap, in place."""
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_flip_horizontal(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, self._stream(stream), buf, 512), buf)
 
     def sync(self) -> None:
         buf = C.create_string_buffer(512)

@@ -115,6 +115,15 @@ int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stri
 int ifb200_apply_matte_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t matte_bgra[4],
                              int alpha_meaningful, char* err, size_t err_cap);
 
+/* Replaces graphics::transpose::bitmap_window_transpose (graphics/transpose.rs:95-121; checks of :46-79):
+ * to[x][y] = from[y][x] for a w x h BGRA8 window; `to` is h pixels wide and w rows tall.  Strides in bytes.
+ * [SURVEY.md section 8(f), item 3] */
+int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* to, uint32_t to_stride,
+                           char* err, size_t err_cap);
+/* Replace flow_bitmap_bgra_flip_vertical_safe / flow_bitmap_bgra_flip_horizontal_safe (graphics/flip.rs:10-22, 25-39), in place. */
+int ifb200_flip_vertical_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t err_cap);
+int ifb200_flip_horizontal_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t err_cap);
+
 /* ---- device-resident batch API (the metric path; not in the reference) -----------------------
  * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
  * enqueue is asynchronous on `cuda_stream`, a cudaStream_t with the usual CUDA meaning (NULL = the legacy
@@ -129,6 +138,12 @@ int  ifb200_batch_color_matrix(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uin
                                const float m[25], void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_apply_matte(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
                               const uint8_t matte_bgra[4], int alpha_meaningful, void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_transpose(ifb200_batch* b, const uint8_t* dev_from, uint32_t from_stride, uint32_t w, uint32_t h,
+                            uint8_t* dev_to, uint32_t to_stride, void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_flip_vertical(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
+                                void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
+                                  void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
 void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */

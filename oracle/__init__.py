@@ -77,6 +77,9 @@ def lib() -> C.CDLL:
     L.ifo_color_filter_matrix.argtypes = [C.c_int, C.c_float, f32p]
     L.ifo_color_filter_matrix.restype = C.c_int
     L.ifo_apply_matte.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_int]
+    L.ifo_transpose.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_uint32]
+    L.ifo_flip_vertical.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.ifo_flip_horizontal.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.ifo_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -185,3 +188,18 @@ def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
 def apply_matte(px: np.ndarray, matte_bgra, alpha_meaningful=True) -> None:
     mm = (C.c_uint8 * 4)(*matte_bgra)
     lib().ifo_apply_matte(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[1], px.shape[0], px.strides[0], mm, int(alpha_meaningful))
+
+
+def transpose(src: np.ndarray, dst: np.ndarray) -> None:
+    """src (H, Ws, 4), dst (W, Hs, 4) uint8 with padded row strides allowed; dst[x, y] = src[y, x] for x < w, y < h."""
+    u8p = C.POINTER(C.c_uint8)
+    h, w = src.shape[0], dst.shape[0]
+    lib().ifo_transpose(src.ctypes.data_as(u8p), src.strides[0], w, h, dst.ctypes.data_as(u8p), dst.strides[0])
+
+
+def flip_vertical(px: np.ndarray, w=None) -> None:
+    lib().ifo_flip_vertical(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[1] if w is None else w, px.shape[0], px.strides[0])
+
+
+def flip_horizontal(px: np.ndarray, w=None) -> None:
+    lib().ifo_flip_horizontal(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[1] if w is None else w, px.shape[0], px.strides[0])

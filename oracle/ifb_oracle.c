@@ -569,3 +569,24 @@ int ifo_max_threads(void) {
     return 1;
 #endif
 }
+
+/* graphics/transpose.rs:95-121 (bitmap_window_transpose): the u32 pixel at (x, y) moves to (y, x) */
+void ifo_transpose(const uint8_t* from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* to, uint32_t to_stride) {
+    for (uint32_t y = 0; y < h; ++y)
+        for (uint32_t x = 0; x < w; ++x)
+            memcpy(to + (size_t)x * to_stride + (size_t)y * 4, from + (size_t)y * from_stride + (size_t)x * 4, 4);
+}
+/* graphics/flip.rs:10-22: top and bottom rows swap; the middle row of an odd height stays */
+void ifo_flip_vertical(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride) {
+    for (uint32_t y = 0; y < h / 2; ++y) {
+        uint8_t* a = px + (size_t)y * stride; uint8_t* b = px + (size_t)(h - 1 - y) * stride;
+        for (uint32_t i = 0; i < w * 4; ++i) { const uint8_t t = a[i]; a[i] = b[i]; b[i] = t; }
+    }
+}
+/* graphics/flip.rs:25-39: every row reversed pixel-wise */
+void ifo_flip_horizontal(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride) {
+    for (uint32_t y = 0; y < h; ++y) {
+        uint32_t* r = (uint32_t*)(px + (size_t)y * stride);
+        for (uint32_t x = 0; x < w / 2; ++x) { const uint32_t t = r[x]; r[x] = r[w - 1 - x]; r[w - 1 - x] = t; }
+    }
+}

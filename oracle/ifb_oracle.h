@@ -13,6 +13,7 @@
  *   - imageflow_core/src/graphics/scaling.rs      (dispatch, composite :254-287, A=255 fix-up :227-232)
  *   - imageflow_core/src/graphics/color_matrix.rs (5x5 matrix on sRGB bytes)
  *   - imageflow_core/src/graphics/blend.rs        (apply_matte)
+ *   - imageflow_core/src/graphics/transpose.rs, flip.rs (data movement only: exact by definition)
  *
  * PARITY STATUS.  Weights, transfer functions, colour matrix, canvas composite
  * and apply_matte are pinned against the reference's own golden vectors / KATs
@@ -96,6 +97,12 @@ void ifo_color_matrix(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, cons
 int  ifo_color_filter_matrix(int which, float p, float out[25]);
 /* blend.rs:6-59 */
 void ifo_apply_matte(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const uint8_t matte_bgra[4], int alpha_meaningful);
+
+/* graphics/transpose.rs:95-121: to[x][y] = from[y][x], w x h BGRA8 words; strides in bytes */
+void ifo_transpose(const uint8_t* from, uint32_t from_stride, uint32_t w, uint32_t h, uint8_t* to, uint32_t to_stride);
+/* graphics/flip.rs:10-22 and :25-39, in place */
+void ifo_flip_vertical(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride);
+void ifo_flip_horizontal(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride);
 
 int ifo_max_threads(void);
 

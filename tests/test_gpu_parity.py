@@ -357,6 +357,48 @@ def test_apply_matte_matches_oracle(ifb):
     assert np.array_equal(same, px0)
 
 
+def test_transpose_and_flips_match_oracle(ifb, torch_mod):
+    """bitmap_window_transpose (transpose.rs:95-121) and the two flips (flip.rs:10-39), host drop-ins
+    and device-resident batch calls, bit-exact vs the oracle; odd sizes, 1-pixel edges, padded strides."""
+    torch = torch_mod
+    batch = ifb.Batch(0)
+    for (w, h) in ((301, 97), (32, 32), (33, 31), (1, 77), (77, 1), (1, 1), (640, 480), (36, 10), (4, 3), (100, 7)):
+        px0 = util.noise(w, h, seed=31 + w, alpha_mode="mixed")
+        # ---- host drop-ins
+        exp_t = np.zeros((w, h, 4), np.uint8); oracle.transpose(px0, exp_t)
+        src = util.padded(px0)
+        dst_store = np.full((w, ((h * 4 + 63) // 64 * 64) // 4, 4), 0xAB, np.uint8); dst = dst_store[:, :h]
+        ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(src), ifb.BitmapWindow.from_numpy(dst))
+        assert np.array_equal(dst, exp_t) and np.array_equal(exp_t, px0.transpose(1, 0, 2))
+        assert (dst_store[:, h:] == 0xAB).all()                                   # row padding untouched
+        for fn, ofn in ((ifb.flow_bitmap_bgra_flip_vertical_safe, oracle.flip_vertical), (ifb.flow_bitmap_bgra_flip_horizontal_safe, oracle.flip_horizontal)):
+            exp = px0.copy(); ofn(exp)
+            got = util.padded(px0)
+            fn(ifb.BitmapWindow.from_numpy(got))
+            assert np.array_equal(got, exp)
+        # ---- device-resident
+        d_src = torch.from_numpy(px0).cuda()
+        d_dst = torch.zeros((w, h, 4), dtype=torch.uint8, device="cuda")
+        batch.transpose(ifb.BitmapWindow.from_torch(d_src), ifb.BitmapWindow.from_torch(d_dst)); batch.sync()
+        assert np.array_equal(d_dst.cpu().numpy(), exp_t)
+        d_v = torch.from_numpy(px0).cuda(); batch.flip_vertical(ifb.BitmapWindow.from_torch(d_v))
+        d_h = torch.from_numpy(px0).cuda(); batch.flip_horizontal(ifb.BitmapWindow.from_torch(d_h)); batch.sync()
+        assert np.array_equal(d_v.cpu().numpy(), px0[::-1]) and np.array_equal(d_h.cpu().numpy(), px0[:, ::-1])
+    # rotate 90 = transpose + flip (flow/nodes/rotate_flip_transpose.rs): twice = rotate 180 = both flips
+    px = util.noise(123, 45, seed=5)
+    t1 = np.zeros((123, 45, 4), np.uint8); ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(px.copy()), ifb.BitmapWindow.from_numpy(t1))
+    ifb.flow_bitmap_bgra_flip_horizontal_safe(ifb.BitmapWindow.from_numpy(t1))
+    t2 = np.zeros((45, 123, 4), np.uint8); ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(t1), ifb.BitmapWindow.from_numpy(t2))
+    ifb.flow_bitmap_bgra_flip_horizontal_safe(ifb.BitmapWindow.from_numpy(t2))
+    assert np.array_equal(t2, px[::-1, ::-1])
+    # argument errors (transpose.rs:46-79, :100-106)
+    with pytest.raises(ifb.FlowError):
+        ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(px.copy()), ifb.BitmapWindow.from_numpy(np.zeros((45, 123, 4), np.uint8)))
+    bad = ifb.BitmapWindow.from_numpy(np.zeros((123, 45, 4), np.uint8)); bad.stride = 44 * 4
+    with pytest.raises(ifb.FlowError):
+        ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(px.copy()), bad)
+
+
 def test_random_geometries_bit_exact(ifb, torch_mod):
     """40 seeded random (geometry, filter, alpha, compose, colourspace, rect) draws: whichever kernel the engine picks
     must match the oracle bit for bit; covers strip/band edges, odd widths, tiny and 1-pixel outputs."""

