@@ -15,6 +15,7 @@ SYMBOLS = [
     "ifb200_scale_and_render", "ifb200_scale_and_render_many", "ifb200_color_matrix_bgra8", "ifb200_apply_matte_bgra8", "ifb200_batch_apply_matte",
     "ifb200_transpose_bgra8", "ifb200_flip_vertical_bgra8", "ifb200_flip_horizontal_bgra8",
     "ifb200_batch_transpose", "ifb200_batch_flip_vertical", "ifb200_batch_flip_horizontal",
+    "ifb200_white_balance_srgb_bgra8", "ifb200_batch_white_balance",
     "ifb200_batch_create", "ifb200_batch_enqueue", "ifb200_batch_color_matrix", "ifb200_batch_sync",
     "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches",
     "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs",
@@ -73,6 +74,10 @@ def lib() -> C.CDLL:
     for f in (L.ifb200_flip_vertical_bgra8, L.ifb200_flip_horizontal_bgra8):
         f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
         f.restype = C.c_int
+    L.ifb200_white_balance_srgb_bgra8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_char_p, C.c_size_t]
+    L.ifb200_white_balance_srgb_bgra8.restype = C.c_int
+    L.ifb200_batch_white_balance.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.ifb200_batch_white_balance.restype = C.c_int
     L.ifb200_batch_transpose.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_char_p, C.c_size_t]
     L.ifb200_batch_transpose.restype = C.c_int
     for f in (L.ifb200_batch_flip_vertical, L.ifb200_batch_flip_horizontal):

@@ -358,6 +358,11 @@ struct PinnedSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr;
 struct ifb200_batch {
     int device = 0;
     cudaStream_t own_stream = nullptr;
+    // An enqueue with many different geometries launches one (small) kernel per geometry: they are spread over a few side
+    // streams that fork from and join back into the caller's stream, so that they overlap instead of queueing up.
+    static constexpr int kSideStreams = 4;
+    cudaStream_t side[kSideStreams] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
     std::mutex mu;
     DevVec<float> t_lin, t_srgb; DevVec<uint8_t> lut16k;
     Tables tables{};
@@ -376,6 +381,9 @@ struct ifb200_batch {
         for (auto& s : pinned) { if (s.ev) cudaEventDestroy(s.ev); if (s.p) cudaFreeHost(s.p); }
         drop_plans();
         if (own_stream) cudaStreamDestroy(own_stream);
+        for (auto& sd : side) if (sd) cudaStreamDestroy(sd);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto& e : ev_join) if (e) cudaEventDestroy(e);
     }
 
     // Bump allocator for plan tables: thousands of small tables cost one cudaMalloc per 32 MiB, not one each.
@@ -591,11 +599,20 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     CUDA_OK(cudaMemcpyAsync(dj, hj, n * sizeof(JobDev), cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaEventRecord(ev, st));
 
+    // many geometries: one small launch each -> fork onto the side streams (the jobs of one call are independent)
+    const bool fork = groups.size() >= 4;
+    const int min_ctas = fork ? std::max(32, b->min_ctas / ifb200_batch::kSideStreams) : b->min_ctas;
+    cudaStream_t const user_stream = st;
+    if (fork) {
+        CUDA_OK(cudaEventRecord(b->ev_fork, user_stream));
+        for (auto& sd : b->side) CUDA_OK(cudaStreamWaitEvent(sd, b->ev_fork, 0));
+    }
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         Group& g = groups[gi];
         Plan& p = *g.plan;
         const JobDev* jobs = dj + gstart[gi];
         const size_t nj = g.idx.size();
+        st = fork ? b->side[gi % ifb200_batch::kSideStreams] : user_stream;
         if (g.kind == 2) {
             const TilePlanDev& t = p.tile;
             ensure_axes(b, st, p);
@@ -613,7 +630,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             FusedVariantTables& ft = fused_tables(b, st, p, b->nt);
             int nb = 1;
             const size_t base = nj * ft.n_strips;
-            if (base < (size_t)b->min_ctas) nb = (int)std::min<size_t>((b->min_ctas + base - 1) / base, std::max<uint32_t>(1u, p.out_h / 8u));
+            if (base < (size_t)min_ctas) nb = (int)std::min<size_t>((min_ctas + base - 1) / base, std::max<uint32_t>(1u, p.out_h / 8u));
             nb = pick_bands(ft, nb);
             FusedPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
@@ -652,6 +669,13 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             }
             CUDA_OK(cudaFreeAsync(inter, st));
             b->generic_jobs += nj;
+        }
+    }
+    st = user_stream;
+    if (fork) {
+        for (int k = 0; k < ifb200_batch::kSideStreams; ++k) {
+            CUDA_OK(cudaEventRecord(b->ev_join[k], b->side[k]));
+            CUDA_OK(cudaStreamWaitEvent(st, b->ev_join[k], 0));
         }
     }
     CUDA_OK(cudaFreeAsync(dj, st));
@@ -735,6 +759,35 @@ void flip_locked(ifb200_batch* b, bool vertical, uint8_t* px, uint32_t w, uint32
     b->launches++;
 }
 
+// flow/nodes/white_balance.rs:93-121 (WhiteBalanceSrgbMutDef::mutate): histograms, area thresholds, byte maps, remap.
+// threshold < 0 stands for None (-> 0.006f32, white_balance.rs:76-77); both thresholds are the same value (:114).
+void white_balance_locked(ifb200_batch* b, uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, cudaStream_t st) {
+    if (!px) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
+    if (w == 0 || h == 0) return;
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
+    if (threshold != threshold) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "threshold is NaN");
+    CUDA_OK(cudaSetDevice(b->device));
+    const double low = (double)(threshold < 0.0f ? 0.006f : threshold);      // f64::from(f32)
+    unsigned long long* hist = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&hist), 768 * sizeof(unsigned long long) + 768, st));
+    uint8_t* maps = reinterpret_cast<uint8_t*>(hist + 768);
+    CUDA_OK(cudaMemsetAsync(hist, 0, 768 * sizeof(unsigned long long), st));
+    const uint64_t total = (uint64_t)w * h;
+    const bool v4 = (w % 4 == 0) && (stride % 16 == 0) && ((uintptr_t)px % 16 == 0);       // four pixels per access
+    const uint64_t elems = v4 ? total / 4 : total;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((elems + 255) / 256, 148u * 8u);
+    if (v4) histogram_bgra8_kernel<true><<<blocks, 256, 0, st>>>(px, w, h, stride, hist);
+    else histogram_bgra8_kernel<false><<<blocks, 256, 0, st>>>(px, w, h, stride, hist);
+    CUDA_OK(cudaGetLastError());
+    white_balance_maps_kernel<<<1, 256, 0, st>>>(hist, (unsigned long long)total, low, maps);
+    CUDA_OK(cudaGetLastError());
+    if (v4) apply_byte_maps_bgra8_kernel<true><<<blocks, 256, 0, st>>>(px, w, h, stride, maps);
+    else apply_byte_maps_bgra8_kernel<false><<<blocks, 256, 0, st>>>(px, w, h, stride, maps);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaFreeAsync(hist, st));
+    b->launches += 3;
+}
+
 struct HostSlot {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
@@ -765,6 +818,9 @@ ifb200_batch* create_batch(int device) {
     std::unique_ptr<ifb200_batch> b(new ifb200_batch());
     b->device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
+    for (auto& sd : b->side) CUDA_OK(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    for (auto& e : b->ev_join) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     {   // job arrays and the generic path's intermediates come from the stream-ordered pool: keep its memory across
         // synchronisation points (the default threshold of 0 returns it to the OS at every synchronise, and the next
         // call pays tens of milliseconds to get it back)
@@ -919,6 +975,15 @@ int ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, u
     });
 }
 
+int ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, float threshold, void* stream,
+                               char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        white_balance_locked(b, dev_px, w, h, stride, threshold, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+
 int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
@@ -1044,6 +1109,26 @@ int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w
         CUDA_OK(cudaMemcpy2DAsync(sl.d_in, pin, from, from_stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
         transpose_locked(b, sl.d_in, (uint32_t)pin, w, h, sl.d_cv, (uint32_t)pout, st);
         CUDA_OK(cudaMemcpy2DAsync(to, to_stride, sl.d_cv, pout, (size_t)h * 4, w, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+int ifb200_white_balance_srgb_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!px) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (w == 0 || h == 0) return;
+        if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
+        ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        white_balance_locked(b, sl.d_cv, w, h, (uint32_t)pitch, threshold, st);
+        CUDA_OK(cudaMemcpy2DAsync(px, stride, sl.d_cv, pitch, (size_t)w * 4, h, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
     });
 }

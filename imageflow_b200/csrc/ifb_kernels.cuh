@@ -374,6 +374,94 @@ __global__ void __launch_bounds__(256) flip_horizontal_bgra8_v4_kernel(uint8_t* 
     }
 }
 
+// ---------------------------------------------------------------- white balance (first half)
+// flow/nodes/white_balance.rs:93-121 = three passes: per-channel histograms (graphics/histogram.rs:7-20), the area-threshold
+// byte mappings (white_balance.rs:14-48, f64 arithmetic, a handful of operations), and the in-place remap (:50-67).
+// hist[0..255] = R, [256..511] = G, [512..767] = B (histogram.rs: "histogram order is RGB").
+// One private histogram per warp (8 x 768 counters = 24 KB of shared memory): lanes of a warp still collide on popular bins,
+// warps do not.  V4: rows are 16-byte aligned and the width is a multiple of 4 -> four pixels per load.
+template <bool V4>
+__global__ void __launch_bounds__(256) histogram_bgra8_kernel(const uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
+                                                              unsigned long long* __restrict__ hist) {
+    __shared__ uint32_t sh[8][768];
+    for (int i = threadIdx.x; i < 8 * 768; i += 256) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    uint32_t* mine = sh[threadIdx.x >> 5];
+    auto count = [&](uint32_t v) {
+        atomicAdd(&mine[(v >> 16) & 0xffu], 1u);
+        atomicAdd(&mine[256u + ((v >> 8) & 0xffu)], 1u);
+        atomicAdd(&mine[512u + (v & 0xffu)], 1u);
+    };
+    const uint32_t we = V4 ? w / 4u : w;
+    const uint64_t total = (uint64_t)we * h;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / we), x = (uint32_t)(i - (uint64_t)y * we);
+        if (V4) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(px + (size_t)y * stride) + x);
+            count(v.x); count(v.y); count(v.z); count(v.w);
+        } else {
+            count(__ldcs(reinterpret_cast<const uint32_t*>(px + (size_t)y * stride) + x));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        uint32_t c = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c += sh[k][i];
+        if (c) atomicAdd(&hist[i], (unsigned long long)c);
+    }
+}
+// white_balance.rs:14-48.  One block of 256 threads: thread c < 3 scans channel c's histogram from both ends (both scans
+// compare against low_threshold, as the reference does), then thread v writes maps[c * 256 + v] for the three channels.
+// `high - low` is a usize subtraction in the reference: it wraps when the thresholds cross (release build semantics).
+__global__ void __launch_bounds__(256) white_balance_maps_kernel(const unsigned long long* __restrict__ hist, unsigned long long total_pixels,
+                                                                 double low_threshold, uint8_t* __restrict__ maps) {
+    __shared__ unsigned long long lo[3], hi[3];
+    const int t = threadIdx.x;
+    if (t < 3) {
+        const unsigned long long* hc = hist + t * 256;
+        const double pixel_count = (double)total_pixels;
+        unsigned long long low = 0, high = 255, area = 0;
+        for (int ix = 0; ix < 256; ++ix) { area += hc[ix]; if (__ddiv_rn((double)area, pixel_count) > low_threshold) { low = ix; break; } }
+        area = 0;
+        for (int ix = 255; ix >= 0; --ix) { area += hc[ix]; if (__ddiv_rn((double)area, pixel_count) > low_threshold) { high = ix; break; } }
+        lo[t] = low; hi[t] = high;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double scale = __ddiv_rn(255.0, (double)(hi[c] - lo[c]));                       // u64 wrap-around like usize
+        const unsigned long long d = (unsigned long long)t > lo[c] ? (unsigned long long)t - lo[c] : 0ull;   // saturating_sub
+        double m = round(__dmul_rn((double)d, scale));
+        m = fmax(fmin(m, 255.0), 0.0);                                                         // NaN -> 255 -> 255, as f64::min/max
+        maps[c * 256 + t] = (uint8_t)m;
+    }
+}
+// white_balance.rs:50-67: r, g, b through their byte maps, alpha untouched, in place
+template <bool V4>
+__global__ void __launch_bounds__(256) apply_byte_maps_bgra8_kernel(uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
+                                                                    const uint8_t* __restrict__ maps) {
+    __shared__ uint8_t sm[768];
+    for (int i = threadIdx.x; i < 768; i += 256) sm[i] = maps[i];
+    __syncthreads();
+    auto remap = [&](uint32_t v) {
+        return (v & 0xff000000u) | ((uint32_t)sm[(v >> 16) & 0xffu] << 16) | ((uint32_t)sm[256u + ((v >> 8) & 0xffu)] << 8) | (uint32_t)sm[512u + (v & 0xffu)];
+    };
+    const uint32_t we = V4 ? w / 4u : w;
+    const uint64_t total = (uint64_t)we * h;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / we), x = (uint32_t)(i - (uint64_t)y * we);
+        if (V4) {
+            uint4* p = reinterpret_cast<uint4*>(px + (size_t)y * stride) + x;
+            const uint4 v = *p;
+            *p = make_uint4(remap(v.x), remap(v.y), remap(v.z), remap(v.w));
+        } else {
+            uint32_t* p = reinterpret_cast<uint32_t*>(px + (size_t)y * stride) + x;
+            *p = remap(*p);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- fused down-scale kernel
 // One CTA = (job, strip of output columns, band of output rows).  Thread t owns source columns
 // k0+4t .. k0+4t+3 for the whole band:

@@ -181,6 +181,12 @@ def flow_bitmap_bgra_flip_horizontal_safe(bitmap: BitmapWindow) -> None:
     _check(lib().ifb200_flip_horizontal_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, buf, 512), buf)
 
 
+def white_balance_srgb_mut(bitmap: BitmapWindow, threshold: Optional[float] = None) -> None:
+    """flow/nodes/white_balance.rs:93-121 (WhiteBalanceHistogramAreaThresholdSrgb { threshold }), in place on a HOST bitmap."""
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_white_balance_srgb_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, -1.0 if threshold is None else float(threshold), buf, 512), buf)
+
+
 def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
     """flow/nodes/color.rs:86-225 presets (0 sepia ... 9 saturation)."""
     m = np.zeros(25, np.float32)
@@ -266,6 +272,12 @@ class Batch:
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_transpose(self._h, from_window.ptr, from_window.stride, from_window.w, from_window.h,
                                             to_window.ptr, to_window.stride, self._stream(stream), buf, 512), buf)
+
+    def white_balance(self, bitmap: BitmapWindow, threshold: Optional[float] = None, stream=None) -> None:
+        """flow/nodes/white_balance.rs:93-121 on a DEVICE bitmap, in place (three kernels, asynchronous on `stream`)."""
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_white_balance(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride,
+                                                -1.0 if threshold is None else float(threshold), self._stream(stream), buf, 512), buf)
 
     def flip_vertical(self, bitmap: BitmapWindow, stream=None) -> None:
         """graphics/flip.rs:10-22 on a DEVICE bitmap, in place."""

@@ -124,11 +124,17 @@ int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w
 int ifb200_flip_vertical_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t err_cap);
 int ifb200_flip_horizontal_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, char* err, size_t err_cap);
 
+/* Replaces the work of WhiteBalanceSrgbMutDef::mutate (flow/nodes/white_balance.rs:93-121): per-channel histograms
+ * (graphics/histogram.rs:7-20), area thresholds and byte maps (white_balance.rs:14-48), in-place remap of B, G, R (:50-67).
+ * threshold < 0 = None (0.006).  [SURVEY.md section 8(f), item 4] */
+int ifb200_white_balance_srgb_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, char* err, size_t err_cap);
+
 /* ---- device-resident batch API (the metric path; not in the reference) -----------------------
  * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
  * enqueue is asynchronous on `cuda_stream`, a cudaStream_t with the usual CUDA meaning (NULL = the legacy
  * default stream); pass IFB200_STREAM_OWN to use the batch's private non-blocking stream, which is the
- * stream ifb200_batch_sync waits on. */
+ * stream ifb200_batch_sync waits on.  The jobs of ONE call must be independent of each other (none may read what
+ * another writes): they may run concurrently.  Calls on the same stream are ordered as usual. */
 #define IFB200_STREAM_OWN ((void*)(intptr_t)-1)
 typedef struct ifb200_batch ifb200_batch;
 int  ifb200_batch_create(int device, ifb200_batch** out, char* err, size_t err_cap);
@@ -144,6 +150,8 @@ int  ifb200_batch_flip_vertical(ifb200_batch* b, uint8_t* dev_px, uint32_t w, ui
                                 void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
                                   void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, float threshold,
+                                void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
 void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */

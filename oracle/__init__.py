@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
     L.ifo_transpose.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, u8p, C.c_uint32]
     L.ifo_flip_vertical.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.ifo_flip_horizontal.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.ifo_white_balance.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, u8p]
     L.ifo_max_threads.restype = C.c_int
     _lib = L
     return L
@@ -203,3 +204,12 @@ def flip_vertical(px: np.ndarray, w=None) -> None:
 
 def flip_horizontal(px: np.ndarray, w=None) -> None:
     lib().ifo_flip_horizontal(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[1] if w is None else w, px.shape[0], px.strides[0])
+
+
+def white_balance(px: np.ndarray, threshold=None, w=None) -> np.ndarray:
+    """in place; returns the (3, 256) byte maps (R, G, B)."""
+    maps = np.zeros((3, 256), np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    lib().ifo_white_balance(px.ctypes.data_as(u8p), px.shape[1] if w is None else w, px.shape[0], px.strides[0],
+                            -1.0 if threshold is None else float(threshold), maps.ctypes.data_as(u8p))
+    return maps

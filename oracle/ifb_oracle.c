@@ -590,3 +590,39 @@ void ifo_flip_horizontal(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride) {
         for (uint32_t x = 0; x < w / 2; ++x) { const uint32_t t = r[x]; r[x] = r[w - 1 - x]; r[w - 1 - x] = t; }
     }
 }
+
+/* white_balance.rs:14-41 (area_threshold): note that BOTH scans compare against low_threshold, as the reference does */
+static void ifo_area_threshold(const uint64_t* hist, uint64_t total, double low_threshold, uint64_t* low_out, uint64_t* high_out) {
+    uint64_t low = 0, high = 255, area = 0;
+    const double pixel_count = (double)total;
+    for (int ix = 0; ix < 256; ++ix) { area += hist[ix]; if ((double)area / pixel_count > low_threshold) { low = (uint64_t)ix; break; } }
+    area = 0;
+    for (int ix = 255; ix >= 0; --ix) { area += hist[ix]; if ((double)area / pixel_count > low_threshold) { high = (uint64_t)ix; break; } }
+    *low_out = low; *high_out = high;
+}
+void ifo_white_balance(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, uint8_t* maps_out) {
+    uint64_t hist[3][256];
+    memset(hist, 0, sizeof hist);
+    for (uint32_t y = 0; y < h; ++y) {                               /* histogram.rs:7-20, order R, G, B */
+        const uint8_t* r = px + (size_t)y * stride;
+        for (uint32_t x = 0; x < w; ++x) { hist[0][r[x * 4 + 2]]++; hist[1][r[x * 4 + 1]]++; hist[2][r[x * 4 + 0]]++; }
+    }
+    const double low_threshold = (double)(threshold < 0.0f ? 0.006f : threshold);   /* white_balance.rs:76-77 */
+    uint8_t maps[3][256];
+    for (int c = 0; c < 3; ++c) {
+        uint64_t low, high;
+        ifo_area_threshold(hist[c], (uint64_t)w * h, low_threshold, &low, &high);
+        const double scale = 255.0 / (double)(high - low);           /* white_balance.rs:44-48; usize subtraction wraps in release builds */
+        for (uint64_t v = 0; v < 256; ++v) {
+            const uint64_t d = v > low ? v - low : 0;                /* saturating_sub */
+            double m = round((double)d * scale);
+            m = fmin(m, 255.0); m = fmax(m, 0.0);                    /* f64::min / f64::max ignore a NaN operand */
+            maps[c][v] = (uint8_t)m;
+        }
+    }
+    for (uint32_t y = 0; y < h; ++y) {                               /* white_balance.rs:50-67 */
+        uint8_t* r = px + (size_t)y * stride;
+        for (uint32_t x = 0; x < w; ++x) { r[x * 4 + 2] = maps[0][r[x * 4 + 2]]; r[x * 4 + 1] = maps[1][r[x * 4 + 1]]; r[x * 4 + 0] = maps[2][r[x * 4 + 0]]; }
+    }
+    if (maps_out) memcpy(maps_out, maps, sizeof maps);
+}

@@ -104,6 +104,10 @@ void ifo_transpose(const uint8_t* from, uint32_t from_stride, uint32_t w, uint32
 void ifo_flip_vertical(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride);
 void ifo_flip_horizontal(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride);
 
+/* flow/nodes/white_balance.rs:14-121 + graphics/histogram.rs:7-20, in place; threshold < 0 = None (0.006f32).
+ * maps_out (may be NULL) receives the three 256-entry byte maps in R, G, B order. */
+void ifo_white_balance(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, uint8_t* maps_out);
+
 int ifo_max_threads(void);
 
 #ifdef __cplusplus

@@ -399,6 +399,34 @@ def test_transpose_and_flips_match_oracle(ifb, torch_mod):
         ifb.bitmap_window_transpose(ifb.BitmapWindow.from_numpy(px.copy()), bad)
 
 
+def test_white_balance_matches_oracle(ifb, torch_mod):
+    """SURVEY section 8(f) item 4 (first half): WhiteBalanceHistogramAreaThresholdSrgb (white_balance.rs:14-121 + histogram.rs),
+    host drop-in and device call, bit-exact vs the oracle; default and explicit thresholds, flat images (high == low),
+    crossing thresholds (usize wrap), padded strides, alpha untouched."""
+    torch = torch_mod
+    batch = ifb.Batch(0)
+    rng = np.random.default_rng(7)
+    imgs = {
+        "normal": rng.normal(120, 30, (97, 301, 4)).clip(0, 255).astype(np.uint8),
+        "noise": util.noise(640, 480, seed=9, alpha_mode="mixed"),
+        "flat": np.full((16, 16, 4), 77, np.uint8),
+        "two_tone": np.concatenate([np.full((8, 31, 4), 20, np.uint8), np.full((8, 31, 4), 200, np.uint8)], axis=0),
+        "one_pixel": np.array([[[1, 2, 3, 4]]], np.uint8),
+    }
+    for name, px0 in imgs.items():
+        for thr in (None, 0.006, 0.05, 0.5, 0.9, 0.0):
+            exp = px0.copy(); oracle.white_balance(exp, thr)
+            got = util.padded(px0)
+            ifb.white_balance_srgb_mut(ifb.BitmapWindow.from_numpy(got), thr)
+            assert np.array_equal(got, exp), (name, thr)
+            assert np.array_equal(got[..., 3], px0[..., 3])
+            d = torch.from_numpy(px0.copy()).cuda()
+            batch.white_balance(ifb.BitmapWindow.from_torch(d), thr); batch.sync()
+            assert np.array_equal(d.cpu().numpy(), exp), (name, thr, "device")
+    with pytest.raises(ifb.FlowError):
+        ifb.white_balance_srgb_mut(ifb.BitmapWindow.from_numpy(imgs["flat"].copy()), float("nan"))
+
+
 def test_random_geometries_bit_exact(ifb, torch_mod):
     """40 seeded random (geometry, filter, alpha, compose, colourspace, rect) draws: whichever kernel the engine picks
     must match the oracle bit for bit; covers strip/band edges, odd widths, tiny and 1-pixel outputs."""

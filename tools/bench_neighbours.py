@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Measurement of the SURVEY.md section 8(f) neighbours of the resample path that are built: transpose, flips and apply_matte
+"""Measurement of the SURVEY.md section 8(f) neighbours of the resample path that are built: transpose, flips and white balance
 (the reference benchmarks transposes at 4K / 8K in benches/bench_graphics.rs:9-62).  Inputs resident in HBM, CUDA events on
 the launching stream, >= 3 warm-up calls; a set of 64 different images per size (>= 2 GB, far larger than L2) is cycled so that
 no call finds its data in cache.  One JSON line per (operation, size) with the HBM roofline of the kernel: algorithmic
@@ -28,18 +28,16 @@ def main():
     import oracle
     for (w, h) in ((3840, 2160), (7680, 4320)):
         n = 64 if w == 3840 else 16
-        imgs = torch.randint(0, 256, (n, h, w, 4), dtype=torch.uint8, device=dev)
+        imgs = (torch.randn((n, h, w, 4), device=dev) * 40 + 128).clamp_(0, 255).to(torch.uint8)
         outs = torch.empty((n, w, h, 4), dtype=torch.uint8, device=dev)
         ops = {
             "transpose": lambda i: batch.transpose(ifb.BitmapWindow.from_torch(imgs[i]), ifb.BitmapWindow.from_torch(outs[i]), stream),
             "flip_vertical": lambda i: batch.flip_vertical(ifb.BitmapWindow.from_torch(imgs[i]), stream),
             "flip_horizontal": lambda i: batch.flip_horizontal(ifb.BitmapWindow.from_torch(imgs[i]), stream),
-            "apply_matte": None,
+            "white_balance": lambda i: batch.white_balance(ifb.BitmapWindow.from_torch(imgs[i]), None, stream),
         }
-        host = np.random.default_rng(1).integers(0, 256, (h, w, 4), dtype=np.uint8)
+        host = np.random.default_rng(1).normal(128, 40, (h, w, 4)).clip(0, 255).astype(np.uint8)      # a bell-shaped histogram
         for name, fn in ops.items():
-            if fn is None:
-                continue
             for i in range(n):          # warm-up: every image once
                 fn(i)
             torch.cuda.synchronize()
@@ -51,11 +49,13 @@ def main():
                     fn(i)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / (reps * n)
-            alg = w * h * 8
+            alg = w * h * (12 if name == "white_balance" else 8)   # white balance: histogram pass (4 B/px) + remap pass (4 + 4 B/px)
             # parity spot check + CPU time of the oracle loop
             t0 = time.perf_counter()
             if name == "transpose":
                 exp = np.zeros((w, h, 4), np.uint8); oracle.transpose(host, exp)
+            elif name == "white_balance":
+                exp = host.copy(); oracle.white_balance(exp)
             else:
                 exp = host.copy(); (oracle.flip_vertical if name == "flip_vertical" else oracle.flip_horizontal)(exp)
             cpu_ms = (time.perf_counter() - t0) * 1e3
@@ -63,6 +63,8 @@ def main():
             if name == "transpose":
                 o = torch.empty((w, h, 4), dtype=torch.uint8, device=dev)
                 batch.transpose(ifb.BitmapWindow.from_torch(d), ifb.BitmapWindow.from_torch(o), stream); got = o
+            elif name == "white_balance":
+                batch.white_balance(ifb.BitmapWindow.from_torch(d), None, stream); got = d
             else:
                 (batch.flip_vertical if name == "flip_vertical" else batch.flip_horizontal)(ifb.BitmapWindow.from_torch(d), stream); got = d
             torch.cuda.synchronize()
