@@ -194,7 +194,7 @@ void build_tile(Plan& p) {
     if (!monotone(p.wv) || !monotone(p.wh)) return;
     TilePlanDev t{};
     t.in_w = p.in_w; t.in_h = p.in_h; t.out_w = p.out_w; t.out_h = p.out_h;
-    t.tow = 64; t.toh = 16;
+    t.tow = kTile2W; t.toh = kTile2H;                       // 64 x 16: both tile kernels
     t.tiles_x = (int)((p.out_w + t.tow - 1) / t.tow); t.tiles_y = (int)((p.out_h + t.toh - 1) / t.toh);
     for (int tx = 0; tx < t.tiles_x; ++tx) {
         const uint32_t X0 = tx * t.tow, X1 = std::min<uint32_t>(X0 + t.tow, p.out_w);
@@ -350,6 +350,15 @@ const FusedEntry* find_fused(int av, int sh, int ch, int nt) {
     return nullptr;
 }
 
+// tile kernel (second form) dispatch: compiled per (channels, working space, compositing mode, colour matrix).
+// Without meaningful alpha the compositing mode changes nothing (scaling.rs:227-232, :262), so those share compose 0.
+using Tile2Fn = void (*)(const JobDev*, uint32_t, Tables, AxisDev, AxisDev, TilePlanDev);
+#define IFB_T2_CM(CH_, LIN_, CO_) {fused_tile2_kernel<CH_, LIN_, CO_, false>, fused_tile2_kernel<CH_, LIN_, CO_, true>}
+#define IFB_T2_CO4(LIN_) {IFB_T2_CM(4, LIN_, 0), IFB_T2_CM(4, LIN_, 1), IFB_T2_CM(4, LIN_, 2)}
+#define IFB_T2_CO3(LIN_) {IFB_T2_CM(3, LIN_, 0), IFB_T2_CM(3, LIN_, 0), IFB_T2_CM(3, LIN_, 0)}
+const Tile2Fn kTile2[2][2][3][2] = {{IFB_T2_CO3(false), IFB_T2_CO3(true)}, {IFB_T2_CO4(false), IFB_T2_CO4(true)}};   // [ch==4][linear][compose][cm]
+Tile2Fn find_tile2(int ch, bool linear, int compose, bool cm) { return kTile2[ch == 4][linear][compose][cm]; }
+
 // ------------------------------------------------------------------------------------------------
 struct PinnedSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
 
@@ -372,6 +381,8 @@ struct ifb200_batch {
     std::vector<PinnedSlot> pinned;
     // options
     bool force_generic = false; int nt = 256; int min_ctas = 296;
+    int tile_variant = 0;    // IFB200_OPT_TILE_KERNEL: 0 default, 1 first form (fused_tile_kernel), 2 second form (fused_tile2_kernel)
+    int sm_count = 148;
     bool ring_ok = true;     // the shared window is laid out as the ring kernel's LUT gather assumes (smem_base_probe_kernel)
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
@@ -547,6 +558,11 @@ JobDev make_job(const ifb200_resample_desc& d, const float* t_lin_host, const fl
             for (int k = 0; k < 4; ++k) j.cm[c * 5 + k] = m[k * 5 + c];
             j.cm[c * 5 + 4] = m[4 * 5 + c] * 255.0f;
         }
+        // r,g,b from r,g,b only, alpha passes through, no bias (sepia, the grayscales, ...): the second tile kernel skips
+        // the zero terms, which is exact (see finish_pixel_sm)
+        bool rgb3 = j.cm[15] == 0.0f && j.cm[16] == 0.0f && j.cm[17] == 0.0f && j.cm[18] == 1.0f && j.cm[19] == 0.0f;
+        for (int c = 0; c < 3; ++c) rgb3 = rgb3 && j.cm[c * 5 + 3] == 0.0f && j.cm[c * 5 + 4] == 0.0f;
+        if (rgb3) j.flags |= JF_CM_RGB3;
     }
     return j;
 }
@@ -564,7 +580,9 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
     b->prebuild_plans(descs, n);
     // group jobs by (plan, kernel class)
-    struct Group { Plan* plan; int ch; int kind; bool simple; std::vector<size_t> idx; };   // kind: 0 generic pair, 1 fused ring, 2 tile
+    // kind: 0 generic pair, 1 fused ring, 2 tile (first form), 3 tile (second form; `variant` = its compile-time case)
+    struct Group { Plan* plan; int ch; int kind; bool simple; int variant; std::vector<size_t> idx; };
+    const int tile_kind = b->tile_variant == 1 ? 2 : 3;
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
         validate(descs[i]);
@@ -578,11 +596,12 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         // the ring kernel streams every source row once and wins whenever rows outnumber outputs (down-scales);
         // for up-scales / 1:1 the tile kernel does less work per source pixel
         const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || (p.out_h >= p.in_h && p.out_w >= p.in_w));
-        const int kind = prefer_tile ? 2 : (fused ? 1 : 0);
+        const int kind = prefer_tile ? tile_kind : (fused ? 1 : 0);
         const bool simple = d.compose == IFB200_REPLACE_SELF && !d.color_matrix;   // store epilogue without composite / matrix code
+        const int variant = kind == 3 ? ((d.linear ? 1 : 0) | ((ch == 4 ? d.compose : 0) << 1) | (d.color_matrix ? 8 : 0)) : 0;
         Group* g = nullptr;
-        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind && gg.simple == simple) { g = &gg; break; }
-        if (!g) { groups.push_back(Group{&p, ch, kind, simple, {}}); g = &groups.back(); }
+        for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind && gg.simple == simple && gg.variant == variant) { g = &gg; break; }
+        if (!g) { groups.push_back(Group{&p, ch, kind, simple, variant, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
     // job array -> device (pinned staging, stream ordered)
@@ -613,7 +632,27 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         const JobDev* jobs = dj + gstart[gi];
         const size_t nj = g.idx.size();
         st = fork ? b->side[gi % ifb200_batch::kSideStreams] : user_stream;
-        if (g.kind == 2) {
+        if (g.kind == 3) {
+            // persistent CTAs: as many as fit on the device (or one per tile if there are fewer tiles), each walks
+            // tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the (job, tile) list
+            const TilePlanDev& t = p.tile;
+            ensure_axes(b, st, p);
+            const bool linear = g.variant & 1;
+            Tile2Fn fn = find_tile2(g.ch, linear, (g.variant >> 1) & 3, (g.variant & 8) != 0);
+            const size_t smem = Tile2Smem::make(t.max_ir, t.max_ic, linear).total;
+            CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, 256, smem));
+            const uint64_t resident = (uint64_t)std::max(per_sm, 1) * b->sm_count;
+            for (size_t off = 0; off < nj; off += 65535) {
+                const size_t cnt = std::min<size_t>(65535, nj - off);
+                const uint64_t total = (uint64_t)cnt * t.tiles_x * t.tiles_y;
+                fn<<<(unsigned)std::min<uint64_t>(total, resident), 256, smem, st>>>(jobs + off, (uint32_t)cnt, b->tables, p.dv.view(*p.axes), p.dh.view(*p.axes), t);
+                CUDA_OK(cudaGetLastError());
+                b->launches++;
+            }
+            b->tile_jobs += nj;
+        } else if (g.kind == 2) {
             const TilePlanDev& t = p.tile;
             ensure_axes(b, st, p);
             const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
@@ -833,6 +872,7 @@ ifb200_batch* create_batch(int device) {
     ifb::byte_to_float_table(true, tl.data()); ifb::byte_to_float_table(false, ts.data()); ifb::linear_to_srgb_table(lut.data());
     b->t_lin.upload(tl); b->t_srgb.upload(ts); b->lut16k.upload(lut);
     b->tables = Tables{b->t_lin.p, b->t_srgb.p, b->lut16k.p};
+    CUDA_OK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
     {   // the ring kernel folds the shared-window offset of dynamic shared memory into its LUT gather: verify it once
         DevVec<uint32_t> probe; probe.upload(std::vector<uint32_t>(1, 0xffffffffu));
         CUDA_OK(cudaFuncSetAttribute((const void*)smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1008,6 +1048,9 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     case IFB200_OPT_MIN_CTAS:
         if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
         b->min_ctas = (int)value; return IFB200_OK;
+    case IFB200_OPT_TILE_KERNEL:
+        if (value < 0 || value > 2) return IFB200_ERR_INVALID_ARGUMENT;
+        b->tile_variant = (int)value; return IFB200_OK;
     default: return IFB200_ERR_INVALID_ARGUMENT;
     }
 }

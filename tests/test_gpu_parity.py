@@ -34,9 +34,10 @@ def _oracle(inp, canvas, **kw):
 
 def _gpu_batch(ifb, torch, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen=0.0, linear=True,
                alpha_meaningful=False, compose=0, matte=(0, 0, 0, 0), color_matrix=None, force_generic=False, nt=256,
-               min_ctas=None):
+               min_ctas=None, tile_kernel=0, counters=None):
     b = ifb.Batch(0)
     b.set_option(ifb.Batch.OPT_FORCE_GENERIC, int(force_generic))
+    b.set_option(ifb.Batch.OPT_TILE_KERNEL, tile_kernel)
     b.set_option(ifb.Batch.OPT_THREADS_PER_CTA, nt)
     if min_ctas is not None:
         b.set_option(ifb.Batch.OPT_MIN_CTAS, min_ctas)
@@ -57,6 +58,8 @@ def _gpu_batch(ifb, torch, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, s
     b.scale_and_render_many([(wi, wc, p, color_matrix)], stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     took_fused = b.fused_jobs
+    if counters is not None:
+        counters.update(fused=b.fused_jobs, tile=b.tile_jobs, generic=b.generic_jobs)
     out = tc.cpu().numpy().copy()
     b.close()
     return out, took_fused
@@ -160,6 +163,69 @@ def test_fused_color_matrix_epilogue(ifb, torch_mod):
         exp = _oracle(inp, canvas, **kw)
         got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, **kw)
         assert util.diff_stats(got, exp)[0] == 0
+
+
+TILE_CASES = [
+    # (in_w, in_h, out_w, out_h, filter): geometries the engine gives to the tile kernel (up-scales, 1:1, small windows)
+    (64, 64, 128, 128, 14),          # 2x Mitchell (config-4 ratio)
+    (100, 60, 333, 200, 4),          # 3.33x Ginseng, ragged tiles
+    (256, 256, 256, 256, 2),         # 1:1 Robidoux
+    (33, 17, 70, 50, 2),             # odd sizes, source narrower than one tile
+    (5, 3, 200, 100, 14),            # 40x: every tile reads the whole source
+    (300, 40, 310, 47, 13),          # barely an up-scale, CatmullRom
+    (480, 270, 960, 540, 14),        # config 4 at quarter size: many tiles per persistent CTA
+]
+
+
+@pytest.mark.parametrize("tile_kernel", [1, 2], ids=["tile1", "tile2"])
+@pytest.mark.parametrize("case", TILE_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_tile_kernel_forms_bit_exact(ifb, torch_mod, case, tile_kernel):
+    """both forms of the tile kernel, every compile-time case of the second (channels x working space x compositing mode
+    x colour matrix, general and rgb-only matrices), destination rect inside a larger canvas: bit-exact against the oracle"""
+    iw, ih, ow, oh, flt = case
+    sepia = ifb.color_filter_matrix(0)
+    general = ifb.color_filter_matrix(6, 0.5)        # alpha row != identity: the general 4x5 path
+    general[4, 0] = 0.1                               # and a bias
+    combos = [(a, l, c, m) for a in (False, True) for l in (True, False) for c in (0, 1, 2) for m in (None, sepia)]
+    combos += [(True, True, 1, general), (False, False, 0, general)]
+    rng = np.random.default_rng(iw * 7 + oh)
+    if ow * oh > 100000:                              # the big case: a sample of the combinations
+        combos = [combos[i] for i in rng.choice(len(combos), 6, replace=False)] + [(True, True, 1, sepia)]
+    for alpha, linear, compose, cm in combos:
+        inp = util.noise(iw, ih, seed=iw + 3 * oh + compose, alpha_mode="mixed" if alpha else "opaque")
+        canvas = util.noise(ow + 5, oh + 3, seed=77 + compose, alpha_mode="mixed")
+        kw = dict(x=2, y=1, w=ow, h=oh, filter=flt, alpha_meaningful=alpha, linear=linear, compose=compose,
+                  matte=(40, 120, 250, 200), color_matrix=cm)
+        exp = _oracle(inp, canvas, **kw)
+        cnt = {}
+        got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, tile_kernel=tile_kernel, counters=cnt, **kw)
+        assert cnt["tile"] == 1, (case, cnt)
+        mx, n = util.diff_stats(got, exp)
+        assert mx == 0, (case, alpha, linear, compose, cm is not None, mx, n)
+
+
+def test_tile_kernel_forms_agree_at_full_size(ifb, torch_mod):
+    """config 4 (1080p -> 4K Mitchell, sepia, composited over a canvas) at full size: the two forms agree bit for bit"""
+    torch = torch_mod
+    from imageflow_b200 import synth
+    cm = ifb.color_filter_matrix(0)
+    ins = [synth.noise_torch(1920, 1080, seed=700 + i, alpha_mode="mixed") for i in range(3)]
+    cv0 = [synth.noise_torch(3840, 2160, seed=800 + i, alpha_mode="mixed") for i in range(3)]
+    outs = {}
+    for form in (1, 2):
+        b = ifb.Batch(0)
+        b.set_option(ifb.Batch.OPT_TILE_KERNEL, form)
+        cvs = [c.clone() for c in cv0]
+        p = ifb.ScaleAndRenderParams(w=3840, h=2160, interpolation_filter=ifb.Filter(14))
+        b.scale_and_render_many([(ifb.BitmapWindow.from_torch(ins[i], alpha_meaningful=True),
+                                  ifb.BitmapWindow.from_torch(cvs[i], compose=ifb.BitmapCompositing(1)), p, cm) for i in range(3)],
+                                stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert b.tile_jobs == 3
+        b.close()
+        outs[form] = cvs
+    for i in range(3):
+        assert torch.equal(outs[1][i], outs[2][i])
 
 
 def test_dropin_host_call_matches_oracle(ifb):
