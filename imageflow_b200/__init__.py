@@ -12,14 +12,14 @@ All arithmetic runs in hand-written sm_100a kernels inside libifb200.so (include
 this package only marshals arguments.  Nothing here imports the CPU oracle.
 """
 from .graphics import (Batch, apply_matte, BitmapCompositing, BitmapWindow, ErrorKind, Filter, FlowError, ScaleAndRenderParams,
-                       WorkingFloatspace, color_filter_matrix, device_count, populate_weights, scale_and_render, scale_and_render_many,
+                       WorkingFloatspace, color_filter_matrix, device_count, plan_probe, populate_weights, scale_and_render, scale_and_render_many,
                        window_bgra32_apply_color_matrix, bitmap_window_transpose, flow_bitmap_bgra_flip_vertical_safe,
                        flow_bitmap_bgra_flip_horizontal_safe, white_balance_srgb_mut)
 from ._lib import LIB_PATH, ResampleDesc, lib
 
 __all__ = [
     "Batch", "apply_matte", "BitmapCompositing", "BitmapWindow", "ErrorKind", "Filter", "FlowError", "ScaleAndRenderParams",
-    "WorkingFloatspace", "color_filter_matrix", "device_count", "populate_weights", "scale_and_render", "scale_and_render_many",
+    "WorkingFloatspace", "color_filter_matrix", "device_count", "plan_probe", "populate_weights", "scale_and_render", "scale_and_render_many",
     "window_bgra32_apply_color_matrix", "bitmap_window_transpose", "flow_bitmap_bgra_flip_vertical_safe",
     "flow_bitmap_bgra_flip_horizontal_safe", "white_balance_srgb_mut", "LIB_PATH", "ResampleDesc", "lib",
 ]

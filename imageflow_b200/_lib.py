@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("IFB200_LIB") or os.path.join(_HERE, "libifb200.so")  
 # every symbol include/ifb200.h declares (tests/test_boundary.py checks the header against this list)
 SYMBOLS = [
     "ifb200_abi_version", "ifb200_status_name", "ifb200_device_count", "ifb200_weights",
-    "ifb200_byte_to_float_table", "ifb200_linear_to_srgb_table", "ifb200_color_filter_matrix",
+    "ifb200_byte_to_float_table", "ifb200_linear_to_srgb_table", "ifb200_color_filter_matrix", "ifb200_plan_probe",
     "ifb200_scale_and_render", "ifb200_scale_and_render_many", "ifb200_color_matrix_bgra8", "ifb200_apply_matte_bgra8", "ifb200_batch_apply_matte",
     "ifb200_transpose_bgra8", "ifb200_flip_vertical_bgra8", "ifb200_flip_horizontal_bgra8",
     "ifb200_batch_transpose", "ifb200_batch_flip_vertical", "ifb200_batch_flip_horizontal",
@@ -59,6 +59,9 @@ def lib() -> C.CDLL:
     L.ifb200_linear_to_srgb_table.restype = None
     L.ifb200_color_filter_matrix.argtypes = [C.c_int, C.c_float, f32p]
     L.ifb200_color_filter_matrix.restype = C.c_int
+    L.ifb200_plan_probe.argtypes = [C.POINTER(ResampleDesc), C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]
+    L.ifb200_plan_probe.restype = C.c_int
     L.ifb200_scale_and_render.argtypes = [C.POINTER(ResampleDesc), C.c_char_p, C.c_size_t]
     L.ifb200_scale_and_render.restype = C.c_int
     L.ifb200_scale_and_render_many.argtypes = [C.POINTER(ResampleDesc), C.c_size_t, C.c_char_p, C.c_size_t]

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -90,10 +91,14 @@ struct DevBlob {
     size_t add(const void* src, size_t bytes) {
         const size_t off = (host.size() + 255) / 256 * 256;
         host.resize(off + bytes);
-        if (bytes) memcpy(host.data() + off, src, bytes);
+        if (bytes && src) memcpy(host.data() + off, src, bytes);
         return off;
     }
     template <class T> size_t add(const std::vector<T>& v) { return add(v.data(), v.size() * sizeof(T)); }
+    // a zero-filled region to be built in place: take the pointer with host_at() AFTER the last add of the group
+    size_t add_zeroed(size_t bytes) { return add(nullptr, bytes); }
+    template <class T> T* host_at(size_t off) { return reinterpret_cast<T*>(host.data() + off); }
+    void reserve(size_t bytes) { host.reserve(bytes); }
     void commit(ifb200_batch* b, cudaStream_t st);
     void use_on(cudaStream_t st) {
         if (done || st == up_stream) return;
@@ -144,6 +149,7 @@ struct Plan {
     int av = 0, sh = 0;
     std::vector<uint32_t> vdone_host;
     std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
+    std::vector<int> nt_failed;         // CTA sizes whose strips cannot hold this geometry (e.g. 3000 -> 1 columns): not fused
 };
 
 bool monotone(const ifb::AxisWeights& a) {
@@ -211,10 +217,10 @@ void build_tile(Plan& p) {
 
 // per-source-row program: weight (float bits) per ring slot -- output row y owns slot y mod AV while its window is
 // open (build_fused_v guarantees at most AV consecutive rows are open at once) -- then the completion word
-std::vector<uint32_t> fused_vprog_host(const Plan& p) {
+size_t fused_vprog_bytes(const Plan& p) { return (size_t)p.in_h * (((uint32_t)p.av + 1 + 3) / 4 * 4) * sizeof(uint32_t); }
+void fused_vprog_host(const Plan& p, uint32_t* prog) {      // prog: fused_vprog_bytes(p) zeroed bytes
     const uint32_t nw = (uint32_t)p.av;
     const uint32_t words = (nw + 1 + 3) / 4 * 4;
-    std::vector<uint32_t> prog((size_t)p.in_h * words, 0u);
     const auto& a = p.wv;
     for (uint32_t y = 0; y < a.out_size; ++y) {
         const float* w = a.w.data() + a.offset[y];
@@ -227,7 +233,6 @@ std::vector<uint32_t> fused_vprog_host(const Plan& p) {
         const uint32_t d = p.vdone_host[j];
         if (d & 0xffu) prog[(size_t)j * words + nw] = (d & ~0xffu) | (((d >> 8) % nw) << 4) | (d & 0xfu);
     }
-    return prog;
 }
 
 // host half: strips, H-weight block, reader meta, row program and band tables, staged in ft->blob.host (no CUDA calls)
@@ -263,8 +268,15 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
     }
     ft->n_strips = (int)ns;
     const int SH = p.sh;
-    std::vector<float> hw((size_t)ns * SH * 4 * nt, 0.0f);
-    std::vector<uint32_t> hrd((size_t)ns * nt, 0u);
+    // everything the kernel reads for this (plan, CTA size) goes into one allocation and one asynchronous copy; the
+    // tables are built in place in the staging blob (no intermediate vectors)
+    const size_t n_hw = (size_t)ns * SH * 4 * nt, n_hrd = (size_t)ns * nt;
+    ft->blob.reserve(strips.size() * sizeof(StripDev) + (n_hw + n_hrd) * 4 + fused_vprog_bytes(p) + 6 * 256 + 16 * 1024);
+    ft->o_strips = ft->blob.add(strips);
+    ft->o_hw = ft->blob.add_zeroed(n_hw * sizeof(float));
+    ft->o_hrd = ft->blob.add_zeroed(n_hrd * sizeof(uint32_t));
+    float* const hw = ft->blob.host_at<float>(ft->o_hw);
+    uint32_t* const hrd = ft->blob.host_at<uint32_t>(ft->o_hrd);
     for (uint32_t s = 0; s < ns; ++s) {
         const StripDev& sd = strips[s];
         uint32_t Xlo = sd.X0;     // first output of the strip whose window may still reach the current group
@@ -295,9 +307,8 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
             hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12) | ((X % (uint32_t)SH) << 28);
         }
     }
-    // everything the kernel reads for this (plan, CTA size) goes into one allocation and one asynchronous copy
-    ft->o_strips = ft->blob.add(strips); ft->o_hw = ft->blob.add(hw); ft->o_hrd = ft->blob.add(hrd);
-    ft->o_vprog[0] = ft->blob.add(fused_vprog_host(p));
+    ft->o_vprog[0] = ft->blob.add_zeroed(fused_vprog_bytes(p));
+    fused_vprog_host(p, ft->blob.host_at<uint32_t>(ft->o_vprog[0]));
     for (int nb = 1; ; nb *= 2) {                        // band tables for power-of-two band counts
         const int use = std::min<int>(nb, (int)std::max<uint32_t>(1u, p.out_h / 8u));
         if (!ft->o_bands.count(use)) {
@@ -311,6 +322,17 @@ std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
         if (use < nb || nb >= 4096) break;
     }
     return ft;
+}
+
+// The host tables of (plan, CTA size) exist or can be built.  A geometry whose H windows are wider than a strip (a
+// 3000 -> 1 column down-scale has 1400+ taps) cannot run on the ring kernel at that CTA size: it is remembered as such and
+// the job takes the tile kernel or the generic pair instead of failing.
+bool fused_host_ready(Plan& p, int nt) {
+    if (!p.fused_ok) return false;
+    if (p.by_nt.count(nt)) return true;
+    if (std::find(p.nt_failed.begin(), p.nt_failed.end(), nt) != p.nt_failed.end()) return false;
+    try { p.by_nt.emplace(nt, fused_tables_host(p, nt)); return true; }
+    catch (const Err& e) { p.nt_failed.push_back(nt); if (p.fused_reason.empty()) p.fused_reason = e.msg; return false; }
 }
 
 // device half: one allocation + one asynchronous copy on the first use; later uses only order their stream after it
@@ -451,8 +473,7 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
         build_fused_v(*p);
         build_tile(*p);
-        if (p->fused_ok && !(p->tile_ok && p->out_h >= p->in_h && p->out_w >= p->in_w))
-            p->by_nt.emplace(nt, fused_tables_host(*p, nt));
+        if (p->fused_ok && !(p->tile_ok && p->out_h >= p->in_h && p->out_w >= p->in_w)) fused_host_ready(*p, nt);
         return p;
     }
     Plan& plan_for(const ifb200_resample_desc& d) {
@@ -593,9 +614,11 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
                      (d.in_stride >= ((uint64_t)d.in_w * 4 + 15) / 16 * 16);
         const int ch = d.alpha_meaningful ? 4 : 3;
         if (fused && !find_fused(p.av, p.sh, ch, b->nt)) fused = false;
+        const bool upscale = p.out_h >= p.in_h && p.out_w >= p.in_w;
+        if (fused && !(p.tile_ok && upscale) && !fused_host_ready(p, b->nt)) fused = false;   // windows wider than a strip
         // the ring kernel streams every source row once and wins whenever rows outnumber outputs (down-scales);
         // for up-scales / 1:1 the tile kernel does less work per source pixel
-        const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || (p.out_h >= p.in_h && p.out_w >= p.in_w));
+        const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || upscale);
         const int kind = prefer_tile ? tile_kind : (fused ? 1 : 0);
         const bool simple = d.compose == IFB200_REPLACE_SELF && !d.color_matrix;   // store epilogue without composite / matrix code
         const int variant = kind == 3 ? ((d.linear ? 1 : 0) | ((ch == 4 ? d.compose : 0) << 1) | (d.color_matrix ? 8 : 0)) : 0;
@@ -955,6 +978,58 @@ int ifb200_weights(int filter, double kws, int lobe_mode, float lobe_value, uint
 
 void ifb200_byte_to_float_table(int linear, float out[256]) { ifb::byte_to_float_table(linear != 0, out); }
 void ifb200_linear_to_srgb_table(uint8_t out[16384]) { ifb::linear_to_srgb_table(out); }
+// Host-side cost of preparing the kernel tables of n geometries: builds the plans (weights as weights.rs, ring / tile
+// tables) on `threads` host threads and discards them.  No CUDA call, no cache: what a mixed workload pays per new geometry.
+int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, double* seconds, uint64_t* table_bytes, uint64_t* table_hash,
+                      char* err, size_t err_cap) {
+    return guarded(err, err_cap, [&] {
+        if (!descs && n) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null descriptor array");
+        for (size_t i = 0; i < n; ++i) {
+            const auto& d = descs[i];
+            if (d.w == 0 || d.h == 0 || d.in_w == 0 || d.in_h == 0) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "empty bitmap");
+            if (d.filter < 1 || d.filter > 31) IFB_THROW(IFB200_ERR_BAD_FILTER, "unknown filter id %d", d.filter);
+        }
+        std::atomic<size_t> next{0};
+        std::atomic<uint64_t> bytes{0};
+        std::vector<uint64_t> hashes(table_hash ? n : 0, 0);         // FNV-1a of each plan's staged tables and CSR windows
+        auto fnv = [](uint64_t h, const void* p, size_t nb) {
+            const uint8_t* b = static_cast<const uint8_t*>(p);
+            for (size_t i = 0; i < nb; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+            return h;
+        };
+        std::vector<Err> errs((size_t)std::max(threads, 1), Err{0, ""});
+        auto worker = [&](int me) {
+            try {
+                for (size_t i; (i = next.fetch_add(1)) < n;) {
+                    auto p = ifb200_batch::build_plan_host(descs[i], 256);
+                    uint64_t b = 0;
+                    for (auto& kv : p->by_nt) b += kv.second->blob.host.size();
+                    bytes += b;
+                    if (table_hash) {
+                        uint64_t h = 14695981039346656037ull;
+                        for (auto& kv : p->by_nt) h = fnv(h, kv.second->blob.host.data(), kv.second->blob.host.size());
+                        for (const ifb::AxisWeights* a : {&p->wv, &p->wh}) {
+                            h = fnv(h, a->left.data(), a->left.size() * 4); h = fnv(h, a->right.data(), a->right.size() * 4);
+                            h = fnv(h, a->offset.data(), a->offset.size() * 4); h = fnv(h, a->w.data(), a->w.size() * 4);
+                        }
+                        hashes[i] = h;
+                    }
+                }
+            } catch (const Err& e) { errs[me] = e; }
+        };
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+        worker(0);
+        for (auto& th : pool) th.join();
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        for (auto& e : errs) if (e.code) throw e;
+        if (seconds) *seconds = dt;
+        if (table_bytes) *table_bytes = bytes.load();
+        if (table_hash) { uint64_t h = 14695981039346656037ull; *table_hash = fnv(h, hashes.data(), hashes.size() * 8); }
+    });
+}
+
 int  ifb200_color_filter_matrix(int which, float p, float out[25]) { return out ? ifb::color_filter_matrix(which, p, out) : IFB200_ERR_INVALID_ARGUMENT; }
 
 int ifb200_batch_create(int device, ifb200_batch** out, char* err, size_t cap) {

@@ -183,9 +183,14 @@ int compute_axis_weights(int filter_id, double kernel_width_scale, Lobe lobe, fl
     out = AxisWeights();
     out.in_size = in_size; out.out_size = out_size;
     out.left.resize(out_size); out.right.resize(out_size); out.offset.resize(static_cast<size_t>(out_size) + 1);
-    out.w.reserve(static_cast<size_t>(out_size) * std::min<uint32_t>(max_window, in_size));
-    std::vector<float> win;
-    win.reserve(max_window);
+    // Windows are written straight into out.w (sized for the worst case, cut back at the end); the filter's case analysis
+    // is hoisted out of the tap loop.  With blur == 1 the division x / blur is the identity and is skipped.
+    const size_t cap = static_cast<size_t>(out_size) * std::min<uint32_t>(max_window, in_size);
+    out.w.resize(cap);
+    float* const wbase = out.w.data();
+    size_t used = 0;
+    const bool unit_blur = k.blur == 1.0;
+    const bool plain_cubic = k.shape == Shape::Cubic && unit_blur;
 
     for (uint32_t u = 0; u < out_size; ++u) {
         const double center = (u + 0.5) / scale - 0.5;
@@ -195,13 +200,21 @@ int compute_axis_weights(int filter_id, double kernel_width_scale, Lobe lobe, fl
         uint32_t last = static_cast<uint32_t>(std::min(hi, static_cast<int32_t>(in_size) - 1));
         const uint32_t count = last - first + 1u;
         if (count > max_window) return IFB200_ERR_SOURCE_COUNT_TOO_LARGE;
+        if (used + count > cap) return IFB200_ERR_SOURCE_COUNT_TOO_LARGE;
 
-        win.clear();
+        float* const win = wbase + used;
         double sum = 0.0, sum_neg = 0.0, sum_pos = 0.0;
-        for (uint32_t ix = first; ix <= last; ++ix) {
-            double v = k.eval(down * (static_cast<double>(ix) - center));
+        for (uint32_t i = 0; i < count; ++i) {
+            const double x = down * (static_cast<double>(first + i) - center);
+            double v;
+            if (plain_cubic) {                                      // Kernel::eval, Shape::Cubic with t = |x| / 1.0
+                const double t = std::fabs(x);
+                v = t < 1.0 ? k.p1 + t * (t * (k.p2 + t * k.p3)) : (t < 2.0 ? k.q1 + t * (k.q2 + t * (k.q3 + t * k.q4)) : 0.0);
+            } else {
+                v = k.eval(x);
+            }
             if (std::fabs(v) <= 2e-8) v = 0.0;                      // weights.rs:728-730
-            win.push_back(static_cast<float>(v));
+            win[i] = static_cast<float>(v);
             sum += v;
             sum_neg += std::min(v, 0.0);
             sum_pos += std::max(v, 0.0);
@@ -219,16 +232,18 @@ int compute_axis_weights(int filter_id, double kernel_width_scale, Lobe lobe, fl
                 return IFB200_ERR_TOTAL_WEIGHT_ZERO;
             }
         }
-        for (float& v : win) v *= (v < 0.0f) ? scale_neg : scale_pos;
+        for (uint32_t i = 0; i < count; ++i) win[i] *= (win[i] < 0.0f) ? scale_neg : scale_pos;
 
-        size_t b = 0, e = win.size();                               // zero-trim, weights.rs:771-782
+        size_t b = 0, e = count;                                    // zero-trim, weights.rs:771-782
         while (e > b && win[e - 1] == 0.0f) { --e; --last; }
         while (b < e && win[b] == 0.0f) { ++b; ++first; }
         if (b == e) return IFB200_ERR_NO_PIXEL_INPUTS;
-        out.left[u] = first; out.right[u] = last; out.offset[u] = static_cast<uint32_t>(out.w.size());
-        out.w.insert(out.w.end(), win.begin() + b, win.begin() + e);
+        if (b) std::memmove(win, win + b, (e - b) * sizeof(float));
+        out.left[u] = first; out.right[u] = last; out.offset[u] = static_cast<uint32_t>(used);
+        used += e - b;
         out.max_taps = std::max<uint32_t>(out.max_taps, static_cast<uint32_t>(e - b));
     }
+    out.w.resize(used);
     out.offset[out_size] = static_cast<uint32_t>(out.w.size());
     return IFB200_OK;
 }

@@ -211,6 +211,20 @@ def populate_weights(filter: int, out_size: int, in_size: int, kernel_width_scal
     return [(int(left[i]), int(right[i]), w[off[i]:off[i + 1]].copy()) for i in range(out_size)]
 
 
+def plan_probe(geometries, threads: int = 1, want_hash: bool = False) -> dict:
+    """Host-side cost of preparing kernel tables: builds (and discards) the plans of `geometries` =
+    [(in_w, in_h, out_w, out_h[, filter[, sharpen_percent]])] on `threads` host threads.  No CUDA call."""
+    arr = (ResampleDesc * len(geometries))()
+    for d, g in zip(arr, geometries):
+        d.in_w, d.in_h, d.w, d.h = g[:4]
+        d.filter = g[4] if len(g) > 4 else int(Filter.Robidoux)
+        d.sharpen_percent = g[5] if len(g) > 5 else 0.0
+    sec, nb, hs = C.c_double(), C.c_uint64(), C.c_uint64()
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_plan_probe(arr, len(geometries), threads, C.byref(sec), C.byref(nb), C.byref(hs) if want_hash else None, buf, 512), buf)
+    return {"seconds": sec.value, "table_bytes": nb.value, "table_hash": hs.value if want_hash else None}
+
+
 def device_count() -> int:
     return lib().ifb200_device_count()
 

@@ -97,6 +97,11 @@ void ifb200_linear_to_srgb_table(uint8_t out[16384]);
 /* ColorFilterSrgb presets (flow/nodes/color.rs:86-225): 0 sepia, 1 grayscale_ntsc, 2 grayscale_flat,
  * 3 grayscale_bt709, 4 grayscale_ry, 5 invert, 6 alpha(p), 7 contrast(p), 8 brightness(p), 9 saturation(p) */
 int  ifb200_color_filter_matrix(int which, float p, float out[25]);
+/* Host-side cost of preparing kernel tables (benchmarks of mixed workloads, where every geometry is new): builds the plans of
+   descs[0..n) -- only in_w, in_h, w, h, filter, sharpen_percent are read -- on `threads` host threads and discards them.
+   No CUDA call.  *table_hash (optional) = a hash of every table built, independent of the thread count. */
+int  ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, double* seconds, uint64_t* table_bytes,
+                       uint64_t* table_hash, char* err, size_t err_cap);
 
 /* ---- drop-in calls: HOST buffers, synchronous (what the Rust adapter calls) ------------------
  * Replaces the bodies of scaling.rs:93-251 (resize_to_canvas / resize_with_matte /

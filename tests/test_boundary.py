@@ -132,6 +132,23 @@ def test_argument_validation_precedes_device_use():
     assert wc.window(0, 0, 5, 4) is None and wc.window(1, 1, 3, 4).w == 2     # bitmaps.rs:413-431
 
 
+def test_plan_tables_build_on_the_host_for_any_geometry():
+    """Host half of the engine (no CUDA call): plans -- weights as weights.rs, ring/tile tables -- for ordinary, ragged, tiny,
+    up-scaling and extreme geometries.  A down-scale whose H windows are wider than a ring-kernel strip (3000 -> 1 columns)
+    must not fail: it is planned for the generic pair.  The tables do not depend on the number of builder threads."""
+    import imageflow_b200 as ifb
+    geos = [(3840, 2160, 512, 512, 2), (3840, 2160, 512, 512, 6), (7680, 4320, 1920, 1080, 2, 50.0), (1920, 1080, 3840, 2160, 14),
+            (33, 17, 7, 5, 2), (8, 8, 1, 1, 2), (4, 4, 4, 1, 17), (1, 1, 1, 1, 2), (1, 1, 300, 200, 14),
+            (3000, 8, 1, 1, 2), (2500, 6, 2, 3, 6), (16, 4000, 3, 1, 2), (4097, 3, 1030, 2, 13)]
+    one = ifb.plan_probe(geos, threads=1, want_hash=True)
+    four = ifb.plan_probe(geos, threads=4, want_hash=True)
+    assert one["table_hash"] == four["table_hash"] and one["table_bytes"] == four["table_bytes"] > 0
+    assert ifb.plan_probe([], threads=2)["table_bytes"] == 0
+    for bad in [(0, 4, 1, 1, 2), (4, 4, 0, 1, 2), (4, 4, 1, 1, 77)]:
+        with pytest.raises(ifb.FlowError):
+            ifb.plan_probe([bad])
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under imageflow_b200/ or include/ may import, link or name it."""
     # functional references only (comments may mention that the oracle exists)

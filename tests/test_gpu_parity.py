@@ -100,6 +100,17 @@ def test_replace_self_bit_exact(ifb, torch_mod, case, force_generic):
     assert mx == 0, f"max |delta| {mx} on {n} channel values"
 
 
+@pytest.mark.parametrize("case", [(3000, 8, 1, 1, 2), (2500, 6, 2, 3, 6), (16, 4000, 3, 1, 2), (2049, 5, 1, 5, 14)], ids=lambda c: "x".join(map(str, c)))
+def test_extreme_downscales_fall_back_instead_of_failing(ifb, torch_mod, case):
+    """windows wider than a ring-kernel strip (1400+ taps): the engine must plan the generic pair, not raise"""
+    iw, ih, ow, oh, flt = case
+    inp = util.noise(iw, ih, seed=iw + ih, alpha_mode="mixed")
+    canvas = np.zeros((oh, ow, 4), np.uint8)
+    exp = _oracle(inp, canvas, filter=flt, alpha_meaningful=True)
+    got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, filter=flt, alpha_meaningful=True)
+    assert util.diff_stats(got, exp)[0] == 0
+
+
 def test_fused_kernel_is_the_one_that_runs(ifb, torch_mod):
     inp = util.gradient(960, 540)
     canvas = np.zeros((128, 128, 4), np.uint8)
