@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--nt", type=int, default=0)
+    ap.add_argument("--tile-kernel", type=int, default=0, choices=[0, 1, 2], help="tile kernel form for up-scales (0 = library default)")
     return ap.parse_args()
 
 
@@ -251,6 +252,8 @@ def main():
     batch = ifb.Batch(local)
     if args.nt:
         batch.set_option(ifb.Batch.OPT_THREADS_PER_CTA, args.nt)
+    if args.tile_kernel:
+        batch.set_option(ifb.Batch.OPT_TILE_KERNEL, args.tile_kernel)
     params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))
     jobs = [(ifb.BitmapWindow.from_torch(inp[i], alpha_meaningful=bool(alpha)),
              ifb.BitmapWindow.from_torch(out[i], compose=ifb.BitmapCompositing(wl["compose"])), params, cm) for i in range(B)]
