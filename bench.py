@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--nt", type=int, default=0)
+    ap.add_argument("--gather-ahead", type=int, default=-1, choices=[-1, 0, 1], help="ring kernel gather-ahead form (-1 = library default)")
     ap.add_argument("--tile-kernel", type=int, default=0, choices=[0, 1, 2], help="tile kernel form for up-scales (0 = library default)")
     return ap.parse_args()
 
@@ -252,6 +253,8 @@ def main():
     batch = ifb.Batch(local)
     if args.nt:
         batch.set_option(ifb.Batch.OPT_THREADS_PER_CTA, args.nt)
+    if args.gather_ahead >= 0:
+        batch.set_option(ifb.Batch.OPT_GATHER_AHEAD, args.gather_ahead)
     if args.tile_kernel:
         batch.set_option(ifb.Batch.OPT_TILE_KERNEL, args.tile_kernel)
     params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))

@@ -354,9 +354,17 @@ int pick_bands(const FusedVariantTables& ft, int want) {
 // ------------------------------------------------------------------------------------------------
 // fused kernel dispatch table
 using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
-struct FusedEntry { int av, sh, ch, nt; FusedFn fn, fn_simple; size_t smem; };
+struct FusedEntry { int av, sh, ch, nt; FusedFn fn, fn_simple, fn_ga, fn_simple_ga; size_t smem; };
+// gather-ahead form (IFB200_OPT_GATHER_AHEAD): the cubic-filter ring (AV 4), 256 threads, shapes whose row stages are an even count
+template <int AV, int SH, int CH, int NT, bool SIMPLE> constexpr FusedFn ga_fn() {
+    if constexpr (AV == 4 && NT == 256 && FusedSmem<AV, SH, CH, NT>::kStages > 0 && FusedSmem<AV, SH, CH, NT>::kStages % 2 == 0)
+        return fused_down_kernel<AV, SH, CH, prefetch_rows(AV, CH), NT, SIMPLE, true>;
+    else
+        return nullptr;
+}
 #define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, false>, \
-                                         fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, true>, (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
+                                         fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, true>, \
+                                         ga_fn<AV_, SH_, CH_, NT_, false>(), ga_fn<AV_, SH_, CH_, NT_, true>(), (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
 #define IFB_FUSED(AV_, SH_) IFB_FUSED_1(AV_, SH_, 3, 256), IFB_FUSED_1(AV_, SH_, 4, 256), IFB_FUSED_1(AV_, SH_, 3, 128), IFB_FUSED_1(AV_, SH_, 4, 128)
 const FusedEntry kFused[] = {
 #ifdef IFB_FEW_SHAPES      /* development builds: only the shapes the 4K->512 benchmarks use */
@@ -405,6 +413,7 @@ struct ifb200_batch {
     bool force_generic = false; int nt = 256; int min_ctas = 296;
     int tile_variant = 0;    // IFB200_OPT_TILE_KERNEL: 0 default, 1 first form (fused_tile_kernel), 2 second form (fused_tile2_kernel)
     int sm_count = 148;
+    bool gather_ahead = false;   // IFB200_OPT_GATHER_AHEAD
     bool ring_ok = true;     // the shared window is laid out as the ring kernel's LUT gather assumes (smem_base_probe_kernel)
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
@@ -702,6 +711,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             pl.hw = ft.blob.at<float>(ft.o_hw); pl.hrd = ft.blob.at<uint32_t>(ft.o_hrd);
             const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
             FusedFn fn = g.simple ? fe->fn_simple : fe->fn;
+            if (b->gather_ahead && (g.simple ? fe->fn_simple_ga : fe->fn_ga)) fn = g.simple ? fe->fn_simple_ga : fe->fn_ga;
             const size_t smem = fe->smem;
             CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             for (size_t off = 0; off < nj; off += 65535) {
@@ -1123,6 +1133,7 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     case IFB200_OPT_MIN_CTAS:
         if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
         b->min_ctas = (int)value; return IFB200_OK;
+    case IFB200_OPT_GATHER_AHEAD: b->gather_ahead = value != 0; return IFB200_OK;
     case IFB200_OPT_TILE_KERNEL:
         if (value < 0 || value > 2) return IFB200_ERR_INVALID_ARGUMENT;
         b->tile_variant = (int)value; return IFB200_OK;

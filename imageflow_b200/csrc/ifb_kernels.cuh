@@ -280,13 +280,17 @@ __global__ void __launch_bounds__(256) fused_tile_kernel(const JobDev* __restric
 __device__ __forceinline__ uint32_t uchar_clamp_ff_rz(float x) { return min(__float2uint_rz(__fadd_rz(x, 0.5f)), 255u); }
 
 constexpr int kTile2W = 64, kTile2H = 16;               // output pixels per tile (the host plan uses the same numbers)
+// V-filtered tile in shared memory: [source column + 3][17] float4 -- column-major with an odd pitch, so that the H pass
+// reads (column, row ys + 4q) at `thread base + immediate` and both its reads and the V pass's writes are conflict free;
+// 3 columns of padding on the left and 13 on the right take the zero-weight slots of the H pass (see phase C).
+constexpr int kTile2VPitch = kTile2H + 1, kTile2VPadLeft = 3, kTile2VPad = 16;
 struct Tile2Smem {                                      // byte offsets inside the CTA's dynamic shared memory
     uint32_t in, v, hl, hr, ho, vl, vr, vo, t, cm, lut, total;
     __host__ __device__ static Tile2Smem make(int max_ir, int max_ic, bool linear) {
         Tile2Smem s;
         s.in = 0;
         s.v = s.in + (uint32_t)max_ir * max_ic * 16u;
-        s.hl = s.v + (uint32_t)kTile2H * max_ic * 16u;
+        s.hl = s.v + (uint32_t)(max_ic + kTile2VPad) * kTile2VPitch * 16u;
         s.hr = s.hl + kTile2W * 4u;
         s.ho = s.hr + kTile2W * 4u;
         s.vl = s.ho + kTile2W * 4u;
@@ -315,14 +319,13 @@ __device__ __forceinline__ uint32_t encode_sm(const uint8_t* __restrict__ sLut, 
 template <int CH, bool LINEAR, int COMPOSE, bool CM>
 __device__ __forceinline__ uint32_t finish_pixel_sm(float b, float g, float r, float a, const uint32_t flags, const float (&matte)[4],
                                                     const float* __restrict__ sT, const uint8_t* __restrict__ sLut,
-                                                    const float* __restrict__ sCm, const uint8_t* dst) {
+                                                    const float* __restrict__ sCm, const uint32_t d) {
     constexpr bool am = CH == 4;
     uint32_t ob, og, orr, oa;
     if (COMPOSE == 1 && am) {                              // BlendWithSelf: scaling.rs:254-287
         if (a > 0.994f) {
             ob = encode_sm<LINEAR>(sLut, b); og = encode_sm<LINEAR>(sLut, g); orr = encode_sm<LINEAR>(sLut, r); oa = 255u;
-        } else {
-            const uint32_t d = *reinterpret_cast<const uint32_t*>(dst);
+        } else {                                           // d = the canvas pixel (fetched by the caller ahead of the H pass)
             const float da = (float)(int)(d >> 24);
             const float dc = __fmul_rn(__fsub_rn(1.0f, a), __fadd_rn(__fmul_rn(1.0f / 255.0f, da), 0.0f));
             const float fa = __fadd_rn(a, dc);
@@ -373,8 +376,11 @@ __device__ __forceinline__ uint32_t finish_pixel_sm(float b, float g, float r, f
     return ob | (og << 8) | (orr << 16) | (oa << 24);
 }
 
+#ifndef IFB_TILE2_MINB
+#define IFB_TILE2_MINB 5                                 // resident CTAs per SM the register budget is cut for (3: 16.5, 4: 15.4, 5: 15.0, 6: 16.0 ms per 128 frames of config 4)
+#endif
 template <int CH, bool LINEAR, int COMPOSE, bool CM>
-__global__ void __launch_bounds__(256, 3) fused_tile2_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, Tables tb, AxisDev av, AxisDev ah,
+__global__ void __launch_bounds__(256, IFB_TILE2_MINB) fused_tile2_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, Tables tb, AxisDev av, AxisDev ah,
                                                              TilePlanDev pl) {
     extern __shared__ __align__(16) unsigned char t2sm[];
     const Tile2Smem L = Tile2Smem::make(pl.max_ir, pl.max_ic, LINEAR);
@@ -392,8 +398,10 @@ __global__ void __launch_bounds__(256, 3) fused_tile2_kernel(const JobDev* __res
     const int t = threadIdx.x;
     constexpr int NC = CH == 4 ? 4 : 3;                                  // channels that are filtered
 
-    // tables: once per CTA
+    // tables: once per CTA; the V tile is cleared once so that its padding never holds a NaN pattern
     sT[t] = __ldg((LINEAR ? tb.t_lin : tb.t_srgb) + t);
+    const int vcols = pl.max_ic + kTile2VPad;
+    for (int i = t; i < vcols * kTile2VPitch; i += 256) sV[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (LINEAR) {
         const uint4* __restrict__ g = reinterpret_cast<const uint4*>(tb.lut16k);      // cudaMalloc'd: 256-byte aligned
         uint4* s = reinterpret_cast<uint4*>(t2sm + L.lut);
@@ -455,35 +463,54 @@ __global__ void __launch_bounds__(256, 3) fused_tile2_kernel(const JobDev* __res
                     a0 = __fmaf_rn(wt, v.x, a0); a1 = __fmaf_rn(wt, v.y, a1); a2 = __fmaf_rn(wt, v.z, a2);
                     if (NC == 4) a3 = __fmaf_rn(wt, v.w, a3);
                 }
-                sV[yl * pitch + c] = make_float4(a0, a1, a2, a3);
+                sV[(c + kTile2VPadLeft) * kTile2VPitch + yl] = make_float4(a0, a1, a2, a3);
                 c += dc; yl += dr;
                 if (c >= ic) { c -= ic; ++yl; }
             }
         }
         __syncthreads();
-        // ---- C: H pass + store epilogue: thread (xl, ys) -> output column X0 + xl of rows ys, ys + 4, ys + 8, ys + 12
-        const int xl = t & 63, ys = t >> 6;
-        if (xl < ncols) {
-            const uint32_t l = sHl[xl], r = sHr[xl];
-            const float* __restrict__ w = ah.w + sHo[xl];
-            const float4* __restrict__ vrow = sV + ys * pitch - c0;
+        // ---- C: H pass + store epilogue: thread (xl, ys) -> output column X0 + xl of rows ys, ys + 4, ys + 8, ys + 12.
+        // The window [l, r] of a column is walked as whole aligned groups of four source columns ("slots"), every lane of
+        // the warp the same number of groups: a slot outside the window gets weight 0, and fmaf(0, v, p) == p for the finite
+        // v read there (padding or a neighbour's column), as is 0 + P for the first group -- only the sign of a zero can
+        // differ, which no later operation can see.  No lane-dependent branch, no address arithmetic inside the loops.
+        {
+            const int xl = t & 63, ys = t >> 6;
+            const bool live = xl < ncols;
+            const int xi = live ? xl : ncols - 1;
+            const uint32_t l = sHl[xi], r = sHr[xi];
+            const float* __restrict__ w = ah.w + sHo[xi];
+            uint8_t* dst = job.out + (size_t)(Y0 + ys) * job.out_stride + (size_t)(X0 + xi) * 4;
+            const size_t step = (size_t)4 * job.out_stride;
+            uint32_t dpx[4] = {0u, 0u, 0u, 0u};
+            if (COMPOSE == 1 && CH == 4) {                 // canvas pixels: on their way while the H pass runs
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (live && ys + 4 * q < nrows) dpx[q] = *reinterpret_cast<const uint32_t*>(dst + q * step);
+            }
+            const uint32_t g0 = l >> 2;
+            const int ng = (int)__reduce_max_sync(0xffffffffu, (r >> 2) - g0 + 1u);
             float f[4][NC];
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int c = 0; c < NC; ++c) f[q][c] = 0.0f;
-            for (uint32_t g = l >> 2; g <= (r >> 2); ++g) {
-                const uint32_t k0 = max(g * 4u, l), k1 = min(g * 4u + 3u, r);
+            for (int gi = 0; gi < ng; ++gi) {
+                const uint32_t cb = (g0 + (uint32_t)gi) * 4u;                      // first source column of the group
+                const int vc = min((int)cb - c0 + kTile2VPadLeft, vcols - 4);       // its column in the V tile (clamped: weights are 0 there)
+                const float4* __restrict__ vp = sV + vc * kTile2VPitch + ys;
                 float p[4][NC];
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
                     for (int c = 0; c < NC; ++c) p[q][c] = 0.0f;
-                for (uint32_t k = k0; k <= k1; ++k) {
-                    const float wt = __ldg(w + (k - l));
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    const uint32_t k = cb + (uint32_t)sl;
+                    const float wt = (k >= l && k <= r) ? __ldg(w + (k - l)) : 0.0f;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float4 v = vrow[q * 4 * pitch + (int)k];
+                        const float4 v = vp[sl * kTile2VPitch + 4 * q];
                         p[q][0] = __fmaf_rn(wt, v.x, p[q][0]); p[q][1] = __fmaf_rn(wt, v.y, p[q][1]); p[q][2] = __fmaf_rn(wt, v.z, p[q][2]);
                         if (NC == 4) p[q][3] = __fmaf_rn(wt, v.w, p[q][3]);
                     }
@@ -493,14 +520,12 @@ __global__ void __launch_bounds__(256, 3) fused_tile2_kernel(const JobDev* __res
 #pragma unroll
                     for (int c = 0; c < NC; ++c) f[q][c] = __fadd_rn(f[q][c], p[q][c]);
             }
-            uint8_t* dst = job.out + (size_t)(Y0 + ys) * job.out_stride + (size_t)(X0 + xl) * 4;
-            const size_t step = (size_t)4 * job.out_stride;
             const float matte[4] = {job.matte[0], job.matte[1], job.matte[2], job.matte[3]};
 #pragma unroll
             for (int q = 0; q < 4; ++q, dst += step) {
-                if (ys + 4 * q < nrows)
+                if (live && ys + 4 * q < nrows)
                     *reinterpret_cast<uint32_t*>(dst) = finish_pixel_sm<CH, LINEAR, COMPOSE, CM>(f[q][0], f[q][1], f[q][2], NC == 4 ? f[q][NC - 1] : 0.0f,
-                                                                                                 flags, matte, sT, sLut, sCm, dst);
+                                                                                                 flags, matte, sT, sLut, sCm, dpx[q]);
             }
         }
     }
@@ -814,7 +839,10 @@ template <int AV, int SH, int CH, int NT> struct FusedSmem {
     static_assert(kHwPairs * 2 * NT / 32 <= 256, "H weights must fit in the LUT holes");
 };
 
-template <int AV, int SH, int CH, int PF, int NT, bool SIMPLE>
+// GA ("gather ahead", staged rows with an even stage count only): the table lookups of source row i+1 are issued before the
+// multiply-adds of row i, into a second set of working registers, so that a warp covers its own shared-memory latency
+// instead of relying on the three other warps of its scheduler.  Same operations on the same values: bit-identical.
+template <int AV, int SH, int CH, int PF, int NT, bool SIMPLE, bool GA = false>
 __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* __restrict__ jobs, Tables tb, FusedPlanDev pl) {
     using PL = ProgLayout<AV>;
     using SM = FusedSmem<AV, SH, CH, NT>;
@@ -823,6 +851,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     constexpr int ST = SM::kStages;                 // > 0: source rows are staged through shared memory, PF is not used
     constexpr int RING = ST > 0 ? ST : 2 * PF;      // unrolled copies of the row code
     static_assert(RING <= 12, "ring positions");
+    static_assert(!GA || (ST > 0 && ST % 2 == 0), "gather-ahead needs an even number of row stages");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x;
     unsigned char* sLut = smem_raw;
@@ -928,6 +957,30 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
     } else {
         request_set(pf[0]);
     }
+    // sRGB bytes -> working floats: window address = (byte << 8) | (lane << 2), one PRMT per lookup
+    auto gather = [&](const uint4& raw, float (&p)[NV]) {
+        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t v = w4[i];
+            p[0 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6504) + kSmemWindowBase);
+            p[1 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6514) + kSmemWindowBase);
+            p[2 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6524) + kSmemWindowBase);
+            if (CH == 4) {
+                // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
+                const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
+                p[0 * 4 + i] = __fmul_rn(p[0 * 4 + i], af);
+                p[1 * 4 + i] = __fmul_rn(p[1 * 4 + i], af);
+                p[2 * 4 + i] = __fmul_rn(p[2 * 4 + i], af);
+                p[(CH - 1) * 4 + i] = af;
+            }
+        }
+    };
+    float pq[GA ? 2 : 1][NV];                       // GA: working floats of the row being accumulated and of the next one
+    if (GA) {                                       // row 0 has landed once all but the newest ST-2 requests have
+        cp_async_wait_group<(ST > 1 ? ST - 2 : 0)>();
+        gather(lds_u32x4(st_base), pq[0]);
+    }
     int ring_pos = 0;
     uint32_t buf = 0;                               // partial buffer (and mbarrier) of the next emitted row == nrow & 1
     uint32_t nrow = 0;                              // rows emitted so far
@@ -983,8 +1036,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                     for (int i = 0; i < ST; ++i) l2_prefetch_bulk(pnext + (size_t)(ST + i) * stride, seg_bytes);
                 }
                 request_row((D + ST - 1) % (ST > 0 ? ST : 1));        // row i+ST-1 into the slot consumed one row ago
-                cp_async_wait_group<(ST > 0 ? ST - 1 : 0)>();         // all but the newest ST-1 requests have landed: row i is here
-                raw = lds_u32x4(st_base + D * SM::kRowStage);
+                if (GA) {
+                    cp_async_wait_group<(ST > 1 ? ST - 2 : 0)>();     // all but the newest ST-2 requests have landed: row i+1 is here
+                    raw = lds_u32x4(st_base + ((D + 1) % (ST > 0 ? ST : 1)) * SM::kRowStage);
+                } else {
+                    cp_async_wait_group<(ST > 0 ? ST - 1 : 0)>();     // all but the newest ST-1 requests have landed: row i is here
+                    raw = lds_u32x4(st_base + D * SM::kRowStage);
+                }
             } else {
                 constexpr int SET = D / PF, IDX = D % PF;
                 raw = pf[SET][IDX];
@@ -1006,24 +1064,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_down_kernel(const JobDev* 
                 }
                 pa += kRec;
             }
-            // ---- sRGB bytes -> working floats: window address = (byte << 8) | (lane << 2), one PRMT per lookup
-            float p[NV];
-            const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t v = w4[i];
-                p[0 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6504) + kSmemWindowBase);
-                p[1 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6514) + kSmemWindowBase);
-                p[2 * 4 + i] = lds_table(__byte_perm(v, lane4, 0x6524) + kSmemWindowBase);
-                if (CH == 4) {
-                    // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
-                    const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
-                    p[0 * 4 + i] = __fmul_rn(p[0 * 4 + i], af);
-                    p[1 * 4 + i] = __fmul_rn(p[1 * 4 + i], af);
-                    p[2 * 4 + i] = __fmul_rn(p[2 * 4 + i], af);
-                    p[(CH - 1) * 4 + i] = af;
-                }
-            }
+            // ---- sRGB bytes -> working floats (GA: of the NEXT row; this row's were gathered one row ago)
+            float (&p)[NV] = pq[GA ? (D & 1) : 0];
+            gather(raw, pq[GA ? ((D + 1) & 1) : 0]);
             // ---- ring accumulate (packed fp32 FMA: two IEEE fmaf per instruction)
 #pragma unroll
             for (int s = 0; s < AV; ++s) {

@@ -232,7 +232,7 @@ def device_count() -> int:
 class Batch:
     """Device-resident batch executor (ifb200_batch_*): many independent scale_and_render calls whose
     bitmaps already live in HBM of one GPU, enqueued on a CUDA stream."""
-    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS, OPT_TILE_KERNEL = 1, 2, 3, 4
+    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS, OPT_TILE_KERNEL, OPT_GATHER_AHEAD = 1, 2, 3, 4, 5
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()

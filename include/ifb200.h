@@ -164,7 +164,8 @@ enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
     IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size: 128 or 256 (strip = 4x that many columns) */
     IFB200_OPT_MIN_CTAS = 3,           /* split images into row bands until the grid has this many CTAs   */
-    IFB200_OPT_TILE_KERNEL = 4         /* tile kernel form: 0 default, 1 first (one tile per CTA), 2 second (persistent, tables in shared memory) */
+    IFB200_OPT_TILE_KERNEL = 4,        /* tile kernel form: 0 default, 1 first (one tile per CTA), 2 second (persistent, tables in shared memory) */
+    IFB200_OPT_GATHER_AHEAD = 5        /* ring kernel: look the next source row up before accumulating the current one (where compiled) */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */

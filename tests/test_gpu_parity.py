@@ -34,10 +34,12 @@ def _oracle(inp, canvas, **kw):
 
 def _gpu_batch(ifb, torch, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen=0.0, linear=True,
                alpha_meaningful=False, compose=0, matte=(0, 0, 0, 0), color_matrix=None, force_generic=False, nt=256,
-               min_ctas=None, tile_kernel=0, counters=None):
+               min_ctas=None, tile_kernel=0, counters=None, gather_ahead=None):
     b = ifb.Batch(0)
     b.set_option(ifb.Batch.OPT_FORCE_GENERIC, int(force_generic))
     b.set_option(ifb.Batch.OPT_TILE_KERNEL, tile_kernel)
+    if gather_ahead is not None:
+        b.set_option(ifb.Batch.OPT_GATHER_AHEAD, int(gather_ahead))
     b.set_option(ifb.Batch.OPT_THREADS_PER_CTA, nt)
     if min_ctas is not None:
         b.set_option(ifb.Batch.OPT_MIN_CTAS, min_ctas)
@@ -129,6 +131,25 @@ def test_fused_decompositions_agree(ifb, torch_mod, nt, min_ctas):
     got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, alpha_meaningful=True, nt=nt, min_ctas=min_ctas)
     assert fused == 1
     assert util.diff_stats(got, exp)[0] == 0
+
+
+@pytest.mark.parametrize("gather_ahead", [0, 1], ids=["plain", "gather_ahead"])
+def test_ring_kernel_forms_bit_exact(ifb, torch_mod, gather_ahead):
+    """the ring kernel with and without the gather-ahead row pipeline (cubic filters, 256 threads): single band, many
+    bands, short bands (fewer source rows than row stages), every store epilogue"""
+    cases = [(1280, 720, 320, 180, 2, True, 0, None, None), (1280, 720, 320, 180, 2, False, 0, None, 4096),
+             (960, 540, 128, 128, 2, True, 1, None, None), (1920, 1080, 640, 360, 14, True, 2, 0, None),
+             (800, 600, 400, 300, 13, False, 1, 0, 64), (1024, 64, 96, 17, 13, True, 0, None, 4096),
+             (640, 9, 160, 2, 2, True, 0, None, None), (3840, 2160, 512, 512, 2, False, 0, None, None)]
+    for (iw, ih, ow, oh, flt, alpha, compose, cmw, min_ctas) in cases:
+        inp = util.noise(iw, ih, seed=iw + ih + flt, alpha_mode="mixed" if alpha else "opaque")
+        canvas = util.noise(ow, oh, seed=5, alpha_mode="mixed")
+        cm = ifb.color_filter_matrix(cmw) if cmw is not None else None
+        kw = dict(filter=flt, alpha_meaningful=alpha, compose=compose, matte=(10, 200, 90, 180), color_matrix=cm)
+        exp = _oracle(inp, canvas, **kw)
+        got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, min_ctas=min_ctas, gather_ahead=gather_ahead, **kw)
+        assert fused == 1, (iw, ih, ow, oh)
+        assert util.diff_stats(got, exp)[0] == 0, (iw, ih, ow, oh, flt, alpha, compose, min_ctas)
 
 
 @pytest.mark.parametrize("compose,alpha", [(1, True), (1, False), (2, True), (2, False)])
