@@ -410,9 +410,11 @@ __global__ void __launch_bounds__(256, IFB_TILE2_MINB) fused_tile2_kernel(const 
 
     const int pitch = pl.max_ic;
     const uint32_t n_tiles = (uint32_t)(pl.tiles_x * pl.tiles_y);
-    const uint64_t total = (uint64_t)n_jobs * n_tiles;
-    for (uint64_t work = blockIdx.x; work < total; work += gridDim.x) {
-        const uint32_t ji = (uint32_t)(work / n_tiles), tile = (uint32_t)(work - (uint64_t)ji * n_tiles);
+    // work item = (job ji, tile): blockIdx.x, blockIdx.x + gridDim.x, ... of the (job, tile) list, advanced without dividing
+    uint32_t ji = blockIdx.x / n_tiles, tile = blockIdx.x - ji * n_tiles;
+    for (; ji < n_jobs; tile += gridDim.x) {
+        while (tile >= n_tiles) { tile -= n_tiles; ++ji; }
+        if (ji >= n_jobs) break;
         const JobDev& job = jobs[ji];
         const int tx = (int)(tile % (uint32_t)pl.tiles_x), ty = (int)(tile / (uint32_t)pl.tiles_x);
         const int X0 = tx * kTile2W, X1 = min(X0 + kTile2W, (int)pl.out_w);
@@ -428,10 +430,13 @@ __global__ void __launch_bounds__(256, IFB_TILE2_MINB) fused_tile2_kernel(const 
         if (t >= 64 && t < 64 + nrows) { const int y = Y0 + t - 64; sVl[t - 64] = __ldg(av.left + y); sVr[t - 64] = __ldg(av.right + y); sVo[t - 64] = __ldg(av.off + y); }
         if (CM && t >= 96 && t < 116) sCm[t - 96] = job.cm[t - 96];
         // ---- A: source tile -> working floats (item i = (r, c) = (i / ic, i % ic), advanced without dividing)
+        // item i of phase A / B = (row, column) = (i / ic, i % ic); thread t starts at item t and advances by 256.  ic < 2^15:
+        // the float quotients below are exact (the true quotient is at least 0.5 / ic away from the next integer)
+        const float ric = 1.0f / (float)ic;
+        const int dr = (int)(256.5f * ric), dc = 256 - dr * ic;
         {
             const int n = ir * ic;
-            const int dr = 256 / ic, dc = 256 - dr * ic;
-            int r = t / ic, c = t - r * ic;
+            int r = (int)(((float)t + 0.5f) * ric), c = t - r * ic;
             const uint8_t* __restrict__ in0 = job.in + (size_t)r0 * job.in_stride + (size_t)c0 * 4;
             const size_t in_stride = job.in_stride;
             for (int i = t; i < n; i += 256) {
@@ -450,8 +455,7 @@ __global__ void __launch_bounds__(256, IFB_TILE2_MINB) fused_tile2_kernel(const 
         // ---- B: V pass for the tile's output rows over its source columns (item i = (yl, c))
         {
             const int n = nrows * ic;
-            const int dr = 256 / ic, dc = 256 - dr * ic;
-            int yl = t / ic, c = t - yl * ic;
+            int yl = (int)(((float)t + 0.5f) * ric), c = t - yl * ic;
             for (int i = t; i < n; i += 256) {
                 const uint32_t l = sVl[yl], r = sVr[yl];
                 const float* __restrict__ w = av.w + sVo[yl];
