@@ -17,7 +17,7 @@ SYMBOLS = [
     "ifb200_batch_transpose", "ifb200_batch_flip_vertical", "ifb200_batch_flip_horizontal",
     "ifb200_white_balance_srgb_bgra8", "ifb200_batch_white_balance",
     "ifb200_batch_create", "ifb200_batch_enqueue", "ifb200_batch_color_matrix", "ifb200_batch_sync",
-    "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches",
+    "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches", "ifb200_batch_host_profile",
     "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs",
 ]
 
@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
     L.ifb200_batch_sync.restype = C.c_int
     L.ifb200_batch_destroy.argtypes = [C.c_void_p]
     L.ifb200_batch_destroy.restype = None
+    L.ifb200_batch_host_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    L.ifb200_batch_host_profile.restype = C.c_int
     L.ifb200_batch_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     L.ifb200_batch_set_option.restype = C.c_int
     for f in ("ifb200_batch_kernel_launches", "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs"):

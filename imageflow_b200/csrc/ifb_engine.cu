@@ -37,6 +37,13 @@ struct Err {
              (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver || e_ == cudaErrorInvalidDevice) ? IFB200_ERR_NO_DEVICE : IFB200_ERR_CUDA; \
     IFB_THROW(c_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
 
+// adds the lifetime of the object, in seconds, to `acc` (host-side profile of the enqueue path; inclusive, nesting allowed)
+struct Tick {
+    double& acc; std::chrono::steady_clock::time_point t0;
+    explicit Tick(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~Tick() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 void put_err(char* err, size_t cap, const std::string& m) {
     if (!err || cap == 0) return;
     size_t n = std::min(cap - 1, m.size());
@@ -417,6 +424,8 @@ struct ifb200_batch {
     bool ring_ok = true;     // the shared window is laid out as the ring kernel's LUT gather assumes (smem_base_probe_kernel)
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
+    // where the calling thread spends an enqueue (seconds, inclusive; ifb200_batch_host_profile)
+    struct { double enqueue = 0, plans = 0, stage = 0, memcpy_ = 0, upload = 0; uint64_t commits = 0, staged_bytes = 0, pinned_allocs = 0; } prof;
 
     ~ifb200_batch() {
         cudaSetDevice(device);
@@ -450,6 +459,7 @@ struct ifb200_batch {
     }
 
     void* stage(size_t bytes, cudaEvent_t* ev_out) {
+        Tick tk(prof.stage);
         for (auto& s : pinned) {
             if (s.used && cudaEventQuery(s.ev) == cudaSuccess) s.used = false;
         }
@@ -458,6 +468,7 @@ struct ifb200_batch {
         s.cap = std::max<size_t>(bytes, 1 << 16);
         CUDA_OK(cudaMallocHost(&s.p, s.cap));
         CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        ++prof.pinned_allocs;
         s.used = true;
         pinned.push_back(s);
         *ev_out = s.ev;
@@ -536,10 +547,12 @@ struct ifb200_batch {
 void DevBlob::commit(ifb200_batch* b, cudaStream_t st) {
     const size_t n = host.size();
     if (!n) return;
+    Tick tk(b->prof.upload);
+    ++b->prof.commits; b->prof.staged_bytes += n;
     p = b->table_alloc(n);
     cudaEvent_t ev;
     void* pin = b->stage(n, &ev);
-    memcpy(pin, host.data(), n);
+    { Tick tm(b->prof.memcpy_); memcpy(pin, host.data(), n); }
     CUDA_OK(cudaMemcpyAsync(p, pin, n, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaEventRecord(ev, st));                     // releases the pinned slot
     CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
@@ -605,10 +618,11 @@ void host_tables() {
 
 void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, cudaStream_t st) {
     if (n == 0) return;
+    Tick tk_all(b->prof.enqueue);
     host_tables();
     CUDA_OK(cudaSetDevice(b->device));
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
-    b->prebuild_plans(descs, n);
+    { Tick tk(b->prof.plans); b->prebuild_plans(descs, n); }
     // group jobs by (plan, kernel class)
     // kind: 0 generic pair, 1 fused ring, 2 tile (first form), 3 tile (second form; `variant` = its compile-time case)
     struct Group { Plan* plan; int ch; int kind; bool simple; int variant; std::vector<size_t> idx; };
@@ -616,7 +630,8 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
         validate(descs[i]);
-        Plan& p = b->plan_for(descs[i]);
+        Plan* pp; { Tick tk(b->prof.plans); pp = &b->plan_for(descs[i]); }
+        Plan& p = *pp;
         const ifb200_resample_desc& d = descs[i];
         // 16-byte row loads: aligned base and pitch, and the pitch must cover the last (possibly partial) group of 4 pixels
         bool fused = p.fused_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0) &&
@@ -1139,6 +1154,13 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
         b->tile_variant = (int)value; return IFB200_OK;
     default: return IFB200_ERR_INVALID_ARGUMENT;
     }
+}
+int ifb200_batch_host_profile(const ifb200_batch* b, double* out, int n) {
+    if (!b) return 0;
+    const double v[8] = {b->prof.enqueue, b->prof.plans, b->prof.stage, b->prof.memcpy_, b->prof.upload,
+                         (double)b->prof.commits, (double)b->prof.staged_bytes, (double)b->prof.pinned_allocs};
+    for (int i = 0; i < n && i < 8; ++i) if (out) out[i] = v[i];
+    return 8;
 }
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b) { return b ? b->launches : 0; }
 uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b) { return b ? b->fused_jobs : 0; }

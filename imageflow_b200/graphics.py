@@ -308,6 +308,13 @@ class Batch:
         _check(lib().ifb200_batch_sync(self._h, buf, 512), buf)
         self._keep.clear()
 
+    def host_profile(self) -> dict:
+        """seconds the calling thread has spent inside enqueue calls so far, by part (ifb200_batch_host_profile)"""
+        v = (C.c_double * 8)()
+        lib().ifb200_batch_host_profile(self._h, v, 8)
+        return {"enqueue_s": v[0], "plans_s": v[1], "staging_slots_s": v[2], "staging_memcpy_s": v[3], "table_uploads_s": v[4],
+                "table_uploads": int(v[5]), "staged_bytes": int(v[6]), "pinned_allocs": int(v[7])}
+
     @property
     def kernel_launches(self) -> int:
         return lib().ifb200_batch_kernel_launches(self._h)

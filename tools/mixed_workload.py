@@ -67,6 +67,7 @@ def main():
     torch.cuda.synchronize()
     del wkeep
     warm = (batch.fused_jobs, batch.generic_jobs, batch.tile_jobs)
+    prof0 = batch.host_profile()
     px_done = 0
     host_ms = {"python_marshalling": 0.0, "enqueue_call": 0.0, "wait_for_gpu": 0.0}    # where the host spends the timed region (rank 0)
     jobs_done = 0
@@ -138,13 +139,16 @@ def main():
             checked = {"chains": args.check, "max_abs_delta_vs_oracle": mx}
         del srcs, results
         torch.cuda.empty_cache()
+    prof1 = batch.host_profile()
     tot_px, max_ms = sharding.aggregate(px_done, t_total, device=dev)
     tot_jobs, _ = sharding.aggregate(jobs_done, 0.0, device=dev)
     if rank == 0:
         print(json.dumps({"workload": "c5_mixed_thumbnails_export_4_sizes", "images": args.images, "n_gpus": world, "resamples": int(tot_jobs),
                           "input_mpx": tot_px / 1e6, "ms": max_ms, "value": tot_px / 1e6 / (max_ms / 1e3), "unit": "Mpx/s (input pixels of every resample)",
                           "lpt_imbalance": sharding.lpt_imbalance(costs, bins), "fused_jobs_rank0": batch.fused_jobs - warm[0], "generic_jobs_rank0": batch.generic_jobs - warm[1], "tile_jobs_rank0": batch.tile_jobs - warm[2],
-                          "host_ms_rank0": {k: round(v, 1) for k, v in host_ms.items()}, "parity_check": checked}))
+                          "host_ms_rank0": {k: round(v, 1) for k, v in host_ms.items()},
+                          "enqueue_profile_rank0": {(k[:-2] + "_ms" if k.endswith("_s") else k): (round((prof1[k] - prof0[k]) * 1e3, 1) if k.endswith("_s") else prof1[k] - prof0[k])
+                                                    for k in prof1}, "parity_check": checked}))
     if world > 1:
         dist.destroy_process_group()
 
