@@ -144,6 +144,15 @@ def test_plan_tables_build_on_the_host_for_any_geometry():
     four = ifb.plan_probe(geos, threads=4, want_hash=True)
     assert one["table_hash"] == four["table_hash"] and one["table_bytes"] == four["table_bytes"] > 0
     assert ifb.plan_probe([], threads=2)["table_bytes"] == 0
+    # regression pins (cubic filters only: polynomial f64 arithmetic, no libm): the kernel tables of the benchmark geometries
+    # as the GPU-verified build of round 1 laid them out.  A deliberate change of the table layout updates these constants.
+    pins = {((3840, 2160, 512, 512, 2),): (0x82369c7626e01cfc, 158208),
+            ((7680, 4320, 1920, 1080, 2, 50.0),): (0xd20130431b3e3011, 317552),
+            ((1920, 1080, 3840, 2160, 14),): (0xe0ce1caa7adbc55b, 0),            # up-scale: tile kernel, no ring tables
+            ((640, 480, 200, 150, 2), (33, 17, 7, 5, 2)): (0x1784450144c6f307, 61232)}
+    for geo, (h, nbytes) in pins.items():
+        r = ifb.plan_probe(list(geo), threads=1, want_hash=True)
+        assert (r["table_hash"], r["table_bytes"]) == (h, nbytes), geo
     for bad in [(0, 4, 1, 1, 2), (4, 4, 0, 1, 2), (4, 4, 1, 1, 77)]:
         with pytest.raises(ifb.FlowError):
             ifb.plan_probe([bad])
