@@ -102,24 +102,31 @@ class BitmapWindow:
                             self.compose, self.matte_bgra, self.pixel_layout, self._keep)
 
 
-def _desc(inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRenderParams, color_matrix=None, keep=None) -> ResampleDesc:
+def _fill_desc(d: ResampleDesc, inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRenderParams, color_matrix=None, keep=None) -> None:
+    """Writes one job into a zero-initialised ResampleDesc (in place: descriptor arrays are filled without temporaries)."""
     if inp.pixel_layout != "BGRA" or canvas.pixel_layout != "BGRA":            # scaling.rs:43-48
         raise FlowError(ErrorKind.MethodNotImplemented, "scale_and_render only supports BGRA bitmaps")
-    d = ResampleDesc()
     d.in_ = inp.ptr; d.in_w = inp.w; d.in_h = inp.h; d.in_stride = inp.stride
     d.canvas = canvas.ptr; d.cv_w = canvas.w; d.cv_h = canvas.h; d.cv_stride = canvas.stride
-    d.x, d.y, d.w, d.h = info.x, info.y, info.w, info.h
+    d.x = info.x; d.y = info.y; d.w = info.w; d.h = info.h
     d.filter = int(info.interpolation_filter)
     d.sharpen_percent = float(info.sharpen_percent_goal)
     d.linear = 1 if info.scale_in_colorspace == WorkingFloatspace.LinearRGB else 0
-    d.alpha_meaningful = int(bool(inp.alpha_meaningful))
+    d.alpha_meaningful = 1 if inp.alpha_meaningful else 0
     d.compose = int(canvas.compose)
-    d.matte_bgra = (C.c_uint8 * 4)(*canvas.matte_bgra)
+    m = canvas.matte_bgra
+    if m[0] or m[1] or m[2] or m[3]:
+        d.matte_bgra = (C.c_uint8 * 4)(*m)
     if color_matrix is not None:
         cm = np.ascontiguousarray(color_matrix, np.float32).reshape(25)
         d.color_matrix = cm.ctypes.data
         (keep if keep is not None else []).append(cm)
         d._cm = cm
+
+
+def _desc(inp: BitmapWindow, canvas: BitmapWindow, info: ScaleAndRenderParams, color_matrix=None, keep=None) -> ResampleDesc:
+    d = ResampleDesc()
+    _fill_desc(d, inp, canvas, info, color_matrix, keep)
     return d
 
 
@@ -252,7 +259,7 @@ class Batch:
         arr = (ResampleDesc * len(jobs))()
         keep = []
         for i, j in enumerate(jobs):
-            arr[i] = _desc(j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
+            _fill_desc(arr[i], j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
         return arr, keep
 
     STREAM_OWN = C.c_void_p(-1)

@@ -158,6 +158,38 @@ def test_plan_tables_build_on_the_host_for_any_geometry():
             ifb.plan_probe([bad])
 
 
+def test_descriptor_arrays_are_filled_in_place_like_single_descriptors():
+    """Batch.make_descs writes into the array elements directly; every field must come out as in the one-job path"""
+    import ctypes as C
+    import imageflow_b200 as ifb
+    from imageflow_b200 import graphics
+    rng = np.random.default_rng(3)
+    jobs = []
+    for i in range(200):
+        a = ifb.BitmapWindow(int(rng.integers(1, 1 << 47)), int(rng.integers(1, 9000)), int(rng.integers(1, 9000)), int(rng.integers(4, 9000)) * 4,
+                             alpha_meaningful=bool(rng.integers(0, 2)))
+        b = ifb.BitmapWindow(int(rng.integers(1, 1 << 47)), int(rng.integers(1, 9000)), int(rng.integers(1, 9000)), int(rng.integers(4, 9000)) * 4,
+                             compose=ifb.BitmapCompositing(int(rng.integers(0, 3))),
+                             matte_bgra=tuple(int(v) for v in rng.integers(0, 256, 4)) if i % 2 else (0, 0, 0, 0))
+        p = ifb.ScaleAndRenderParams(x=int(rng.integers(0, 50)), y=int(rng.integers(0, 50)), w=int(rng.integers(1, 4000)), h=int(rng.integers(1, 4000)),
+                                     sharpen_percent_goal=float(rng.choice([0.0, 25.0])), interpolation_filter=ifb.Filter(int(rng.integers(1, 32))),
+                                     scale_in_colorspace=ifb.WorkingFloatspace(int(rng.integers(0, 2))))
+        jobs.append((a, b, p, ifb.color_filter_matrix(0)) if i % 5 == 0 else (a, b, p))
+    arr, keep = ifb.Batch.make_descs(ifb.Batch.__new__(ifb.Batch), jobs)
+    assert len(keep) == 40
+    sz, off = C.sizeof(ifb.ResampleDesc), ifb.ResampleDesc.color_matrix.offset
+    for i, j in enumerate(jobs):
+        one = bytearray(bytes(graphics._desc(*j)))
+        got = bytearray(bytes(arr)[i * sz:(i + 1) * sz])
+        for blob in (one, got):                               # the matrix pointer differs per call: compare what it points at
+            ptr = int.from_bytes(blob[off:off + 8], "little")
+            assert (ptr != 0) == (len(j) > 3)
+            if ptr:
+                assert np.array_equal(np.ctypeslib.as_array((C.c_float * 25).from_address(ptr)), ifb.color_filter_matrix(0).reshape(25))
+            blob[off:off + 8] = bytes(8)
+        assert one == got, i
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under imageflow_b200/ or include/ may import, link or name it."""
     # functional references only (comments may mention that the oracle exists)

