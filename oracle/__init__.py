@@ -213,3 +213,42 @@ def white_balance(px: np.ndarray, threshold=None, w=None) -> np.ndarray:
     lib().ifo_white_balance(px.ctypes.data_as(u8p), px.shape[1] if w is None else w, px.shape[0], px.strides[0],
                             -1.0 if threshold is None else float(threshold), maps.ctypes.data_as(u8p))
     return maps
+
+
+def detect_content(px: np.ndarray, threshold: int = 1, alpha_meaningful: bool = True, w=None):
+    """graphics/whitespace.rs:284-331 -> ((x1, y1, x2, y2), number of window-interior pixels evaluated)."""
+    L = lib()
+    L.ifo_detect_content.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    L.ifo_detect_content.restype = C.c_int
+    rect = (C.c_uint32 * 4)(); n = C.c_uint64()
+    rc = L.ifo_detect_content(px.ctypes.data_as(C.POINTER(C.c_uint8)), px.shape[1] if w is None else w, px.shape[0], px.strides[0],
+                              int(alpha_meaningful), int(threshold), rect, C.byref(n))
+    if rc:
+        raise OracleError(rc)
+    return tuple(rect), n.value
+
+
+def whitespace_codes(px: np.ndarray, threshold: int = 1, alpha_meaningful: bool = True) -> np.ndarray:
+    """per-pixel code of sobel_scharr_detect (see ifb_oracle.h), shape (h, w) uint8."""
+    L = lib()
+    L.ifo_whitespace_codes.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint8)]
+    L.ifo_whitespace_codes.restype = None
+    h, w = px.shape[0], px.shape[1]
+    m = np.zeros((h, w), np.uint8)
+    L.ifo_whitespace_codes(px.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, px.strides[0], int(alpha_meaningful), int(threshold),
+                           m.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return m
+
+
+def detect_content_from_codes(codes: np.ndarray):
+    """the window walk of detect_content replayed over a code map (whitespace_codes) -> ((x1, y1, x2, y2), centres)."""
+    L = lib()
+    L.ifo_detect_content_from_codes.argtypes = [C.POINTER(C.c_uint8), C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
+    L.ifo_detect_content_from_codes.restype = C.c_int
+    codes = np.ascontiguousarray(codes, np.uint8)
+    rect = (C.c_uint32 * 4)(); n = C.c_uint64()
+    rc = L.ifo_detect_content_from_codes(codes.ctypes.data_as(C.POINTER(C.c_uint8)), codes.shape[1], codes.shape[0], rect, C.byref(n))
+    if rc:
+        raise OracleError(rc)
+    return tuple(rect), n.value

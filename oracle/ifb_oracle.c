@@ -626,3 +626,164 @@ void ifo_white_balance(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, flo
     }
     if (maps_out) memcpy(maps_out, maps, sizeof maps);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Whitespace detection (graphics/whitespace.rs), SURVEY.md section 8(f) item 4. */
+typedef enum { WS_TOP, WS_RIGHT, WS_BOTTOM, WS_LEFT, WS_NONDIR } ws_edge;
+typedef struct { ws_edge edge; float x1p, y1p, x2p, y2p; } ws_region;
+/* whitespace.rs:30-131 (twelve thin strips), :133-158 (four inward scans), :159-165 (everything at once) */
+static const ws_region WS_QUICK[12] = {
+    {WS_LEFT, 0.0f, 0.5f, 0.5f, 0.5f},     {WS_RIGHT, 0.5f, 0.5f, 1.0f, 0.5f},
+    {WS_LEFT, 0.0f, 0.677f, 0.5f, 0.677f}, {WS_RIGHT, 0.5f, 0.677f, 1.0f, 0.677f},
+    {WS_LEFT, 0.0f, 0.333f, 0.5f, 0.333f}, {WS_RIGHT, 0.5f, 0.333f, 1.0f, 0.333f},
+    {WS_TOP, 0.5f, 0.0f, 0.5f, 0.5f},      {WS_TOP, 0.677f, 0.0f, 0.677f, 0.5f},   {WS_TOP, 0.333f, 0.0f, 0.333f, 0.5f},
+    {WS_BOTTOM, 0.5f, 0.5f, 0.5f, 1.0f},   {WS_BOTTOM, 0.677f, 0.5f, 0.677f, 1.0f}, {WS_BOTTOM, 0.333f, 0.5f, 0.333f, 1.0f},
+};
+static const ws_region WS_INWARD[4] = {
+    {WS_TOP, 0.0f, 0.0f, 1.0f, 1.0f}, {WS_RIGHT, 0.0f, 0.0f, 1.0f, 1.0f}, {WS_BOTTOM, 0.0f, 0.0f, 1.0f, 1.0f}, {WS_LEFT, 0.0f, 0.0f, 1.0f, 1.0f},
+};
+static const ws_region WS_FULL = {WS_NONDIR, 0.0f, 0.0f, 1.0f, 1.0f};
+
+typedef struct { uint32_t w, h, threshold, min_x, max_x, min_y, max_y; uint64_t centres; } ws_search;
+static uint32_t ws_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static uint32_t ws_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+/* whitespace.rs:220-281; returns 0 when nothing is left to search */
+static int ws_search_rect(const ws_search* s, const ws_region* r, uint32_t* ox1, uint32_t* oy1, uint32_t* ox2, uint32_t* oy2) {
+    uint32_t x1 = ws_min(s->w, (uint32_t)floorf(r->x1p * (float)(s->w - 1)));
+    uint32_t x2 = ws_min(s->w, (uint32_t)floorf(r->x2p * (float)(s->w - 1)));
+    uint32_t y1 = ws_min(s->h, (uint32_t)floorf(r->y1p * (float)(s->h - 1)));
+    uint32_t y2 = ws_min(s->h, (uint32_t)floorf(r->y2p * (float)(s->h - 1)));
+    switch (r->edge) {
+    case WS_LEFT:   x1 = 0; x2 = ws_min(x2, s->min_x); break;
+    case WS_RIGHT:  x1 = ws_max(x1, s->max_x); x2 = s->w; break;
+    case WS_TOP:    y1 = 0; y2 = ws_min(y2, s->min_y); break;
+    case WS_BOTTOM: y1 = ws_max(y1, s->max_y); y2 = s->h; break;
+    default: break;
+    }
+    if (x1 == x2 || y1 == y2) return 0;                     /* :256-258 -- note: every thin strip of WS_QUICK ends here */
+    const uint32_t min_w = (r->edge == WS_RIGHT || r->edge == WS_LEFT) ? 3u : 7u;
+    const uint32_t min_h = (r->edge == WS_TOP || r->edge == WS_BOTTOM) ? 3u : 7u;
+    while (y2 - y1 < min_h && (y1 > 0 || y2 < s->h)) { y1 = y1 > 0 ? y1 - 1 : 0; y2 = ws_min(s->h, y2 + 1); }
+    while (x2 - x1 < min_w && (x1 > 0 || x2 < s->w)) { x1 = x1 > 0 ? x1 - 1 : 0; x2 = ws_min(s->w, x2 + 1); }
+    *ox1 = x1; *oy1 = y1; *ox2 = x2; *oy2 = y2;
+    return 1;
+}
+
+/* whitespace.rs:465-505: Bgra32 (alpha meaningful) weighs by alpha and rounds up; Bgr32 ignores the fourth byte */
+static uint8_t ws_gray(const uint8_t* p, int alpha_meaningful) {
+    const uint32_t lum = 233u * p[0] + 1197u * p[1] + 610u * p[2];
+    if (!alpha_meaningful) return (uint8_t)(lum / 2048u);
+    const uint32_t v = lum * p[3];
+    const uint32_t g = v / 524288u + (v % 524288u ? 1u : 0u);           /* div_ceil, then `as u16`, then clamp */
+    return g > 255u ? 255u : (uint8_t)g;
+}
+
+/* whitespace.rs:540-613 for one 3x3 neighbourhood m (row-major): 0xFF, or the packed local box (see ifb_oracle.h) */
+static uint8_t ws_code(const uint8_t m[9], int32_t threshold) {
+    const int32_t gx = 3 * m[0] + 10 * m[3] + 3 * m[6] - 3 * m[2] - 10 * m[5] - 3 * m[8];
+    const int32_t gy = 3 * m[0] + 10 * m[1] + 3 * m[2] - 3 * m[6] - 10 * m[7] - 3 * m[8];
+    if (abs(gx) + abs(gy) <= threshold) return 0xFF;
+    uint32_t lminx = 2, lminy = 2, lmaxx = 1, lmaxy = 1;
+    for (uint32_t my = 0; my < 3; ++my) {
+        int found = 0;
+        if (abs((int32_t)m[my * 3] - (int32_t)m[my * 3 + 1]) > threshold) { lminx = ws_min(lminx, 1); lmaxx = ws_max(lmaxx, 1); found = 1; }
+        if (abs((int32_t)m[my * 3 + 1] - (int32_t)m[my * 3 + 2]) > threshold) { lminx = ws_min(lminx, 2); lmaxx = ws_max(lmaxx, 2); found = 1; }
+        if (found) { lminy = ws_min(lminy, my); lmaxy = ws_max(lmaxy, my + 1); }
+    }
+    for (uint32_t mx = 0; mx < 3; ++mx) {
+        int found = 0;
+        if (abs((int32_t)m[mx] - (int32_t)m[mx + 3]) > threshold) { lminy = ws_min(lminy, 1); lmaxy = ws_max(lmaxy, 1); found = 1; }
+        if (abs((int32_t)m[mx + 3] - (int32_t)m[mx + 6]) > threshold) { lminy = ws_min(lminy, 2); lmaxy = ws_max(lmaxy, 2); found = 1; }
+        if (found) { lminx = ws_min(lminx, mx); lmaxx = ws_max(lmaxx, mx + 1); }
+    }
+    return (uint8_t)(lminx | ((lmaxx - 1) << 2) | (lminy << 4) | ((lmaxy - 1) << 6));
+}
+
+/* whitespace.rs:333-421 */
+/* codes != NULL: take the per-pixel codes from this w*h map (ifo_whitespace_codes) instead of computing them from px */
+static void ws_check_region(ws_search* s, const uint8_t* px, uint32_t stride, int am, const ws_region* region, const uint8_t* codes) {
+    uint32_t x1, y1, x2, y2;
+    if (!ws_search_rect(s, region, &x1, &y1, &x2, &y2)) return;
+    const uint32_t w = x2 - x1, h = y2 - y1, buf_size = 2048u;
+    const uint32_t window_width = ws_min(w, region->edge == WS_NONDIR ? buf_size / 7u : (uint32_t)ceilf(sqrtf((float)buf_size)));
+    const uint32_t window_height = ws_min(h, buf_size / window_width);
+    if (window_width <= 2 || window_height <= 2) return;    /* the reference would divide by zero here; not reachable from detect_content */
+    const uint32_t vertical_windows = (uint32_t)ceilf((float)h / (float)(window_height - 2));
+    const uint32_t horizontal_windows = (uint32_t)ceilf((float)w / (float)(window_width - 2));
+    uint8_t gray[2048];
+    for (uint32_t wr = 0; wr < vertical_windows; ++wr) {
+        for (uint32_t wc = 0; wc < horizontal_windows; ++wc) {
+            uint32_t bx = x1 + (window_width - 2) * wc, by = y1 + (window_height - 2) * wr;
+            uint32_t bw = ws_min(ws_max(3, x2 - bx), window_width), bh = ws_min(ws_max(3, y2 - by), window_height);
+            const uint32_t bx2 = bx + bw, by2 = by + bh;
+            const int excluded_x = s->min_x < bx && s->max_x > bx2;
+            const int excluded_y = s->min_y < by && s->max_y > by2;
+            if (excluded_x && excluded_y) continue;
+            if (excluded_y && s->min_x < bx2 && bx2 < s->max_x) bw = ws_max(3, s->min_x - bx);
+            else if (excluded_y && s->max_x > bx && bx > s->min_x) { bx = ws_min(bx2 - 3, s->max_x); bw = bx2 - bx; }
+            if (excluded_x && s->min_y < by2 && by2 < s->max_y) bh = ws_max(3, s->min_y - by);
+            else if (excluded_x && s->max_y > by && by > s->min_y) { by = ws_min(by2 - 3, s->max_y); bh = by2 - by; }
+            if (by + bh > s->h) { if (bh <= s->h) by = s->h - bh; else { by = 0; bh = s->h; } }
+            if (bx + bw > s->w) { if (bw <= s->w) bx = s->w - bw; else { bx = 0; bw = s->w; } }
+            if ((size_t)bw * bh > sizeof gray) return;       /* cannot happen: bw <= window_width, bh <= window_height */
+            if (!codes)
+                for (uint32_t y = 0; y < bh; ++y)
+                    for (uint32_t x = 0; x < bw; ++x) gray[y * bw + x] = ws_gray(px + (size_t)(by + y) * stride + (size_t)(bx + x) * 4, am);
+            for (uint32_t y = 1; y + 1 < bh; ++y) {
+                for (uint32_t x = 1; x + 1 < bw; ++x) {
+                    uint8_t c;
+                    if (codes) c = codes[(size_t)(by + y) * s->w + (bx + x)];
+                    else {
+                        uint8_t m[9];
+                        for (int k = 0; k < 9; ++k) m[k] = gray[(y - 1 + k / 3) * bw + (x - 1 + k % 3)];
+                        c = ws_code(m, (int32_t)s->threshold);
+                    }
+                    ++s->centres;
+                    if (c == 0xFF) continue;
+                    const uint32_t lminx = (c & 3u) + bx + x - 1, lmaxx = ((c >> 2) & 3u) + 1 + bx + x - 1;
+                    const uint32_t lminy = ((c >> 4) & 3u) + by + y - 1, lmaxy = ((c >> 6) & 3u) + 1 + by + y - 1;
+                    if (lminx < s->min_x) s->min_x = lminx;
+                    if (lmaxx > s->max_x) s->max_x = lmaxx;
+                    if (lminy < s->min_y) s->min_y = lminy;
+                    if (lmaxy > s->max_y) s->max_y = lmaxy;
+                }
+            }
+        }
+    }
+}
+
+static int ws_detect(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold,
+                     uint32_t rect_out[4], uint64_t* centres_out, const uint8_t* codes) {                /* whitespace.rs:284-331 */
+    if ((!px && !codes) || !rect_out || w == 0 || h == 0 || w > 0x7fffffffu || h > 0x7fffffffu) return IFO_ERR_INVALID_ARGUMENT;
+    if (centres_out) *centres_out = 0;
+    if (w < 3 || h < 3) { rect_out[0] = 0; rect_out[1] = 0; rect_out[2] = w; rect_out[3] = h; return 0; }
+    ws_search s = {w, h, threshold, w, 0, h, 0, 0};
+    for (int i = 0; i < 12; ++i) ws_check_region(&s, px, stride, alpha_meaningful, &WS_QUICK[i], codes);
+    const int64_t separately = (int64_t)s.min_x * s.h + (int64_t)s.min_y * s.w + ((int64_t)s.w - s.max_x) * s.h + ((int64_t)s.h - s.max_y) * s.w;
+    if (separately > (int64_t)s.h * s.w) ws_check_region(&s, px, stride, alpha_meaningful, &WS_FULL, codes);
+    else for (int i = 0; i < 4; ++i) ws_check_region(&s, px, stride, alpha_meaningful, &WS_INWARD[i], codes);
+    if (s.min_x == w && s.max_x == 0 && s.min_y == h && s.max_y == 0) { rect_out[0] = 0; rect_out[1] = 0; rect_out[2] = w; rect_out[3] = h; }
+    else { rect_out[0] = s.min_x; rect_out[1] = s.min_y; rect_out[2] = s.max_x; rect_out[3] = s.max_y; }
+    if (centres_out) *centres_out = s.centres;
+    return 0;
+}
+
+int ifo_detect_content(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold,
+                       uint32_t rect_out[4], uint64_t* centres_out) {
+    return ws_detect(px, w, h, stride, alpha_meaningful, threshold, rect_out, centres_out, NULL);
+}
+int ifo_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t h, uint32_t rect_out[4], uint64_t* centres_out) {
+    return ws_detect(NULL, w, h, 0, 0, 0, rect_out, centres_out, codes);
+}
+
+void ifo_whitespace_codes(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold, uint8_t* map) {
+    for (uint32_t y = 0; y < h; ++y) {
+        for (uint32_t x = 0; x < w; ++x) {
+            if (x == 0 || y == 0 || x + 1 >= w || y + 1 >= h) { map[(size_t)y * w + x] = 0xFF; continue; }
+            uint8_t m[9];
+            for (int k = 0; k < 9; ++k) m[k] = ws_gray(px + (size_t)(y - 1 + k / 3) * stride + (size_t)(x - 1 + k % 3) * 4, alpha_meaningful);
+            map[(size_t)y * w + x] = ws_code(m, (int32_t)threshold);
+        }
+    }
+}

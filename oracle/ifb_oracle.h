@@ -108,6 +108,21 @@ void ifo_flip_horizontal(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride);
  * maps_out (may be NULL) receives the three 256-entry byte maps in R, G, B order. */
 void ifo_white_balance(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, uint8_t* maps_out);
 
+/* graphics/whitespace.rs:284-331 detect_content, with everything under it (get_search_rect :220-281, check_region :333-421,
+ * approximate_grayscale :426-523 for Bgra32 (alpha meaningful) / Bgr32, sobel_scharr_detect :525-634), replayed in the
+ * reference's order: which windows are evaluated depends on the bounding box found so far.
+ * rect_out = {x1, y1, x2, y2}.  Returns 0, or IFO_ERR_INVALID_ARGUMENT for empty bitmaps.
+ * centres_out (optional): number of window-interior pixels the scan evaluated. */
+int ifo_detect_content(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold,
+                       uint32_t rect_out[4], uint64_t* centres_out);
+/* The window-independent part of sobel_scharr_detect: one code per pixel as the centre of its 3x3 neighbourhood.
+ * 0xFF: border pixel, or Scharr value <= threshold.  Otherwise bits 1:0 = local_min_x (0..2), 3:2 = local_max_x - 1,
+ * 5:4 = local_min_y, 7:6 = local_max_y - 1 (whitespace.rs:567-613), relative to (x - 1, y - 1).  map: w * h bytes. */
+void ifo_whitespace_codes(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold, uint8_t* map);
+/* detect_content with the window walk replayed over such a map (the threshold is already in the codes): same result,
+ * same number of evaluated centres as ifo_detect_content on the bitmap the map was made from. */
+int ifo_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t h, uint32_t rect_out[4], uint64_t* centres_out);
+
 int ifo_max_threads(void);
 
 #ifdef __cplusplus
