@@ -23,6 +23,7 @@
 #include "../../include/ifb200.h"
 #include "ifb_kernels.cuh"
 #include "ifb_weights.h"
+#include "ifb_whitespace.h"
 
 namespace {
 
@@ -875,6 +876,34 @@ void white_balance_locked(ifb200_batch* b, uint8_t* px, uint32_t w, uint32_t h, 
     b->launches += 3;
 }
 
+// detect_content (graphics/whitespace.rs:284-331) on a DEVICE bitmap: the per-pixel code map on the GPU, one byte per pixel
+// back to the host, the reference's window walk over it there.  Returns a rectangle, so it synchronises `st`.
+void detect_content_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                           uint32_t threshold, cudaStream_t st, uint32_t rect[4]) {
+    if (!px || !rect) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+    if (w == 0 || h == 0 || w > 0x7fffffffu || h > 0x7fffffffu) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "empty or oversized bitmap");
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
+    if (threshold > 0x7fffffffu) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "threshold out of range");
+    rect[0] = 0; rect[1] = 0; rect[2] = w; rect[3] = h;
+    if (w < 3 || h < 3) return;                              // whitespace.rs:288-290
+    CUDA_OK(cudaSetDevice(b->device));
+    const size_t n = (size_t)w * h;
+    uint8_t* dcodes = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dcodes), n, st));
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    if (grid.y > 65535u) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap taller than 524280 rows");
+    whitespace_codes_kernel<<<grid, dim3(32, 8), 0, st>>>(px, w, h, stride, alpha_meaningful ? 1u : 0u, (int)threshold, dcodes);
+    CUDA_OK(cudaGetLastError());
+    b->launches++;
+    cudaEvent_t ev;
+    uint8_t* codes = static_cast<uint8_t*>(b->stage(n, &ev));
+    CUDA_OK(cudaMemcpyAsync(codes, dcodes, n, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(ev, st));
+    CUDA_OK(cudaFreeAsync(dcodes, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (!ifb::detect_content_from_codes(codes, w, h, rect, nullptr)) IFB_THROW(IFB200_ERR_INVALID_STATE, "whitespace walk failed");
+}
+
 struct HostSlot {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
@@ -1261,6 +1290,39 @@ int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w
         transpose_locked(b, sl.d_in, (uint32_t)pin, w, h, sl.d_cv, (uint32_t)pout, st);
         CUDA_OK(cudaMemcpy2DAsync(to, to_stride, sl.d_cv, pout, (size_t)h * 4, w, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaStreamSynchronize(st));
+    });
+}
+
+int ifb200_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t h, uint32_t rect[4], uint64_t* centres) {
+    return ifb::detect_content_from_codes(codes, w, h, rect, centres) ? IFB200_OK : IFB200_ERR_INVALID_ARGUMENT;
+}
+
+int ifb200_batch_detect_content(ifb200_batch* b, const uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                                uint32_t threshold, uint32_t rect[4], void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        detect_content_locked(b, dev_px, w, h, stride, alpha_meaningful, threshold,
+                              stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream), rect);
+    });
+}
+
+int ifb200_detect_content_bgra8(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold,
+                                uint32_t rect[4], char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!px || !rect) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (w == 0 || h == 0) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "empty bitmap");
+        if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
+        ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
+        detect_content_locked(b, sl.d_cv, w, h, (uint32_t)pitch, alpha_meaningful, threshold, st, rect);
     });
 }
 

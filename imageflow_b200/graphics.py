@@ -194,6 +194,25 @@ def white_balance_srgb_mut(bitmap: BitmapWindow, threshold: Optional[float] = No
     _check(lib().ifb200_white_balance_srgb_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, -1.0 if threshold is None else float(threshold), buf, 512), buf)
 
 
+def detect_content(bitmap: BitmapWindow, threshold: int = 1):
+    """graphics/whitespace.rs:284-331 with a HOST bitmap -> (x1, y1, x2, y2)."""
+    rect = (C.c_uint32 * 4)()
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_detect_content_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, int(bool(bitmap.alpha_meaningful)), int(threshold), rect, buf, 512), buf)
+    return tuple(rect)
+
+
+def detect_content_from_codes(codes: np.ndarray):
+    """host half of detect_content alone: the reference's window walk over a (h, w) uint8 code map (ifb_whitespace.h);
+    no CUDA call.  -> ((x1, y1, x2, y2), pixels visited)"""
+    codes = np.ascontiguousarray(codes, np.uint8)
+    rect = (C.c_uint32 * 4)(); n = C.c_uint64()
+    rc = lib().ifb200_detect_content_from_codes(codes.ctypes.data, codes.shape[1], codes.shape[0], rect, C.byref(n))
+    if rc:
+        raise FlowError(rc, "empty or oversized code map")
+    return tuple(rect), n.value
+
+
 def color_filter_matrix(which: int, p: float = 0.0) -> np.ndarray:
     """flow/nodes/color.rs:86-225 presets (0 sepia ... 9 saturation)."""
     m = np.zeros(25, np.float32)
@@ -299,6 +318,14 @@ class Batch:
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_white_balance(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride,
                                                 -1.0 if threshold is None else float(threshold), self._stream(stream), buf, 512), buf)
+
+    def detect_content(self, bitmap: BitmapWindow, threshold: int = 1, stream=None):
+        """graphics/whitespace.rs:284-331 on a DEVICE bitmap -> (x1, y1, x2, y2); synchronises `stream`."""
+        rect = (C.c_uint32 * 4)()
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_detect_content(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, int(bool(bitmap.alpha_meaningful)),
+                                                 int(threshold), rect, self._stream(stream), buf, 512), buf)
+        return tuple(rect)
 
     def flip_vertical(self, bitmap: BitmapWindow, stream=None) -> None:
         """graphics/flip.rs:10-22 on a DEVICE bitmap, in place."""

@@ -97,6 +97,11 @@ void ifb200_linear_to_srgb_table(uint8_t out[16384]);
 /* ColorFilterSrgb presets (flow/nodes/color.rs:86-225): 0 sepia, 1 grayscale_ntsc, 2 grayscale_flat,
  * 3 grayscale_bt709, 4 grayscale_ry, 5 invert, 6 alpha(p), 7 contrast(p), 8 brightness(p), 9 saturation(p) */
 int  ifb200_color_filter_matrix(int which, float p, float out[25]);
+/* detect_content with a HOST bitmap (drop-in for graphics/whitespace.rs:284); and its host half alone: the window walk over a
+ * w*h code map (layout: imageflow_b200/csrc/ifb_whitespace.h), no CUDA call -- `centres` (optional) = pixels visited. */
+int  ifb200_detect_content_bgra8(const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful, uint32_t threshold,
+                                 uint32_t rect[4], char* err, size_t err_cap);
+int  ifb200_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t h, uint32_t rect[4], uint64_t* centres);
 /* Host-side cost of preparing kernel tables (benchmarks of mixed workloads, where every geometry is new): builds the plans of
    descs[0..n) -- only in_w, in_h, w, h, filter, sharpen_percent are read -- on `threads` host threads and discards them.
    No CUDA call.  *table_hash (optional) = a hash of every table built, independent of the thread count. */
@@ -157,6 +162,13 @@ int  ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, 
                                   void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, float threshold,
                                 void* cuda_stream, char* err, size_t err_cap);
+/* graphics/whitespace.rs:284-331 detect_content(&BitmapWindowMut<u8>, threshold) -> RectCorners{x1, y1, x2, y2}: the rectangle the
+ * reference's whitespace scan finds (trim / `trim.threshold`).  The per-pixel arithmetic (approximate_grayscale :426-523, Scharr
+ * and the local edge box :525-613) runs on the GPU for all pixels; the reference's order-dependent window walk (:333-421) is
+ * replayed on the host over that one-byte-per-pixel map, so the result is the reference's, not the bounding box of all edges.
+ * alpha_meaningful selects the Bgra32 (1) or Bgr32 (0) grayscale.  Synchronous (a rectangle comes back). */
+int  ifb200_batch_detect_content(ifb200_batch* b, const uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                                 uint32_t threshold, uint32_t rect[4], void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
 void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */
