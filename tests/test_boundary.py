@@ -190,6 +190,16 @@ def test_descriptor_arrays_are_filled_in_place_like_single_descriptors():
         assert one == got, i
 
 
+def test_three_instruction_clamp_equals_uchar_clamp_ff_for_every_float(tmp_path):
+    """fused_tile2_kernel clamps with min(cvt.rzi.u32(add.rz(x, 0.5)), 255); tools/check_clamp_rz.c compares that with the
+    reference's uchar_clamp_ff (color.rs:101-108) on all 2^32 float bit patterns (a few seconds on the host cores)."""
+    exe = str(tmp_path / "check_clamp_rz")
+    src = os.path.join(ROOT, "tools", "check_clamp_rz.c")
+    subprocess.run(["gcc", "-O2", "-fopenmp", "-frounding-math", src, "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.strip().endswith("0 mismatches over all 2^32 floats"), r.stdout[-500:]
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under imageflow_b200/ or include/ may import, link or name it."""
     # functional references only (comments may mention that the oracle exists)
