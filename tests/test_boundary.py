@@ -200,6 +200,16 @@ def test_three_instruction_clamp_equals_uchar_clamp_ff_for_every_float(tmp_path)
     assert r.returncode == 0 and r.stdout.strip().endswith("0 mismatches over all 2^32 floats"), r.stdout[-500:]
 
 
+def test_tile_kernel_float_quotients_are_exact():
+    """fused_tile2_kernel starts a thread's items at (t / ic, t % ic) and advances by 256 / ic without an integer division:
+    q = (int)((t + 0.5f) * (1.0f / ic)) and (int)(256.5f * (1.0f / ic)).  Exact for every t < 256 and every tile width."""
+    t = np.arange(256, dtype=np.float32)
+    for ic in range(1, 40000):
+        ric = np.float32(1.0) / np.float32(ic)
+        assert np.array_equal(((t + np.float32(0.5)) * ric).astype(np.int32), np.arange(256) // ic), ic
+        assert int(np.float32(256.5) * ric) == 256 // ic, ic
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under imageflow_b200/ or include/ may import, link or name it."""
     # functional references only (comments may mention that the oracle exists)
