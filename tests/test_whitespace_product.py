@@ -54,6 +54,28 @@ def test_reference_known_answers_through_the_product_walk():               # smo
             assert ifb.detect_content_from_codes(oracle.whitespace_codes(c, 1))[0] == (x, y, x + rw, y + rh), (x, y, rw, rh)
 
 
+def test_kernel_source_under_cpu_emulation_matches_the_oracle(tmp_path):
+    """tests/cpu_emu/whitespace_kernel_emu.cc compiles the product's CUDA source of whitespace_codes_kernel (unmodified) with
+    g++ under a sequential emulation of threadIdx / blockIdx / __shared__ / __syncthreads and runs it with the launch geometry
+    the engine uses: every code byte must equal the oracle's, for ragged sizes, padded pitches, both grayscale formulas."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libws_emu.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", "-o", so, os.path.join(root, "tests", "cpu_emu", "whitespace_kernel_emu.cc")], check=True)
+    L = C.CDLL(so)
+    L.emu_whitespace_codes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    for a, thr, am in _images(200, 5):
+        h, w = a.shape[:2]
+        pitch = (w * 4 + 63) // 64 * 64                                   # like the engine's device copies
+        buf = np.zeros((h, pitch), np.uint8)
+        np.lib.stride_tricks.as_strided(buf, (h, w, 4), (pitch, 4, 1))[...] = a
+        codes = np.full((h, w), 7, np.uint8)
+        L.emu_whitespace_codes(buf.ctypes.data, w, h, pitch, int(am), thr, codes.ctypes.data)
+        assert np.array_equal(codes, oracle.whitespace_codes(a, thr, am)), (a.shape, thr, am)
+
+
 def test_bad_code_maps_are_rejected():
     import imageflow_b200 as ifb
     with pytest.raises(ifb.FlowError):
