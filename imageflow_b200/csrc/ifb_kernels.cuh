@@ -20,42 +20,8 @@
 
 namespace ifbk {
 
-// ---------------------------------------------------------------- device-side descriptors
-struct JobDev {                 // one scale_and_render call
-    const uint8_t* in;          // input window origin
-    uint8_t* out;               // canvas origin already offset to (x, y)
-    uint32_t in_stride, out_stride;
-    uint32_t flags;             // bit0 linear, bit1 alpha_meaningful, bits2-3 compose, bit4 has colour matrix
-    float matte[4];             // premultiplied working-space matte (B,G,R,A positional; scaling.rs:141-143)
-    float cm[20];               // cm[c*5 + k]: output channel c (0=r,1=g,2=b,3=a) = sum_k cm[c*5+k]*{r,g,b,a,1} (bias already *255)
-};
-enum : uint32_t { JF_LINEAR = 1u, JF_ALPHA = 2u, JF_COMPOSE_SHIFT = 2, JF_CM = 16u };
-
-struct Tables {                 // per-device constant tables
-    const float* t_lin;         // ColorContext::byte_to_float, LinearRGB (color.rs:23-48)
-    const float* t_srgb;        // same, StandardRGB (== v * (1/255f)); also the alpha table
-    const uint8_t* lut16k;      // LINEAR_TO_SRGB_LUT (lut.rs:14)
-};
-
-struct AxisDev {                // CSR contribution windows of one axis (weights.rs PixelRowWeights)
-    const uint32_t* left; const uint32_t* right; const uint32_t* off; const float* w;
-};
-
-struct StripDev { int X0, X1, k0, pad; };       // output columns [X0,X1) read source columns from k0 (multiple of 4)
-struct BandDev  { int Y0, Y1, j0, j1; };        // output rows [Y0,Y1) read source rows j0..j1 inclusive
-
-struct FusedPlanDev {
-    uint32_t in_w, in_h, out_w, out_h;
-    int n_strips, n_bands;
-    uint32_t zero;              // always 0 (run-time constant used to order loads after a scoreboard wait)
-    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weight (float bits) of the output row in each ring slot (row y lives in
-                                //   slot y mod AV), then ((first completed y << 8) | (its slot << 4) | count)
-    const StripDev* strips;
-    const BandDev* bands;
-    const float* hw;            // [strip][SH*4*NT]: H weights of thread t by partial plane p = output column mod SH and own column i:
-                                //   p < 2*(SH/2): word 2*(((p/2)*4+i)*NT+t) + (p&1); odd last plane: word 2*(((SH/2)*4+i/2)*NT+t) + (i&1)
-    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12) | ((X mod SH) << 28)
-};
+// ---------------------------------------------------------------- device-side descriptors (their own file: tests/cpu_emu includes it too)
+#include "ifb_types.cuh"
 
 // ---------------------------------------------------------------- scalar helpers
 // color.rs:101-108 uchar_clamp_ff: trunc(x + 0.5) computed exactly, saturated to [0,255], NaN -> 0
@@ -191,12 +157,6 @@ __global__ void __launch_bounds__(128) hpass_generic_kernel(const JobDev* __rest
 // shared-memory float4 tile, the V pass writes a second shared-memory tile [TOH][source columns], the H pass reads
 // it; nothing but the source pixels and the destination pixels touches HBM.  Same arithmetic, same bits as the
 // other kernels (V chain ascending; H per aligned group of 4 source columns, partials added ascending).
-struct TilePlanDev {
-    uint32_t in_w, in_h, out_w, out_h;
-    int tow, toh;               // tile size in output pixels
-    int tiles_x, tiles_y;
-    int max_ic, max_ir;         // largest source extent of any tile (shared-memory tile dimensions)
-};
 
 __global__ void __launch_bounds__(256) fused_tile_kernel(const JobDev* __restrict__ jobs, Tables tb, AxisDev av, AxisDev ah, TilePlanDev pl) {
     extern __shared__ __align__(16) float4 tsm[];
@@ -262,278 +222,8 @@ __global__ void __launch_bounds__(256) fused_tile_kernel(const JobDev* __restric
     }
 }
 
-// ---------------------------------------------------------------- tile kernel, second form
-// Same decomposition and the same arithmetic as fused_tile_kernel (bit-identical results), rebuilt around what bounds
-// an up-scale: the per-OUTPUT-pixel work.  Every output pixel of a 2x up-scale costs one H pass (4 taps) and one store
-// epilogue -- composite over the canvas (scaling.rs:254-287), three divisions, three 16 K-table encodes, a 5x5 matrix --
-// while only a quarter of a source pixel is converted for it, so
-//   * the transfer tables live in shared memory: the 16 KB linear->sRGB table gathered from L1 with 32 different
-//     addresses per warp was most of the old kernel's time; shared memory serves the same gather at bank rate;
-//   * the kernel is compiled per (channels, working space, compositing mode, matrix) so that the epilogue carries no
-//     code for the cases it cannot meet;
-//   * one CTA walks many tiles (persistent, tile index strided by the grid), so the tables are filled once per CTA;
-//   * thread (x, ys) finishes output column x of rows ys, ys+4, ys+8, ys+12: an H weight is fetched once for four
-//     rows, and no index is ever divided inside a loop;
-//   * the window descriptors of the tile's rows and columns are staged in shared memory next to the pixels.
-// uchar_clamp_ff (color.rs:101-108) = trunc(x + 0.5) saturated: a round-toward-zero add cannot cross an integer, so
-// trunc(rz(x + 0.5)) == trunc(x + 0.5) exactly; cvt.rzi.u32 saturates negatives and NaN to 0 like the reference's casts.
-__device__ __forceinline__ uint32_t uchar_clamp_ff_rz(float x) { return min(__float2uint_rz(__fadd_rz(x, 0.5f)), 255u); }
-
-constexpr int kTile2W = 64, kTile2H = 16;               // output pixels per tile (the host plan uses the same numbers)
-// V-filtered tile in shared memory: [source column + 3][17] float4 -- column-major with an odd pitch, so that the H pass
-// reads (column, row ys + 4q) at `thread base + immediate` and both its reads and the V pass's writes are conflict free;
-// 3 columns of padding on the left and 13 on the right take the zero-weight slots of the H pass (see phase C).
-constexpr int kTile2VPitch = kTile2H + 1, kTile2VPadLeft = 3, kTile2VPad = 16;
-struct Tile2Smem {                                      // byte offsets inside the CTA's dynamic shared memory
-    uint32_t in, v, hl, hr, ho, vl, vr, vo, t, cm, lut, total;
-    __host__ __device__ static Tile2Smem make(int max_ir, int max_ic, bool linear) {
-        Tile2Smem s;
-        s.in = 0;
-        s.v = s.in + (uint32_t)max_ir * max_ic * 16u;
-        s.hl = s.v + (uint32_t)(max_ic + kTile2VPad) * kTile2VPitch * 16u;
-        s.hr = s.hl + kTile2W * 4u;
-        s.ho = s.hr + kTile2W * 4u;
-        s.vl = s.ho + kTile2W * 4u;
-        s.vr = s.vl + kTile2H * 4u;
-        s.vo = s.vr + kTile2H * 4u;
-        s.t = s.vo + kTile2H * 4u;
-        s.cm = s.t + 256u * 4u;
-        s.lut = s.cm + 32u * 4u;
-        s.total = s.lut + (linear ? 16384u : 0u);
-        return s;
-    }
-};
-enum : uint32_t { JF_CM_RGB3 = 32u };                    // colour matrix = 3x3 on r,g,b; alpha row identity; no bias (e.g. sepia)
-
-template <bool LINEAR>
-__device__ __forceinline__ uint32_t encode_sm(const uint8_t* __restrict__ sLut, float v) {    // color.rs:59-69, lut.rs:4-8
-    if (LINEAR) {
-        float s = __fmul_rn(v, 16383.0f);
-        s = fminf(fmaxf(s, 0.0f), 16383.0f);
-        return (uint32_t)sLut[(int)s];
-    }
-    return uchar_clamp_ff_rz(__fmul_rn(255.0f, v));
-}
-
-// finish_pixel() with the case analysis done at compile time and the tables in shared memory.  Same operations, same order.
-template <int CH, bool LINEAR, int COMPOSE, bool CM>
-__device__ __forceinline__ uint32_t finish_pixel_sm(float b, float g, float r, float a, const uint32_t flags, const float (&matte)[4],
-                                                    const float* __restrict__ sT, const uint8_t* __restrict__ sLut,
-                                                    const float* __restrict__ sCm, const uint32_t d) {
-    constexpr bool am = CH == 4;
-    uint32_t ob, og, orr, oa;
-    if (COMPOSE == 1 && am) {                              // BlendWithSelf: scaling.rs:254-287
-        if (a > 0.994f) {
-            ob = encode_sm<LINEAR>(sLut, b); og = encode_sm<LINEAR>(sLut, g); orr = encode_sm<LINEAR>(sLut, r); oa = 255u;
-        } else {                                           // d = the canvas pixel (fetched by the caller ahead of the H pass)
-            const float da = (float)(int)(d >> 24);
-            const float dc = __fmul_rn(__fsub_rn(1.0f, a), __fadd_rn(__fmul_rn(1.0f / 255.0f, da), 0.0f));
-            const float fa = __fadd_rn(a, dc);
-            ob = encode_sm<LINEAR>(sLut, __fdiv_rn(__fadd_rn(b, __fmul_rn(dc, sT[d & 0xffu])), fa));
-            og = encode_sm<LINEAR>(sLut, __fdiv_rn(__fadd_rn(g, __fmul_rn(dc, sT[(d >> 8) & 0xffu])), fa));
-            orr = encode_sm<LINEAR>(sLut, __fdiv_rn(__fadd_rn(r, __fmul_rn(dc, sT[(d >> 16) & 0xffu])), fa));
-            oa = uchar_clamp_ff_rz(__fmul_rn(fa, 255.0f));
-        }
-    } else if (!am) {                                      // scaling.rs:227-232 (and BlendWithSelf without meaningful alpha)
-        ob = encode_sm<LINEAR>(sLut, b); og = encode_sm<LINEAR>(sLut, g); orr = encode_sm<LINEAR>(sLut, r); oa = 255u;
-    } else {
-        if (COMPOSE == 2) {                                // BlendWithMatte (scaling.rs:119-148)
-            const float t = __fsub_rn(1.0f, a);
-            b = __fadd_rn(b, __fmul_rn(t, matte[0]));
-            g = __fadd_rn(g, __fmul_rn(t, matte[1]));
-            r = __fadd_rn(r, __fmul_rn(t, matte[2]));
-            a = __fadd_rn(a, __fmul_rn(t, matte[3]));
-        }
-        if (a > 0.0f) { b = __fdiv_rn(b, a); g = __fdiv_rn(g, a); r = __fdiv_rn(r, a); }
-        ob = encode_sm<LINEAR>(sLut, b); og = encode_sm<LINEAR>(sLut, g); orr = encode_sm<LINEAR>(sLut, r);
-        oa = uchar_clamp_ff_rz(__fmul_rn(a, 255.0f));
-    }
-    if (CM) {                                              // color_matrix.rs:5-28, on sRGB bytes
-        const float fr = (float)orr, fg = (float)og, fb = (float)ob;
-        if (flags & JF_CM_RGB3) {
-            // Zero coefficients contribute +-0 products of finite bytes, which change no partial sum (except the sign of a
-            // zero, invisible after the clamp), and the identity alpha row returns the alpha byte: skipping them is exact.
-            auto row3 = [&](int c) {
-                float s = __fmul_rn(sCm[c * 5 + 0], fr);
-                s = __fadd_rn(s, __fmul_rn(sCm[c * 5 + 1], fg));
-                s = __fadd_rn(s, __fmul_rn(sCm[c * 5 + 2], fb));
-                return uchar_clamp_ff_rz(s);
-            };
-            orr = row3(0); og = row3(1); ob = row3(2);
-        } else {
-            const float fa = (float)oa;
-            auto row = [&](int c) {
-                float s = __fmul_rn(sCm[c * 5 + 0], fr);
-                s = __fadd_rn(s, __fmul_rn(sCm[c * 5 + 1], fg));
-                s = __fadd_rn(s, __fmul_rn(sCm[c * 5 + 2], fb));
-                s = __fadd_rn(s, __fmul_rn(sCm[c * 5 + 3], fa));
-                return uchar_clamp_ff_rz(__fadd_rn(s, sCm[c * 5 + 4]));
-            };
-            const uint32_t nr = row(0), ng = row(1), nb = row(2), na = row(3);
-            orr = nr; og = ng; ob = nb; oa = na;
-        }
-    }
-    return ob | (og << 8) | (orr << 16) | (oa << 24);
-}
-
-#ifndef IFB_TILE2_MINB
-#define IFB_TILE2_MINB 5                                 // resident CTAs per SM the register budget is cut for (3: 16.5, 4: 15.4, 5: 15.0, 6: 16.0 ms per 128 frames of config 4)
-#endif
-template <int CH, bool LINEAR, int COMPOSE, bool CM>
-__global__ void __launch_bounds__(256, IFB_TILE2_MINB) fused_tile2_kernel(const JobDev* __restrict__ jobs, uint32_t n_jobs, Tables tb, AxisDev av, AxisDev ah,
-                                                             TilePlanDev pl) {
-    extern __shared__ __align__(16) unsigned char t2sm[];
-    const Tile2Smem L = Tile2Smem::make(pl.max_ir, pl.max_ic, LINEAR);
-    float4* const sIn = reinterpret_cast<float4*>(t2sm + L.in);          // [max_ir][max_ic] working floats of the source tile
-    float4* const sV = reinterpret_cast<float4*>(t2sm + L.v);            // [kTile2H][max_ic] V-filtered rows
-    uint32_t* const sHl = reinterpret_cast<uint32_t*>(t2sm + L.hl);
-    uint32_t* const sHr = reinterpret_cast<uint32_t*>(t2sm + L.hr);
-    uint32_t* const sHo = reinterpret_cast<uint32_t*>(t2sm + L.ho);
-    uint32_t* const sVl = reinterpret_cast<uint32_t*>(t2sm + L.vl);
-    uint32_t* const sVr = reinterpret_cast<uint32_t*>(t2sm + L.vr);
-    uint32_t* const sVo = reinterpret_cast<uint32_t*>(t2sm + L.vo);
-    float* const sT = reinterpret_cast<float*>(t2sm + L.t);
-    float* const sCm = reinterpret_cast<float*>(t2sm + L.cm);
-    const uint8_t* const sLut = t2sm + L.lut;
-    const int t = threadIdx.x;
-    constexpr int NC = CH == 4 ? 4 : 3;                                  // channels that are filtered
-
-    // tables: once per CTA; the V tile is cleared once so that its padding never holds a NaN pattern
-    sT[t] = __ldg((LINEAR ? tb.t_lin : tb.t_srgb) + t);
-    const int vcols = pl.max_ic + kTile2VPad;
-    for (int i = t; i < vcols * kTile2VPitch; i += 256) sV[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (LINEAR) {
-        const uint4* __restrict__ g = reinterpret_cast<const uint4*>(tb.lut16k);      // cudaMalloc'd: 256-byte aligned
-        uint4* s = reinterpret_cast<uint4*>(t2sm + L.lut);
-        for (int i = t; i < 1024; i += 256) s[i] = __ldg(g + i);
-    }
-
-    const int pitch = pl.max_ic;
-    const uint32_t n_tiles = (uint32_t)(pl.tiles_x * pl.tiles_y);
-    // work item = (job ji, tile): blockIdx.x, blockIdx.x + gridDim.x, ... of the (job, tile) list, advanced without dividing
-    uint32_t ji = blockIdx.x / n_tiles, tile = blockIdx.x - ji * n_tiles;
-    for (; ji < n_jobs; tile += gridDim.x) {
-        while (tile >= n_tiles) { tile -= n_tiles; ++ji; }
-        if (ji >= n_jobs) break;
-        const JobDev& job = jobs[ji];
-        const int tx = (int)(tile % (uint32_t)pl.tiles_x), ty = (int)(tile / (uint32_t)pl.tiles_x);
-        const int X0 = tx * kTile2W, X1 = min(X0 + kTile2W, (int)pl.out_w);
-        const int Y0 = ty * kTile2H, Y1 = min(Y0 + kTile2H, (int)pl.out_h);
-        const int ncols = X1 - X0, nrows = Y1 - Y0;
-        const int c0 = (int)__ldg(ah.left + X0), c1 = (int)__ldg(ah.right + (X1 - 1));
-        const int r0 = (int)__ldg(av.left + Y0), r1 = (int)__ldg(av.right + (Y1 - 1));
-        const int ic = c1 - c0 + 1, ir = r1 - r0 + 1;
-        const uint32_t flags = job.flags;
-        __syncthreads();                                   // the previous tile is finished (and, first time, the tables are filled)
-        // ---- window descriptors of the tile, colour matrix
-        if (t < ncols) { sHl[t] = __ldg(ah.left + X0 + t); sHr[t] = __ldg(ah.right + X0 + t); sHo[t] = __ldg(ah.off + X0 + t); }
-        if (t >= 64 && t < 64 + nrows) { const int y = Y0 + t - 64; sVl[t - 64] = __ldg(av.left + y); sVr[t - 64] = __ldg(av.right + y); sVo[t - 64] = __ldg(av.off + y); }
-        if (CM && t >= 96 && t < 116) sCm[t - 96] = job.cm[t - 96];
-        // ---- A: source tile -> working floats (item i = (r, c) = (i / ic, i % ic), advanced without dividing)
-        // item i of phase A / B = (row, column) = (i / ic, i % ic); thread t starts at item t and advances by 256.  ic < 2^15:
-        // the float quotients below are exact (the true quotient is at least 0.5 / ic away from the next integer)
-        const float ric = 1.0f / (float)ic;
-        const int dr = (int)(256.5f * ric), dc = 256 - dr * ic;
-        {
-            const int n = ir * ic;
-            int r = (int)(((float)t + 0.5f) * ric), c = t - r * ic;
-            const uint8_t* __restrict__ in0 = job.in + (size_t)r0 * job.in_stride + (size_t)c0 * 4;
-            const size_t in_stride = job.in_stride;
-            for (int i = t; i < n; i += 256) {
-                const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(in0 + (size_t)r * in_stride) + c);
-                float pb = sT[px & 0xffu], pg = sT[(px >> 8) & 0xffu], pr = sT[(px >> 16) & 0xffu], pa = 0.0f;
-                if (CH == 4) {
-                    pa = __fmul_rn(__uint2float_rn(px >> 24), 1.0f / 255.0f);
-                    pb = __fmul_rn(pb, pa); pg = __fmul_rn(pg, pa); pr = __fmul_rn(pr, pa);
-                }
-                sIn[r * pitch + c] = make_float4(pb, pg, pr, pa);
-                c += dc; r += dr;
-                if (c >= ic) { c -= ic; ++r; }
-            }
-        }
-        __syncthreads();
-        // ---- B: V pass for the tile's output rows over its source columns (item i = (yl, c))
-        {
-            const int n = nrows * ic;
-            int yl = (int)(((float)t + 0.5f) * ric), c = t - yl * ic;
-            for (int i = t; i < n; i += 256) {
-                const uint32_t l = sVl[yl], r = sVr[yl];
-                const float* __restrict__ w = av.w + sVo[yl];
-                const float4* __restrict__ col = sIn + (int)(l - (uint32_t)r0) * pitch + c;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (uint32_t j = l; j <= r; ++j, col += pitch) {
-                    const float wt = __ldg(w + (j - l));
-                    const float4 v = *col;
-                    a0 = __fmaf_rn(wt, v.x, a0); a1 = __fmaf_rn(wt, v.y, a1); a2 = __fmaf_rn(wt, v.z, a2);
-                    if (NC == 4) a3 = __fmaf_rn(wt, v.w, a3);
-                }
-                sV[(c + kTile2VPadLeft) * kTile2VPitch + yl] = make_float4(a0, a1, a2, a3);
-                c += dc; yl += dr;
-                if (c >= ic) { c -= ic; ++yl; }
-            }
-        }
-        __syncthreads();
-        // ---- C: H pass + store epilogue: thread (xl, ys) -> output column X0 + xl of rows ys, ys + 4, ys + 8, ys + 12.
-        // The window [l, r] of a column is walked as whole aligned groups of four source columns ("slots"), every lane of
-        // the warp the same number of groups: a slot outside the window gets weight 0, and fmaf(0, v, p) == p for the finite
-        // v read there (padding or a neighbour's column), as is 0 + P for the first group -- only the sign of a zero can
-        // differ, which no later operation can see.  No lane-dependent branch, no address arithmetic inside the loops.
-        {
-            const int xl = t & 63, ys = t >> 6;
-            const bool live = xl < ncols;
-            const int xi = live ? xl : ncols - 1;
-            const uint32_t l = sHl[xi], r = sHr[xi];
-            const float* __restrict__ w = ah.w + sHo[xi];
-            uint8_t* dst = job.out + (size_t)(Y0 + ys) * job.out_stride + (size_t)(X0 + xi) * 4;
-            const size_t step = (size_t)4 * job.out_stride;
-            uint32_t dpx[4] = {0u, 0u, 0u, 0u};
-            if (COMPOSE == 1 && CH == 4) {                 // canvas pixels: on their way while the H pass runs
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (live && ys + 4 * q < nrows) dpx[q] = *reinterpret_cast<const uint32_t*>(dst + q * step);
-            }
-            const uint32_t g0 = l >> 2;
-            const int ng = (int)__reduce_max_sync(0xffffffffu, (r >> 2) - g0 + 1u);
-            float f[4][NC];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int c = 0; c < NC; ++c) f[q][c] = 0.0f;
-            for (int gi = 0; gi < ng; ++gi) {
-                const uint32_t cb = (g0 + (uint32_t)gi) * 4u;                      // first source column of the group
-                const int vc = min((int)cb - c0 + kTile2VPadLeft, vcols - 4);       // its column in the V tile (clamped: weights are 0 there)
-                const float4* __restrict__ vp = sV + vc * kTile2VPitch + ys;
-                float p[4][NC];
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) p[q][c] = 0.0f;
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    const uint32_t k = cb + (uint32_t)sl;
-                    const float wt = (k >= l && k <= r) ? __ldg(w + (k - l)) : 0.0f;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 v = vp[sl * kTile2VPitch + 4 * q];
-                        p[q][0] = __fmaf_rn(wt, v.x, p[q][0]); p[q][1] = __fmaf_rn(wt, v.y, p[q][1]); p[q][2] = __fmaf_rn(wt, v.z, p[q][2]);
-                        if (NC == 4) p[q][3] = __fmaf_rn(wt, v.w, p[q][3]);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) f[q][c] = __fadd_rn(f[q][c], p[q][c]);
-            }
-            const float matte[4] = {job.matte[0], job.matte[1], job.matte[2], job.matte[3]};
-#pragma unroll
-            for (int q = 0; q < 4; ++q, dst += step) {
-                if (live && ys + 4 * q < nrows)
-                    *reinterpret_cast<uint32_t*>(dst) = finish_pixel_sm<CH, LINEAR, COMPOSE, CM>(f[q][0], f[q][1], f[q][2], NC == 4 ? f[q][NC - 1] : 0.0f,
-                                                                                                 flags, matte, sT, sLut, sCm, dpx[q]);
-            }
-        }
-    }
-}
+// ---------------------------------------------------------------- tile kernel, second form (its own file: tests/cpu_emu runs this source on the CPU)
+#include "ifb_tile2_kernel.cuh"
 
 // ---------------------------------------------------------------- standalone colour matrix (color_matrix.rs:5-28)
 __global__ void __launch_bounds__(256) color_matrix_kernel(uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
