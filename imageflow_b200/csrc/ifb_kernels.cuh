@@ -223,6 +223,9 @@ __global__ void __launch_bounds__(256) fused_tile_kernel(const JobDev* __restric
 }
 
 // ---------------------------------------------------------------- tile kernel, second form (its own file: tests/cpu_emu runs this source on the CPU)
+#ifndef IFB_DYNAMIC_SMEM                                 // (tests/cpu_emu defines it as a pointer to an exactly-sized heap block)
+#define IFB_DYNAMIC_SMEM(name_) extern __shared__ __align__(16) unsigned char name_[]
+#endif
 #include "ifb_tile2_kernel.cuh"
 
 // ---------------------------------------------------------------- standalone colour matrix (color_matrix.rs:5-28)

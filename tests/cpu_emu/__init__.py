@@ -1,0 +1,91 @@
+"""CPU emulation of product CUDA kernels (test infrastructure): the kernel sources are compiled with g++ under an emulation of
+the CUDA built-ins they use and run on small cases, so that indexing, arithmetic and -- under AddressSanitizer -- memory accesses
+of a kernel can be checked without a GPU.  Nothing in the product imports this package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+u32, f32 = C.c_uint32, C.c_float
+
+
+class JobDev(C.Structure):                          # imageflow_b200/csrc/ifb_types.cuh
+    _fields_ = [("in_", C.c_void_p), ("out", C.c_void_p), ("in_stride", u32), ("out_stride", u32), ("flags", u32),
+                ("matte", f32 * 4), ("cm", f32 * 20)]
+
+
+def build_tile2(out_dir: str, sanitize: bool = False) -> str:
+    so = os.path.join(out_dir, "libtile2_emu_asan.so" if sanitize else "libtile2_emu.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off"]
+    if sanitize:
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    subprocess.run(cmd + ["-o", so, os.path.join(HERE, "tile2_kernel_emu.cc")], check=True)
+    return so
+
+
+def csr(ws):
+    left = np.array([w[0] for w in ws], np.uint32); right = np.array([w[1] for w in ws], np.uint32)
+    off = np.zeros(len(ws), np.uint32); off[1:] = np.cumsum([len(w[2]) for w in ws])[:-1]
+    return left, right, off, np.concatenate([np.asarray(w[2], np.float32) for w in ws])
+
+
+def run_tile2(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=14, linear=True, alpha_meaningful=False, compose=0,
+              matte=(0, 0, 0, 0), color_matrix=None, grid=3, jobs_repeat=1):
+    """One launch of the emulated fused_tile2_kernel for `jobs_repeat` identical jobs (each on its own copy of the canvas);
+    mirrors what enqueue_locked / make_job / build_tile do on the host (ifb_engine.cu).  Returns the list of result canvases."""
+    L = lib
+    ih, iw = inp.shape[:2]
+    w = canvas.shape[1] - x if w is None else w
+    h = canvas.shape[0] - y if h is None else h
+    wv, wh = ifb.populate_weights(filter, h, ih), ifb.populate_weights(filter, w, iw)
+    vl, vr, vo, vw = csr(wv); hl, hr, ho, hw = csr(wh)
+    tiles_x, tiles_y = (w + 63) // 64, (h + 15) // 16
+    max_ic = max(int(hr[min(tx * 64 + 64, w) - 1]) - int(hl[tx * 64]) + 1 for tx in range(tiles_x))
+    max_ir = max(int(vr[min(ty * 16 + 16, h) - 1]) - int(vl[ty * 16]) + 1 for ty in range(tiles_y))
+    plan = np.array([iw, ih, w, h, 64, 16, tiles_x, tiles_y, max_ic, max_ir], np.int32)
+    t_lin, t_srgb, lut = (np.zeros(256, np.float32), np.zeros(256, np.float32), np.zeros(16384, np.uint8))
+    f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
+    ifb.lib().ifb200_byte_to_float_table(1, t_lin.ctypes.data_as(f32p)); ifb.lib().ifb200_byte_to_float_table(0, t_srgb.ctypes.data_as(f32p))
+    ifb.lib().ifb200_linear_to_srgb_table(lut.ctypes.data_as(u8p))
+    assert L.emu_tile2_sizeof_jobdev() == C.sizeof(JobDev)
+    inp = np.ascontiguousarray(inp)
+    outs = [np.ascontiguousarray(canvas.copy()) for _ in range(jobs_repeat)]
+    jobs = (JobDev * jobs_repeat)()
+    ch = 4 if alpha_meaningful else 3
+    for j, o in zip(jobs, outs):
+        j.in_ = inp.ctypes.data; j.out = o.ctypes.data + y * o.strides[0] + x * 4
+        j.in_stride, j.out_stride = inp.strides[0], o.strides[0]
+        j.flags = (1 if linear else 0) | (2 if alpha_meaningful else 0) | (compose << 2)
+        if compose == 2 and alpha_meaningful:
+            T = t_lin if linear else t_srgb
+            ma = np.float32(matte[3]) * np.float32(1.0 / 255.0)
+            for c in range(3):
+                j.matte[c] = float(np.float32(T[matte[c]]) * ma)
+            j.matte[3] = float(ma)
+        if color_matrix is not None:
+            m = np.ascontiguousarray(color_matrix, np.float32).reshape(25)
+            j.flags |= 16
+            for c in range(4):
+                for k in range(4):
+                    j.cm[c * 5 + k] = float(m[k * 5 + c])
+                j.cm[c * 5 + 4] = float(np.float32(m[20 + c]) * np.float32(255.0))
+            cm = np.array(list(j.cm), np.float32)
+            if all(cm[15 + k] == (1.0 if k == 3 else 0.0) for k in range(5)) and all(cm[c * 5 + 3] == 0 and cm[c * 5 + 4] == 0 for c in range(3)):
+                j.flags |= 32
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = L.emu_tile2_launch(ch, int(linear), compose, int(color_matrix is not None), grid, C.cast(jobs, C.c_void_p), jobs_repeat,
+                            p(t_lin, C.c_float), p(t_srgb, C.c_float), p(lut, C.c_uint8),
+                            p(vl, u32), p(vr, u32), p(vo, u32), p(vw, C.c_float), p(hl, u32), p(hr, u32), p(ho, u32), p(hw, C.c_float),
+                            p(plan, C.c_int32))
+    assert rc == 0
+    return outs
+
+
+def load_tile2(so):
+    L = C.CDLL(so)
+    L.emu_tile2_sizeof_jobdev.restype = u32
+    L.emu_tile2_launch.restype = C.c_int
+    L.emu_tile2_launch.argtypes = [C.c_int] * 4 + [C.c_uint, C.c_void_p, u32] + [C.c_void_p] * 11 + [C.c_void_p]
+    return L
