@@ -55,9 +55,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--nt", type=int, default=0)
-    ap.add_argument("--gather-ahead", type=int, default=-1, choices=[-1, 0, 1], help="ring kernel gather-ahead form (-1 = library default)")
-    ap.add_argument("--tile-kernel", type=int, default=0, choices=[0, 1, 2], help="tile kernel form for up-scales (0 = library default)")
+    ap.add_argument("--strip-cols", type=int, default=0, help="ring kernel: widest strip of output columns per warp (0 = library default)")
+    ap.add_argument("--min-items", type=int, default=-1, help="ring kernel: band split target (-1 = library default)")
     return ap.parse_args()
 
 
@@ -251,12 +250,10 @@ def main():
     cm = ifb.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
 
     batch = ifb.Batch(local)
-    if args.nt:
-        batch.set_option(ifb.Batch.OPT_THREADS_PER_CTA, args.nt)
-    if args.gather_ahead >= 0:
-        batch.set_option(ifb.Batch.OPT_GATHER_AHEAD, args.gather_ahead)
-    if args.tile_kernel:
-        batch.set_option(ifb.Batch.OPT_TILE_KERNEL, args.tile_kernel)
+    if args.strip_cols:
+        batch.set_option(ifb.Batch.OPT_STRIP_COLUMNS, args.strip_cols)
+    if args.min_items >= 0:
+        batch.set_option(ifb.Batch.OPT_MIN_ITEMS, args.min_items)
     params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))
     jobs = [(ifb.BitmapWindow.from_torch(inp[i], alpha_meaningful=bool(alpha)),
              ifb.BitmapWindow.from_torch(out[i], compose=ifb.BitmapCompositing(wl["compose"])), params, cm) for i in range(B)]

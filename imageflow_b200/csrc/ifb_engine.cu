@@ -16,8 +16,10 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ifb200.h"
@@ -126,24 +128,13 @@ struct AxisOnDev {
     AxisDev view(const DevBlob& blob) const { return AxisDev{blob.at<uint32_t>(o_left), blob.at<uint32_t>(o_right), blob.at<uint32_t>(o_off), blob.at<float>(o_w)}; }
 };
 
-// Supported (AV, SH) instantiations of the fused kernel.
-constexpr int kAvChoices[] = {2, 4, 6};
-constexpr int kShChoices[] = {3, 5, 6, 7, 8};
-// Rows per prefetch set (two sets in registers): as deep as the register budget of the variant allows (128 registers per
-// thread at two 256-thread CTAs per SM; the ring takes AV * 4 * CH of them).
-constexpr int prefetch_rows(int av, int ch) {
-#ifdef IFB_PF
-    return IFB_PF;
-#else
-    return ch == 3 ? (av <= 2 ? 6 : av <= 4 ? 5 : 3) : (av <= 2 ? 6 : av <= 4 ? 3 : 2);
-#endif
-}
-
-struct FusedVariantTables {      // depends on NT (strips) and band count
-    int nt = 0, n_strips = 0;
-    DevBlob blob;                       // strips, hw, hrd, the row program and the band tables, one allocation
-    size_t o_strips = 0, o_hw = 0, o_hrd = 0, o_vprog[2] = {0, 0};
-    std::map<int, size_t> o_bands;      // by band count (a fixed set, chosen when the tables are built)
+// ------------------------------------------------------------------------------------------------
+// Streaming H-then-V ring kernel (ifb_hv_kernel.cuh): host tables of one plan.
+struct HvTables {
+    int max_cols = 0, n_strips = 0;
+    std::vector<HvStripDev> strips;     // host copy (band choice, tests)
+    DevBlob blob;                       // strips, hw, hdone, vw, vdone: one allocation, one asynchronous copy
+    size_t o_strips = 0, o_hw = 0, o_hdone = 0, o_vw = 0, o_vdone = 0;
 };
 
 struct Plan {
@@ -152,12 +143,11 @@ struct Plan {
     AxisOnDev dv, dh; std::unique_ptr<DevBlob> axes;   // CSR windows on the device: only the tile kernel and the generic pair read them
     // tile kernel (small windows: up-scales, 1:1, mild down-scales)
     bool tile_ok = false; TilePlanDev tile{};
-    // fused
-    bool fused_ok = false; std::string fused_reason;
-    int av = 0, sh = 0;
-    std::vector<uint32_t> vdone_host;
-    std::map<int, std::unique_ptr<FusedVariantTables>> by_nt;
-    std::vector<int> nt_failed;         // CTA sizes whose strips cannot hold this geometry (e.g. 3000 -> 1 columns): not fused
+    // ring kernel
+    bool hv_ok = false; std::string hv_reason;
+    int av = 0;                          // ring depth of the kernel variant: 4 or 6 (both axes)
+    std::map<int, std::unique_ptr<HvTables>> by_cols;   // by the largest strip width allowed (IFB200_OPT_STRIP_COLUMNS)
+    std::vector<int> cols_failed;        // strip widths at which some column's window does not fit the weight table: not ring
 };
 
 bool monotone(const ifb::AxisWeights& a) {
@@ -166,41 +156,23 @@ bool monotone(const ifb::AxisWeights& a) {
     return true;
 }
 
-int pick(const int* choices, int n, int need) {
-    for (int i = 0; i < n; ++i) if (choices[i] >= need) return choices[i];
-    return 0;
-}
-
-void build_fused_v(Plan& p) {
-    const auto& a = p.wv;
-    if (!monotone(a) || !monotone(p.wh)) { p.fused_reason = "non-monotone windows"; return; }
-    if (p.in_w < 4) { p.fused_reason = "in_w < 4"; return; }
-    // ring depth: smallest A with left[y+A] > right[y] for all y
+// smallest A such that at most A consecutive outputs are open at any source sample: left[y+A] > right[y] for all y
+int ring_depth(const ifb::AxisWeights& a) {
     int need = 1;
-    for (;; ++need) {
+    for (; need <= 64; ++need) {
         bool ok = true;
         for (uint32_t y = 0; y + need < a.out_size && ok; ++y) ok = a.left[y + need] > a.right[y];
         if (ok) break;
-        if (need > 64) break;
     }
-    p.av = pick(kAvChoices, (int)(sizeof kAvChoices / sizeof *kAvChoices), need);
-    if (!p.av) { p.fused_reason = "vertical ring depth " + std::to_string(need) + " > 6"; return; }
-    // horizontal slots per aligned group of 4 source columns
-    std::vector<int> cnt(p.in_w / 4 + 2, 0);
-    for (uint32_t X = 0; X < p.wh.out_size; ++X)
-        for (uint32_t g = p.wh.left[X] / 4; g <= p.wh.right[X] / 4; ++g) cnt[g]++;
-    int hneed = *std::max_element(cnt.begin(), cnt.end());
-    p.sh = pick(kShChoices, (int)(sizeof kShChoices / sizeof *kShChoices), hneed);
-    if (!p.sh) { p.fused_reason = "horizontal slots " + std::to_string(hneed) + " > 8"; return; }
+    return need;
+}
 
-    std::vector<uint32_t> vdone(p.in_h, 0u);
-    for (uint32_t y = 0; y < a.out_size; ++y) {
-        uint32_t& d = vdone[a.right[y]];
-        if ((d & 0xffu) == 0) d = (y << 8) | 1u; else d += 1u;
-        if ((d & 0xffu) > 15u) { p.fused_reason = "too many rows complete at once"; return; }
-    }
-    p.vdone_host = std::move(vdone);
-    p.fused_ok = true;
+void build_hv(Plan& p) {
+    if (!monotone(p.wv) || !monotone(p.wh)) { p.hv_reason = "non-monotone windows"; return; }
+    const int need = std::max(ring_depth(p.wv), ring_depth(p.wh));
+    if (need > 6) { p.hv_reason = "ring depth " + std::to_string(need) + " > 6"; return; }
+    p.av = need <= 4 ? 4 : 6;
+    p.hv_ok = true;
 }
 
 // tile kernel: 64 x 16 output pixels per CTA; usable when the source extent of every tile fits in shared memory
@@ -208,7 +180,7 @@ void build_tile(Plan& p) {
     if (!monotone(p.wv) || !monotone(p.wh)) return;
     TilePlanDev t{};
     t.in_w = p.in_w; t.in_h = p.in_h; t.out_w = p.out_w; t.out_h = p.out_h;
-    t.tow = kTile2W; t.toh = kTile2H;                       // 64 x 16: both tile kernels
+    t.tow = kTile2W; t.toh = kTile2H;
     t.tiles_x = (int)((p.out_w + t.tow - 1) / t.tow); t.tiles_y = (int)((p.out_h + t.toh - 1) / t.toh);
     for (int tx = 0; tx < t.tiles_x; ++tx) {
         const uint32_t X0 = tx * t.tow, X1 = std::min<uint32_t>(X0 + t.tow, p.out_w);
@@ -218,173 +190,147 @@ void build_tile(Plan& p) {
         const uint32_t Y0 = ty * t.toh, Y1 = std::min<uint32_t>(Y0 + t.toh, p.out_h);
         t.max_ir = std::max<int>(t.max_ir, (int)(p.wv.right[Y1 - 1] - p.wv.left[Y0] + 1));
     }
-    const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
-    if (smem > 96 * 1024) return;                        // large windows: the ring kernel or the generic pair
+    if (Tile2Smem::make(t.max_ir, t.max_ic, true).total > 96u * 1024u) return;   // large windows: the ring kernel or the generic pair
     p.tile = t; p.tile_ok = true;
 }
 
-// per-source-row program: weight (float bits) per ring slot -- output row y owns slot y mod AV while its window is
-// open (build_fused_v guarantees at most AV consecutive rows are open at once) -- then the completion word
-size_t fused_vprog_bytes(const Plan& p) { return (size_t)p.in_h * (((uint32_t)p.av + 1 + 3) / 4 * 4) * sizeof(uint32_t); }
-void fused_vprog_host(const Plan& p, uint32_t* prog) {      // prog: fused_vprog_bytes(p) zeroed bytes
-    const uint32_t nw = (uint32_t)p.av;
-    const uint32_t words = (nw + 1 + 3) / 4 * 4;
-    const auto& a = p.wv;
-    for (uint32_t y = 0; y < a.out_size; ++y) {
-        const float* w = a.w.data() + a.offset[y];
-        for (uint32_t j = a.left[y]; j <= a.right[y]; ++j) {
-            uint32_t bits; memcpy(&bits, &w[j - a.left[y]], 4);
-            prog[(size_t)j * words + y % nw] = bits;
-        }
-    }
-    for (uint32_t j = 0; j < p.in_h; ++j) {
-        const uint32_t d = p.vdone_host[j];
-        if (d & 0xffu) prog[(size_t)j * words + nw] = (d & ~0xffu) | (((d >> 8) % nw) << 4) | (d & 0xfu);
-    }
-}
+template <class F> void hv_for_av(int av, F&& f) { if (av == 4) f(std::integral_constant<int, 4>{}); else f(std::integral_constant<int, 6>{}); }
 
-// host half: strips, H-weight block, reader meta, row program and band tables, staged in ft->blob.host (no CUDA calls)
-std::unique_ptr<FusedVariantTables> fused_tables_host(const Plan& p, int nt) {
-    auto ft = std::make_unique<FusedVariantTables>();
-    ft->nt = nt;
-    const auto& h = p.wh;
-    const uint32_t span = 4u * nt;
-    auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1)
-        uint32_t k0 = (h.left[X0] / 4) * 4;
-        return (X1 - X0) <= (uint32_t)nt && h.right[X1 - 1] < k0 + span;
+// host half: strips, per-strip H weights by ring slot in pixel-stream order, completion counts, V weights by ring slot
+std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
+    auto ht = std::make_unique<HvTables>();
+    ht->max_cols = max_cols;
+    const auto& h = p.wh; const auto& v = p.wv;
+    const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4), ng = av == 4 ? 4 : 2;
+    const uint32_t col_cap = (uint32_t)std::min(max_cols, ng * 32);
+    auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1): at most col_cap columns and a pixel stream (whole stages of 16) within the table
+        return X1 - X0 <= col_cap && (h.right[X1 - 1] - h.left[X0] + 1 + 15) / 16 * 16 <= (uint32_t)cap;
     };
-    // greedy count, then balance
     uint32_t ns = 0;
     for (uint32_t X0 = 0; X0 < h.out_size; ++ns) {
         uint32_t X1 = X0 + 1;
-        if (!fits(X0, X1)) IFB_THROW(IFB200_ERR_INVALID_STATE, "strip cannot hold one output column (taps %u, nt %d)", h.max_taps, nt);
+        if (!fits(X0, X1)) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: one output column reads %u source columns (> %d)", h.right[X0] - h.left[X0] + 1, cap);
         while (X1 < h.out_size && fits(X0, X1 + 1)) ++X1;
         X0 = X1;
     }
-    std::vector<StripDev> strips;
-    for (;; ++ns) {
+    std::vector<HvStripDev>& strips = ht->strips;
+    for (;; ++ns) {                                  // balance: equal column counts, if they fit
         strips.clear();
         bool ok = true;
         for (uint32_t s = 0; s < ns && ok; ++s) {
-            uint32_t X0 = (uint32_t)((uint64_t)h.out_size * s / ns), X1 = (uint32_t)((uint64_t)h.out_size * (s + 1) / ns);
+            const uint32_t X0 = (uint32_t)((uint64_t)h.out_size * s / ns), X1 = (uint32_t)((uint64_t)h.out_size * (s + 1) / ns);
             if (X1 <= X0) { ok = false; break; }
             ok = fits(X0, X1);
-            strips.push_back(StripDev{(int)X0, (int)X1, (int)((h.left[X0] / 4) * 4), 0});
+            HvStripDev sd{};
+            sd.X0 = (int)X0; sd.X1 = (int)X1; sd.k0 = (int)h.left[X0];
+            sd.nst = (int)((h.right[X1 - 1] - h.left[X0] + 1 + 15) / 16);
+            uint32_t Xf = X0;                        // first column completing inside the stream: right[Xf] >= k0
+            while (Xf > 0 && h.right[Xf - 1] >= h.left[X0]) --Xf;
+            sd.Xf = (int)Xf; sd.hslot0 = (int)(Xf % (uint32_t)av);
+            strips.push_back(sd);
         }
         if (ok) break;
-        if (ns > h.out_size) IFB_THROW(IFB200_ERR_INVALID_STATE, "strip partition failed");
+        if (ns > h.out_size) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: strip partition failed");
     }
-    ft->n_strips = (int)ns;
-    const int SH = p.sh;
-    // everything the kernel reads for this (plan, CTA size) goes into one allocation and one asynchronous copy; the
-    // tables are built in place in the staging blob (no intermediate vectors)
-    const size_t n_hw = (size_t)ns * SH * 4 * nt, n_hrd = (size_t)ns * nt;
-    ft->blob.reserve(strips.size() * sizeof(StripDev) + (n_hw + n_hrd) * 4 + fused_vprog_bytes(p) + 6 * 256 + 16 * 1024);
-    ft->o_strips = ft->blob.add(strips);
-    ft->o_hw = ft->blob.add_zeroed(n_hw * sizeof(float));
-    ft->o_hrd = ft->blob.add_zeroed(n_hrd * sizeof(uint32_t));
-    float* const hw = ft->blob.host_at<float>(ft->o_hw);
-    uint32_t* const hrd = ft->blob.host_at<uint32_t>(ft->o_hrd);
+    ht->n_strips = (int)ns;
+    const size_t hd_stride = (size_t)cap + 32;
+    ht->blob.reserve(ns * (sizeof(HvStripDev) + (size_t)cap * avp * 4 + hd_stride) + (size_t)p.in_h * (avp * 4 + 1) + 4096);
+    ht->o_strips = ht->blob.add(strips);
+    ht->o_hw = ht->blob.add_zeroed((size_t)ns * cap * avp * sizeof(float));
+    ht->o_hdone = ht->blob.add_zeroed((size_t)ns * hd_stride);
+    ht->o_vw = ht->blob.add_zeroed((size_t)p.in_h * avp * sizeof(float));
+    ht->o_vdone = ht->blob.add_zeroed((size_t)p.in_h + 32);
+    float* const hw = ht->blob.host_at<float>(ht->o_hw);
+    uint8_t* const hdone = ht->blob.host_at<uint8_t>(ht->o_hdone);
+    float* const vw = ht->blob.host_at<float>(ht->o_vw);
+    uint8_t* const vdone = ht->blob.host_at<uint8_t>(ht->o_vdone);
     for (uint32_t s = 0; s < ns; ++s) {
-        const StripDev& sd = strips[s];
-        uint32_t Xlo = sd.X0;     // first output of the strip whose window may still reach the current group
-        for (int t = 0; t < nt; ++t) {
-            const uint32_t c0 = sd.k0 + 4u * t, c1 = c0 + 3u;
-            while (Xlo < (uint32_t)sd.X1 && h.right[Xlo] < c0) ++Xlo;
-            uint32_t Xa = Xlo, n = 0;
-            for (uint32_t X = Xlo; X < (uint32_t)sd.X1 && h.left[X] <= c1; ++X) ++n;
-            if (n > (uint32_t)SH) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: %u outputs in one column group > SH=%d", n, SH);
-            for (uint32_t q = 0; q < n; ++q) {
-                const uint32_t X = Xa + q;
-                const float* w = h.w.data() + h.offset[X];
-                for (uint32_t i = 0; i < 4; ++i) {
-                    const uint32_t k = c0 + i;
-                    if (k < h.left[X] || k > h.right[X]) continue;
-                    // by partial plane pl = X mod SH: planes (2k, 2k+1) interleaved as float2, an odd last plane as two float2
-                    const size_t base = (size_t)s * SH * 4 * nt;
-                    const uint32_t pl = X % (uint32_t)SH;
-                    const size_t idx = (pl / 2 < (uint32_t)SH / 2) ? 2 * ((size_t)((pl / 2) * 4 + i) * nt + t) + (pl & 1)
-                                                                   : 2 * ((size_t)((SH / 2) * 4 + i / 2) * nt + t) + (i & 1);
-                    hw[base + idx] = w[k - h.left[X]];
-                }
+        const HvStripDev& sd = strips[s];
+        const uint32_t k0 = (uint32_t)sd.k0, kend = k0 + (uint32_t)sd.nst * 16u - 1u;
+        for (uint32_t X = (uint32_t)sd.Xf; X < h.out_size && h.left[X] <= kend; ++X) {
+            const float* w = h.w.data() + h.offset[X];
+            const uint32_t slot = X % (uint32_t)av;
+            for (uint32_t k = std::max(h.left[X], k0); k <= std::min(h.right[X], kend); ++k)
+                hw[((size_t)s * cap + (k - k0)) * avp + slot] = w[k - h.left[X]];
+            if (h.right[X] >= k0 && h.right[X] <= kend) {
+                uint8_t& d = hdone[(size_t)s * hd_stride + (h.right[X] - k0)];
+                if (d == 255) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: too many columns complete at once");
+                ++d;
             }
         }
-        for (uint32_t X = sd.X0; X < (uint32_t)sd.X1; ++X) {
-            const uint32_t tg0 = h.left[X] / 4 - sd.k0 / 4, ng = h.right[X] / 4 - h.left[X] / 4 + 1;
-            if (tg0 + ng > (uint32_t)nt || ng >= 4096u) IFB_THROW(IFB200_ERR_INVALID_STATE, "internal: reader range outside strip");
-            hrd[(size_t)s * nt + (X - sd.X0)] = tg0 | (ng << 12) | ((X % (uint32_t)SH) << 28);
-        }
     }
-    ft->o_vprog[0] = ft->blob.add_zeroed(fused_vprog_bytes(p));
-    fused_vprog_host(p, ft->blob.host_at<uint32_t>(ft->o_vprog[0]));
-    for (int nb = 1; ; nb *= 2) {                        // band tables for power-of-two band counts
-        const int use = std::min<int>(nb, (int)std::max<uint32_t>(1u, p.out_h / 8u));
-        if (!ft->o_bands.count(use)) {
-            std::vector<BandDev> bv;
-            for (int i = 0; i < use; ++i) {
-                const int Y0 = (int)((int64_t)p.out_h * i / use), Y1 = (int)((int64_t)p.out_h * (i + 1) / use);
-                bv.push_back(BandDev{Y0, Y1, (int)p.wv.left[Y0], (int)p.wv.right[Y1 - 1]});
-            }
-            ft->o_bands[use] = ft->blob.add(bv);
-        }
-        if (use < nb || nb >= 4096) break;
+    for (uint32_t y = 0; y < v.out_size; ++y) {
+        const float* w = v.w.data() + v.offset[y];
+        const uint32_t slot = y % (uint32_t)av;
+        for (uint32_t j = v.left[y]; j <= v.right[y]; ++j) vw[(size_t)j * avp + slot] = w[j - v.left[y]];
+        uint8_t& d = vdone[v.right[y]];
+        if (d == 255) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: too many rows complete at once");
+        ++d;
     }
-    return ft;
+    return ht;
 }
 
-// The host tables of (plan, CTA size) exist or can be built.  A geometry whose H windows are wider than a strip (a
-// 3000 -> 1 column down-scale has 1400+ taps) cannot run on the ring kernel at that CTA size: it is remembered as such and
-// the job takes the tile kernel or the generic pair instead of failing.
-bool fused_host_ready(Plan& p, int nt) {
-    if (!p.fused_ok) return false;
-    if (p.by_nt.count(nt)) return true;
-    if (std::find(p.nt_failed.begin(), p.nt_failed.end(), nt) != p.nt_failed.end()) return false;
-    try { p.by_nt.emplace(nt, fused_tables_host(p, nt)); return true; }
-    catch (const Err& e) { p.nt_failed.push_back(nt); if (p.fused_reason.empty()) p.fused_reason = e.msg; return false; }
+// The host tables of (plan, strip width) exist or can be built.  A geometry whose H windows are wider than the weight table
+// (a 3000 -> 1 column down-scale has 1400+ taps) cannot run on the ring kernel: it is remembered as such and the job takes the
+// tile kernel or the generic pair instead of failing.
+bool hv_host_ready(Plan& p, int max_cols) {
+    if (!p.hv_ok) return false;
+    if (p.by_cols.count(max_cols)) return true;
+    if (std::find(p.cols_failed.begin(), p.cols_failed.end(), max_cols) != p.cols_failed.end()) return false;
+    try { p.by_cols.emplace(max_cols, hv_tables_host(p, max_cols)); return true; }
+    catch (const Err& e) { p.cols_failed.push_back(max_cols); if (p.hv_reason.empty()) p.hv_reason = e.msg; return false; }
 }
 
 // device half: one allocation + one asynchronous copy on the first use; later uses only order their stream after it
-FusedVariantTables& fused_tables(ifb200_batch* bt, cudaStream_t st, Plan& p, int nt) {
-    auto it = p.by_nt.find(nt);
-    if (it == p.by_nt.end()) it = p.by_nt.emplace(nt, fused_tables_host(p, nt)).first;
-    FusedVariantTables& ft = *it->second;
-    if (!ft.blob.p) ft.blob.commit(bt, st); else ft.blob.use_on(st);
-    return ft;
+HvTables& hv_tables(ifb200_batch* bt, cudaStream_t st, Plan& p, int max_cols) {
+    auto it = p.by_cols.find(max_cols);
+    if (it == p.by_cols.end()) it = p.by_cols.emplace(max_cols, hv_tables_host(p, max_cols)).first;
+    HvTables& ht = *it->second;
+    if (!ht.blob.p) ht.blob.commit(bt, st); else ht.blob.use_on(st);
+    return ht;
 }
 
-// smallest prepared band count >= want
-int pick_bands(const FusedVariantTables& ft, int want) {
-    int best = ft.o_bands.rbegin()->first;
-    for (const auto& kv : ft.o_bands) if (kv.first >= want) { best = kv.first; break; }
+// Row bands of one launch: output rows split evenly, each band with the source rows its windows need.
+std::vector<HvBandDev> hv_bands(const Plan& p, int nb) {
+    const auto& v = p.wv;
+    std::vector<HvBandDev> bands;
+    for (int i = 0; i < nb; ++i) {
+        const uint32_t Y0 = (uint32_t)((uint64_t)p.out_h * i / nb), Y1 = (uint32_t)((uint64_t)p.out_h * (i + 1) / nb);
+        if (Y1 <= Y0) continue;
+        HvBandDev b{};
+        b.Y0 = (int)Y0; b.Y1 = (int)Y1; b.j0 = (int)v.left[Y0]; b.nrows = (int)(v.right[Y1 - 1] - v.left[Y0] + 1);
+        uint32_t Yf = Y0;
+        while (Yf > 0 && v.right[Yf - 1] >= v.left[Y0]) --Yf;
+        b.Yf = (int)Yf; b.vslot0 = (int)(Yf % (uint32_t)p.av);
+        bands.push_back(b);
+    }
+    return bands;
+}
+// Band count of a launch: enough work items for every warp of the grid, then the count whose last round of items is fullest,
+// counting what the band halos (the V window is re-read at every band edge) cost.
+int hv_pick_bands(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
+    const int max_nb = (int)std::max<uint32_t>(1u, p.out_h / 8u);
+    const double halo = (double)p.wv.max_taps / (double)std::max<uint32_t>(p.in_h, 1u);
+    int best = 1; double best_eff = -1.0;
+    for (int nb = 1; nb <= std::min(max_nb, 64); ++nb) {
+        const double items = (double)jobs_x_strips * nb;
+        if (items < (double)min_items && nb < max_nb && nb < 64) continue;
+        const double rounds = std::ceil(items / warps);
+        const double eff = items / warps / rounds / (1.0 + halo * (nb - 1));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = nb; }
+    }
     return best;
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused kernel dispatch table
-using FusedFn = void (*)(const JobDev*, Tables, FusedPlanDev);
-struct FusedEntry { int av, sh, ch, nt; FusedFn fn, fn_simple, fn_ga, fn_simple_ga; size_t smem; };
-// gather-ahead form (IFB200_OPT_GATHER_AHEAD): the cubic-filter ring (AV 4), 256 threads, shapes whose row stages are an even count
-template <int AV, int SH, int CH, int NT, bool SIMPLE> constexpr FusedFn ga_fn() {
-    if constexpr (AV == 4 && NT == 256 && FusedSmem<AV, SH, CH, NT>::kStages > 0 && FusedSmem<AV, SH, CH, NT>::kStages % 2 == 0)
-        return fused_down_kernel<AV, SH, CH, prefetch_rows(AV, CH), NT, SIMPLE, true>;
-    else
-        return nullptr;
-}
-#define IFB_FUSED_1(AV_, SH_, CH_, NT_) {AV_, SH_, CH_, NT_, fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, false>, \
-                                         fused_down_kernel<AV_, SH_, CH_, prefetch_rows(AV_, CH_), NT_, true>, \
-                                         ga_fn<AV_, SH_, CH_, NT_, false>(), ga_fn<AV_, SH_, CH_, NT_, true>(), (size_t)FusedSmem<AV_, SH_, CH_, NT_>::kTotal}
-#define IFB_FUSED(AV_, SH_) IFB_FUSED_1(AV_, SH_, 3, 256), IFB_FUSED_1(AV_, SH_, 4, 256), IFB_FUSED_1(AV_, SH_, 3, 128), IFB_FUSED_1(AV_, SH_, 4, 128)
-const FusedEntry kFused[] = {
-#ifdef IFB_FEW_SHAPES      /* development builds: only the shapes the 4K->512 benchmarks use */
-    IFB_FUSED(4, 5), IFB_FUSED(6, 7),
-#else
-    IFB_FUSED(2, 3), IFB_FUSED(2, 5), IFB_FUSED(2, 6), IFB_FUSED(2, 7), IFB_FUSED(2, 8),
-    IFB_FUSED(4, 3), IFB_FUSED(4, 5), IFB_FUSED(4, 6), IFB_FUSED(4, 7), IFB_FUSED(4, 8),
-    IFB_FUSED(6, 3), IFB_FUSED(6, 5), IFB_FUSED(6, 6), IFB_FUSED(6, 7), IFB_FUSED(6, 8),
-#endif
-};
-const FusedEntry* find_fused(int av, int sh, int ch, int nt) {
-    for (const auto& e : kFused) if (e.av == av && e.sh == sh && e.ch == ch && e.nt == nt) return &e;
+// ring kernel dispatch table
+using HvFn = void (*)(const JobDev*, const HvTmap*, Tables, HvPlanDev, uint32_t, uint32_t*);
+struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps; uint32_t (*smem)(uint32_t); };
+template <int AV, int CH> uint32_t hv_smem_bytes(uint32_t sb_low16) { return HvCfg<AV, CH>::total_bytes(sb_low16); }
+#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, hv_smem_bytes<AV_, CH_>}
+const HvEntry kHv[] = {IFB_HV(4, 3), IFB_HV(4, 4), IFB_HV(6, 3), IFB_HV(6, 4)};
+const HvEntry* find_hv(int av, int ch) {
+    for (const auto& e : kHv) if (e.av == av && e.ch == ch) return &e;
     return nullptr;
 }
 
@@ -399,6 +345,21 @@ Tile2Fn find_tile2(int ch, bool linear, int compose, bool cm) { return kTile2[ch
 
 // ------------------------------------------------------------------------------------------------
 struct PinnedSlot { void* p = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; };
+
+// cuTensorMapEncodeTiled, looked up through the runtime (cudaGetDriverEntryPoint): the library does not link libcuda
+using TmapEncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct TmapKey {
+    uintptr_t base; uint32_t w, h, stride;
+    bool operator==(const TmapKey& o) const { return base == o.base && w == o.w && h == o.h && stride == o.stride; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t x = (uint64_t)k.base * 0x9E3779B97F4A7C15ull;
+        x ^= ((uint64_t)k.w << 32 | k.h) * 0xC2B2AE3D27D4EB4Full; x ^= (uint64_t)k.stride * 0x165667B19E3779F9ull;
+        return (size_t)(x ^ (x >> 29));
+    }
+};
 
 }  // namespace
 
@@ -418,11 +379,15 @@ struct ifb200_batch {
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
-    bool force_generic = false; int nt = 256; int min_ctas = 296;
-    int tile_variant = 0;    // IFB200_OPT_TILE_KERNEL: 0 default, 1 first form (fused_tile_kernel), 2 second form (fused_tile2_kernel)
+    bool force_generic = false; int strip_cols = 128; int min_items = 0;
     int sm_count = 148;
-    bool gather_ahead = false;   // IFB200_OPT_GATHER_AHEAD
-    bool ring_ok = true;     // the shared window is laid out as the ring kernel's LUT gather assumes (smem_base_probe_kernel)
+    // ring kernel: where dynamic shared memory starts in the shared window (probed once), whether TMA descriptors can be made
+    uint32_t smem_base_low16 = 0x400u;
+    bool ring_ok = true; std::string ring_reason;
+    TmapEncodeFn tmap_encode = nullptr;
+    std::unordered_map<TmapKey, HvTmap, TmapKeyHash> tmaps;   // encoded once per (base, width, height, pitch)
+    std::map<std::pair<const void*, size_t>, int> tile_occupancy;   // resident tile-kernel CTAs per SM, by (variant, shared memory)
+    std::set<const void*> hv_attr_set;                        // ring-kernel variants whose shared-memory attribute is set
     // counters
     uint64_t launches = 0, fused_jobs = 0, generic_jobs = 0, tile_jobs = 0;
     // where the calling thread spends an enqueue (seconds, inclusive; ifb200_batch_host_profile)
@@ -483,7 +448,7 @@ struct ifb200_batch {
     }
     // Everything of a plan that needs no CUDA call (weights exactly as weights.rs, kernel tables staged for upload);
     // thread-safe, so that an enqueue with many new geometries builds its plans on several host threads.
-    static std::unique_ptr<Plan> build_plan_host(const ifb200_resample_desc& d, int nt) {
+    static std::unique_ptr<Plan> build_plan_host(const ifb200_resample_desc& d, int strip_cols) {
         const float sp = d.sharpen_percent > 0.0f ? d.sharpen_percent : 0.0f;
         auto p = std::make_unique<Plan>();
         p->in_w = d.in_w; p->in_h = d.in_h; p->out_w = d.w; p->out_h = d.h;
@@ -492,16 +457,16 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "vertical weights failed: %s", ifb200_status_name(rc));
         rc = ifb::compute_axis_weights(d.filter, 1.0, lobe, sp, d.w, d.in_w, p->wh);
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
-        build_fused_v(*p);
+        build_hv(*p);
         build_tile(*p);
-        if (p->fused_ok && !(p->tile_ok && p->out_h >= p->in_h && p->out_w >= p->in_w)) fused_host_ready(*p, nt);
+        if (p->hv_ok) hv_host_ready(*p, strip_cols);
         return p;
     }
     Plan& plan_for(const ifb200_resample_desc& d) {
         const Key k = key_of(d);
         auto it = plans.find(k);
         if (it != plans.end()) return *it->second;
-        Plan& ref = *(plans[k] = build_plan_host(d, nt));
+        Plan& ref = *(plans[k] = build_plan_host(d, strip_cols));
         return ref;
     }
     // build the plans this call needs and the cache lacks, in parallel
@@ -526,7 +491,7 @@ struct ifb200_batch {
         std::vector<Err> errs(work.size(), Err{0, ""});
         std::atomic<size_t> next{0};
         const unsigned nthreads = std::max(1u, std::min<unsigned>({std::thread::hardware_concurrency(), 32u, (unsigned)work.size()}));
-        const int cta = nt;
+        const int cta = strip_cols;
         auto worker = [&] {
             for (size_t w; (w = next.fetch_add(1)) < work.size();) {
                 try { built[w] = build_plan_host(descs[work[w].second], cta); }
@@ -588,7 +553,7 @@ JobDev make_job(const ifb200_resample_desc& d, const float* t_lin_host, const fl
     JobDev j{};
     j.in = d.in;
     j.out = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
-    j.in_stride = d.in_stride; j.out_stride = d.cv_stride;
+    j.in_stride = d.in_stride; j.out_stride = d.cv_stride; j.in_xoff = 0;
     j.flags = (d.linear ? JF_LINEAR : 0u) | (d.alpha_meaningful ? JF_ALPHA : 0u) | ((uint32_t)d.compose << JF_COMPOSE_SHIFT);
     if (d.compose == IFB200_BLEND_WITH_MATTE && d.alpha_meaningful) {
         const float* T = d.linear ? t_lin_host : t_srgb_host;
@@ -617,6 +582,39 @@ void host_tables() {
     std::call_once(g_tables_once, [] { ifb::byte_to_float_table(true, g_t_lin_host); ifb::byte_to_float_table(false, g_t_srgb_host); });
 }
 
+// TMA descriptor of one input bitmap for the ring kernel: u32 pixels, box 16 x 32, SWIZZLE_64B, out-of-bounds = 0.
+// The base is aligned down to 16 bytes (a window may start at any pixel: bitmaps.rs:413-431); the kernel adds the 0..3 pixels
+// it was moved by to its x coordinates.
+const HvTmap& tmap_for(ifb200_batch* b, const ifb200_resample_desc& d, uint32_t* xoff_out) {
+    const uintptr_t addr = (uintptr_t)d.in;
+    const uintptr_t base = addr & ~(uintptr_t)15;
+    const uint32_t xoff = (uint32_t)((addr - base) / 4);
+    *xoff_out = xoff;
+    const TmapKey key{base, d.in_w + xoff, d.in_h, d.in_stride};
+    auto it = b->tmaps.find(key);
+    if (it != b->tmaps.end()) return it->second;
+    if (b->tmaps.size() > 65536) b->tmaps.clear();
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)d.in_w + xoff, (cuuint64_t)d.in_h};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.in_stride};
+    const cuuint32_t box[2] = {16u, 32u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = b->tmap_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IFB_THROW(IFB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %ux%u bitmap, pitch %u", (int)r, d.in_w, d.in_h, d.in_stride);
+    HvTmap h;
+    static_assert(sizeof(CUtensorMap) == sizeof(h.bytes), "tensor map size");
+    memcpy(h.bytes, &tm, sizeof h.bytes);
+    return b->tmaps.emplace(key, h).first->second;
+}
+
+// frees a stream-ordered allocation when the scope is left by an exception (the normal path frees it itself)
+struct AsyncFree {
+    void* p = nullptr; cudaStream_t st = nullptr;
+    ~AsyncFree() { if (p) cudaFreeAsync(p, st); }
+    void release() { p = nullptr; }
+};
+
 void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n, cudaStream_t st) {
     if (n == 0) return;
     Tick tk_all(b->prof.enqueue);
@@ -625,59 +623,96 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
     { Tick tk(b->prof.plans); b->prebuild_plans(descs, n); }
     // group jobs by (plan, kernel class)
-    // kind: 0 generic pair, 1 fused ring, 2 tile (first form), 3 tile (second form; `variant` = its compile-time case)
+    // kind: 0 generic pair, 1 ring kernel, 3 tile kernel (`variant` = its compile-time case)
     struct Group { Plan* plan; int ch; int kind; bool simple; int variant; std::vector<size_t> idx; };
-    const int tile_kind = b->tile_variant == 1 ? 2 : 3;
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
-        validate(descs[i]);
         Plan* pp; { Tick tk(b->prof.plans); pp = &b->plan_for(descs[i]); }
         Plan& p = *pp;
         const ifb200_resample_desc& d = descs[i];
-        // 16-byte row loads: aligned base and pitch, and the pitch must cover the last (possibly partial) group of 4 pixels
-        bool fused = p.fused_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0) &&
-                     (d.in_stride >= ((uint64_t)d.in_w * 4 + 15) / 16 * 16);
+        // TMA rows: the pitch must be a multiple of 16 bytes (any Bitmap::create_u8 buffer: 64-byte padded rows)
+        bool ring = p.hv_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0);
         const int ch = d.alpha_meaningful ? 4 : 3;
-        if (fused && !find_fused(p.av, p.sh, ch, b->nt)) fused = false;
         const bool upscale = p.out_h >= p.in_h && p.out_w >= p.in_w;
-        if (fused && !(p.tile_ok && upscale) && !fused_host_ready(p, b->nt)) fused = false;   // windows wider than a strip
+        if (ring && !(p.tile_ok && upscale) && !hv_host_ready(p, b->strip_cols)) ring = false;   // windows wider than the weight table
         // the ring kernel streams every source row once and wins whenever rows outnumber outputs (down-scales);
         // for up-scales / 1:1 the tile kernel does less work per source pixel
-        const bool prefer_tile = p.tile_ok && !b->force_generic && (!fused || upscale);
-        const int kind = prefer_tile ? tile_kind : (fused ? 1 : 0);
+        const bool prefer_tile = p.tile_ok && !b->force_generic && (!ring || upscale);
+        const int kind = prefer_tile ? 3 : (ring ? 1 : 0);
         const bool simple = d.compose == IFB200_REPLACE_SELF && !d.color_matrix;   // store epilogue without composite / matrix code
-        const int variant = kind == 3 ? ((d.linear ? 1 : 0) | ((ch == 4 ? d.compose : 0) << 1) | (d.color_matrix ? 8 : 0)) : 0;
+        // the ring kernel keeps ONE transfer table per CTA: jobs of different working spaces go to different launches
+        const int variant = kind == 3 ? ((d.linear ? 1 : 0) | ((ch == 4 ? d.compose : 0) << 1) | (d.color_matrix ? 8 : 0)) : kind == 1 ? (d.linear ? 1 : 0) : 0;
         Group* g = nullptr;
         for (auto& gg : groups) if (gg.plan == &p && gg.ch == ch && gg.kind == kind && gg.simple == simple && gg.variant == variant) { g = &gg; break; }
         if (!g) { groups.push_back(Group{&p, ch, kind, simple, variant, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
-    // job array -> device (pinned staging, stream ordered)
-    cudaEvent_t ev;
-    JobDev* hj = static_cast<JobDev*>(b->stage(n * sizeof(JobDev), &ev));
-    size_t pos = 0;
-    std::vector<size_t> gstart;
-    for (auto& g : groups) {
-        gstart.push_back(pos);
-        for (size_t i : g.idx) hj[pos++] = make_job(descs[i], g_t_lin_host, g_t_srgb_host);
+    // job array (+ the ring kernel's TMA descriptors, band tables and work counters) -> device (pinned staging, stream ordered)
+    struct GroupLayout { size_t jobs = 0, tmaps = 0, bands = 0, counters = 0; int nb = 0, grid = 0; std::vector<HvBandDev> bv; };
+    std::vector<GroupLayout> lay(groups.size());
+    size_t bytes = 0;
+    auto take = [&](size_t nbytes) { const size_t o = (bytes + 127) / 128 * 128; bytes = o + nbytes; return o; };
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group& g = groups[gi];
+        lay[gi].jobs = take(g.idx.size() * sizeof(JobDev));
+        if (g.kind == 1) {
+            Plan& p = *g.plan;
+            const HvTables& ht = *p.by_cols.at(b->strip_cols);
+            const HvEntry* he = find_hv(p.av, g.ch);
+            const size_t jxs = g.idx.size() * (size_t)ht.n_strips;
+            const int warps_all = b->sm_count * he->warps;
+            lay[gi].nb = hv_pick_bands(p, jxs, warps_all, b->min_items > 0 ? b->min_items : warps_all);
+            lay[gi].bv = hv_bands(p, lay[gi].nb);
+            lay[gi].nb = (int)lay[gi].bv.size();
+            const size_t items = jxs * lay[gi].nb;
+            lay[gi].grid = (int)std::min<size_t>((size_t)b->sm_count, (items + he->warps - 1) / he->warps);
+            lay[gi].tmaps = take(g.idx.size() * sizeof(HvTmap));
+            lay[gi].bands = take(lay[gi].bv.size() * sizeof(HvBandDev));
+            lay[gi].counters = take((size_t)ht.n_strips * sizeof(uint32_t));
+        }
     }
-    JobDev* dj = nullptr;
-    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dj), n * sizeof(JobDev), st));
-    CUDA_OK(cudaMemcpyAsync(dj, hj, n * sizeof(JobDev), cudaMemcpyHostToDevice, st));
+    cudaEvent_t ev;
+    uint8_t* hbuf = static_cast<uint8_t*>(b->stage(bytes, &ev));
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+        Group& g = groups[gi];
+        JobDev* hj = reinterpret_cast<JobDev*>(hbuf + lay[gi].jobs);
+        HvTmap* ht = g.kind == 1 ? reinterpret_cast<HvTmap*>(hbuf + lay[gi].tmaps) : nullptr;
+        size_t pos = 0;
+        for (size_t i : g.idx) {
+            hj[pos] = make_job(descs[i], g_t_lin_host, g_t_srgb_host);
+            if (ht) { uint32_t xoff = 0; ht[pos] = tmap_for(b, descs[i], &xoff); hj[pos].in_xoff = xoff; }
+            ++pos;
+        }
+        if (g.kind == 1) {
+            memcpy(hbuf + lay[gi].bands, lay[gi].bv.data(), lay[gi].bv.size() * sizeof(HvBandDev));
+            memset(hbuf + lay[gi].counters, 0, (size_t)g.plan->by_cols.at(b->strip_cols)->n_strips * sizeof(uint32_t));
+        }
+    }
+    uint8_t* dbuf = nullptr;
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dbuf), bytes, st));
+    AsyncFree dbuf_guard{dbuf, st};
+    CUDA_OK(cudaMemcpyAsync(dbuf, hbuf, bytes, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaEventRecord(ev, st));
 
     // many geometries: one small launch each -> fork onto the side streams (the jobs of one call are independent)
     const bool fork = groups.size() >= 4;
-    const int min_ctas = fork ? std::max(32, b->min_ctas / ifb200_batch::kSideStreams) : b->min_ctas;
     cudaStream_t const user_stream = st;
     if (fork) {
         CUDA_OK(cudaEventRecord(b->ev_fork, user_stream));
         for (auto& sd : b->side) CUDA_OK(cudaStreamWaitEvent(sd, b->ev_fork, 0));
     }
+    struct Join {                                   // the side streams always rejoin the caller's stream, also when a launch throws
+        ifb200_batch* b; cudaStream_t user; bool on;
+        ~Join() {
+            if (!on) return;
+            for (int k = 0; k < ifb200_batch::kSideStreams; ++k)
+                if (cudaEventRecord(b->ev_join[k], b->side[k]) == cudaSuccess) cudaStreamWaitEvent(user, b->ev_join[k], 0);
+        }
+    } join{b, user_stream, fork};
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         Group& g = groups[gi];
         Plan& p = *g.plan;
-        const JobDev* jobs = dj + gstart[gi];
+        const JobDev* jobs = reinterpret_cast<const JobDev*>(dbuf + lay[gi].jobs);
         const size_t nj = g.idx.size();
         st = fork ? b->side[gi % ifb200_batch::kSideStreams] : user_stream;
         if (g.kind == 3) {
@@ -688,10 +723,13 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             const bool linear = g.variant & 1;
             Tile2Fn fn = find_tile2(g.ch, linear, (g.variant >> 1) & 3, (g.variant & 8) != 0);
             const size_t smem = Tile2Smem::make(t.max_ir, t.max_ic, linear).total;
-            CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, 256, smem));
-            const uint64_t resident = (uint64_t)std::max(per_sm, 1) * b->sm_count;
+            int& per_sm = b->tile_occupancy[std::make_pair((const void*)fn, smem)];
+            if (per_sm == 0) {
+                CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, 256, smem));
+                per_sm = std::max(per_sm, 1);
+            }
+            const uint64_t resident = (uint64_t)per_sm * b->sm_count;
             for (size_t off = 0; off < nj; off += 65535) {
                 const size_t cnt = std::min<size_t>(65535, nj - off);
                 const uint64_t total = (uint64_t)cnt * t.tiles_x * t.tiles_y;
@@ -700,73 +738,49 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
                 b->launches++;
             }
             b->tile_jobs += nj;
-        } else if (g.kind == 2) {
-            const TilePlanDev& t = p.tile;
-            ensure_axes(b, st, p);
-            const size_t smem = ((size_t)t.max_ir + t.toh) * t.max_ic * sizeof(float4);
-            CUDA_OK(cudaFuncSetAttribute((const void*)fused_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            for (size_t off = 0; off < nj; off += 65535) {
-                const size_t cnt = std::min<size_t>(65535, nj - off);
-                dim3 grid((unsigned)(t.tiles_x * t.tiles_y), (unsigned)cnt);
-                fused_tile_kernel<<<grid, 256, smem, st>>>(jobs + off, b->tables, p.dv.view(*p.axes), p.dh.view(*p.axes), t);
-                CUDA_OK(cudaGetLastError());
-                b->launches++;
-            }
-            b->tile_jobs += nj;
         } else if (g.kind == 1) {
-            FusedVariantTables& ft = fused_tables(b, st, p, b->nt);
-            int nb = 1;
-            const size_t base = nj * ft.n_strips;
-            if (base < (size_t)min_ctas) nb = (int)std::min<size_t>((min_ctas + base - 1) / base, std::max<uint32_t>(1u, p.out_h / 8u));
-            nb = pick_bands(ft, nb);
-            FusedPlanDev pl{};
+            HvTables& ht = hv_tables(b, st, p, b->strip_cols);
+            const HvEntry* he = find_hv(p.av, g.ch);
+            HvPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
-            pl.n_strips = ft.n_strips; pl.n_bands = nb;
-            pl.vprog = ft.blob.at<uint32_t>(ft.o_vprog[0]); pl.strips = ft.blob.at<StripDev>(ft.o_strips);
-            pl.bands = ft.blob.at<BandDev>(ft.o_bands.at(nb));
-            pl.hw = ft.blob.at<float>(ft.o_hw); pl.hrd = ft.blob.at<uint32_t>(ft.o_hrd);
-            const FusedEntry* fe = find_fused(p.av, p.sh, g.ch, b->nt);
-            FusedFn fn = g.simple ? fe->fn_simple : fe->fn;
-            if (b->gather_ahead && (g.simple ? fe->fn_simple_ga : fe->fn_ga)) fn = g.simple ? fe->fn_simple_ga : fe->fn_ga;
-            const size_t smem = fe->smem;
-            CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            for (size_t off = 0; off < nj; off += 65535) {
-                const size_t cnt = std::min<size_t>(65535, nj - off);
-                dim3 grid((unsigned)(ft.n_strips * nb), (unsigned)cnt);
-                fn<<<grid, b->nt, smem, st>>>(jobs + off, b->tables, pl);
-                CUDA_OK(cudaGetLastError());
-                b->launches++;
+            pl.n_strips = ht.n_strips; pl.n_bands = lay[gi].nb;
+            pl.strips = ht.blob.at<HvStripDev>(ht.o_strips);
+            pl.bands = reinterpret_cast<const HvBandDev*>(dbuf + lay[gi].bands);
+            pl.hw = ht.blob.at<float>(ht.o_hw); pl.hdone = ht.blob.at<uint8_t>(ht.o_hdone);
+            pl.vw = ht.blob.at<float>(ht.o_vw); pl.vdone = ht.blob.at<uint8_t>(ht.o_vdone);
+            HvFn fn = g.simple ? he->fn_simple : he->fn;
+            const size_t smem = he->smem(b->smem_base_low16);
+            if (!b->hv_attr_set.count((const void*)fn)) {
+                CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                b->hv_attr_set.insert((const void*)fn);
             }
+            fn<<<(unsigned)lay[gi].grid, he->threads, smem, st>>>(jobs, reinterpret_cast<const HvTmap*>(dbuf + lay[gi].tmaps), b->tables, pl, (uint32_t)nj,
+                                                                  reinterpret_cast<uint32_t*>(dbuf + lay[gi].counters));
+            CUDA_OK(cudaGetLastError());
+            b->launches++;
             b->fused_jobs += nj;
         } else {
-            // generic pair; bound the float4 intermediate to ~1 GiB per chunk
-            const size_t per = (size_t)p.out_h * p.in_w * sizeof(float4);
+            // generic pair; the float4 intermediate [in_h][out_w] is bounded to ~1 GiB per chunk of jobs
+            const size_t per = (size_t)p.in_h * p.out_w * sizeof(float4);
             const size_t chunk = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nj, 65535), ((size_t)1 << 30) / std::max<size_t>(per, 1)));
             ensure_axes(b, st, p);
             float4* inter = nullptr;
             CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&inter), per * chunk, st));
+            AsyncFree inter_guard{inter, st};
             for (size_t off = 0; off < nj; off += chunk) {
                 const size_t cnt = std::min(chunk, nj - off);
-                dim3 gv((p.in_w + 127) / 128, p.out_h, (unsigned)cnt);
-                vpass_generic_kernel<<<gv, 128, 0, st>>>(jobs + off, b->tables, p.dv.view(*p.axes), p.in_w, p.out_h, inter);
+                dim3 gh((p.out_w + 127) / 128, std::min<uint32_t>(p.in_h, 65535u), (unsigned)cnt);
+                hpass_generic_kernel<<<gh, 128, 0, st>>>(jobs + off, b->tables, p.dh.view(*p.axes), p.in_h, p.out_w, inter);
                 CUDA_OK(cudaGetLastError());
-                dim3 gh((p.out_w + 127) / 128, p.out_h, (unsigned)cnt);
-                hpass_generic_kernel<<<gh, 128, 0, st>>>(jobs + off, b->tables, p.dh.view(*p.axes), p.in_w, p.out_w, p.out_h, inter);
+                dim3 gv((p.out_w + 127) / 128, std::min<uint32_t>(p.out_h, 65535u), (unsigned)cnt);
+                vpass_generic_kernel<<<gv, 128, 0, st>>>(jobs + off, b->tables, p.dv.view(*p.axes), p.in_h, p.out_w, p.out_h, inter);
                 CUDA_OK(cudaGetLastError());
                 b->launches += 2;
             }
-            CUDA_OK(cudaFreeAsync(inter, st));
             b->generic_jobs += nj;
         }
     }
     st = user_stream;
-    if (fork) {
-        for (int k = 0; k < ifb200_batch::kSideStreams; ++k) {
-            CUDA_OK(cudaEventRecord(b->ev_join[k], b->side[k]));
-            CUDA_OK(cudaStreamWaitEvent(st, b->ev_join[k], 0));
-        }
-    }
-    CUDA_OK(cudaFreeAsync(dj, st));
 }
 
 void color_matrix_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, const float* m, cudaStream_t st) {
@@ -950,7 +964,8 @@ ifb200_batch* create_batch(int device) {
     b->t_lin.upload(tl); b->t_srgb.upload(ts); b->lut16k.upload(lut);
     b->tables = Tables{b->t_lin.p, b->t_srgb.p, b->lut16k.p};
     CUDA_OK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
-    {   // the ring kernel folds the shared-window offset of dynamic shared memory into its LUT gather: verify it once
+    {   // the ring kernel lays its shared memory out around a 64 KB-aligned (in the shared window) lookup table: learn where
+        // dynamic shared memory starts in the window, and check that every variant then fits
         DevVec<uint32_t> probe; probe.upload(std::vector<uint32_t>(1, 0xffffffffu));
         CUDA_OK(cudaFuncSetAttribute((const void*)smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         smem_base_probe_kernel<<<1, 32, 100 * 1024, b->own_stream>>>(probe.p);
@@ -958,7 +973,21 @@ ifb200_batch* create_batch(int device) {
         uint32_t got = 0;
         CUDA_OK(cudaMemcpyAsync(&got, probe.p, 4, cudaMemcpyDeviceToHost, b->own_stream));
         CUDA_OK(cudaStreamSynchronize(b->own_stream));
-        b->ring_ok = (got & 0xffffu) == kSmemWindowBase;
+        b->smem_base_low16 = got & 0xffffu;
+        int optin = 0;
+        CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        for (const auto& e : kHv)
+            if (e.smem(b->smem_base_low16) > (uint32_t)optin) {
+                b->ring_ok = false;
+                b->ring_reason = "ring kernel needs " + std::to_string(e.smem(b->smem_base_low16)) + " bytes of shared memory per CTA, the device offers " + std::to_string(optin);
+            }
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            b->ring_ok = false; b->ring_reason = "cuTensorMapEncodeTiled is not available from this driver";
+        }
+        b->tmap_encode = reinterpret_cast<TmapEncodeFn>(fn);
     }
     return b.release();
 }
@@ -1055,13 +1084,13 @@ int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, 
         auto worker = [&](int me) {
             try {
                 for (size_t i; (i = next.fetch_add(1)) < n;) {
-                    auto p = ifb200_batch::build_plan_host(descs[i], 256);
+                    auto p = ifb200_batch::build_plan_host(descs[i], 128);
                     uint64_t b = 0;
-                    for (auto& kv : p->by_nt) b += kv.second->blob.host.size();
+                    for (auto& kv : p->by_cols) b += kv.second->blob.host.size();
                     bytes += b;
                     if (table_hash) {
                         uint64_t h = 14695981039346656037ull;
-                        for (auto& kv : p->by_nt) h = fnv(h, kv.second->blob.host.data(), kv.second->blob.host.size());
+                        for (auto& kv : p->by_cols) h = fnv(h, kv.second->blob.host.data(), kv.second->blob.host.size());
                         for (const ifb::AxisWeights* a : {&p->wv, &p->wh}) {
                             h = fnv(h, a->left.data(), a->left.size() * 4); h = fnv(h, a->right.data(), a->right.size() * 4);
                             h = fnv(h, a->offset.data(), a->offset.size() * 4); h = fnv(h, a->w.data(), a->w.size() * 4);
@@ -1081,6 +1110,29 @@ int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, 
         if (seconds) *seconds = dt;
         if (table_bytes) *table_bytes = bytes.load();
         if (table_hash) { uint64_t h = 14695981039346656037ull; *table_hash = fnv(h, hashes.data(), hashes.size() * 8); }
+    });
+}
+
+// The ring kernel's host tables for one geometry (tests: tests/cpu_emu runs the kernel's source over them on the CPU; no CUDA call).
+int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_bands, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
+                          char* err, size_t err_cap) {
+    return guarded(err, err_cap, [&] {
+        if (!d || !info) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (strip_cols < 32 || strip_cols > 128 || strip_cols % 32 || n_bands < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band count");
+        memset(info, 0, sizeof *info);
+        auto p = ifb200_batch::build_plan_host(*d, strip_cols);
+        if (!p->hv_ok || !p->by_cols.count(strip_cols)) return;          // info->ok stays 0: not a ring-kernel geometry
+        HvTables& ht = *p->by_cols.at(strip_cols);
+        const std::vector<HvBandDev> bands = hv_bands(*p, n_bands);
+        const size_t o_bands = (ht.blob.host.size() + 255) / 256 * 256;
+        info->ok = 1; info->av = p->av; info->n_strips = ht.n_strips; info->n_bands = (int32_t)bands.size();
+        info->avp = p->av == 4 ? 4 : 8; info->cap_px = 16384 / (info->avp * 4);
+        info->o_strips = ht.o_strips; info->o_hw = ht.o_hw; info->o_hdone = ht.o_hdone; info->o_vw = ht.o_vw; info->o_vdone = ht.o_vdone;
+        info->o_bands = o_bands; info->total = o_bands + bands.size() * sizeof(HvBandDev);
+        if (!buf) return;
+        if (cap < info->total) IFB_THROW(IFB200_ERR_CAPACITY, "buffer of %zu bytes, %llu needed", cap, (unsigned long long)info->total);
+        memcpy(buf, ht.blob.host.data(), ht.blob.host.size());
+        memcpy(buf + o_bands, bands.data(), bands.size() * sizeof(HvBandDev));
     });
 }
 
@@ -1171,16 +1223,12 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     std::lock_guard<std::mutex> lk(b->mu);
     switch (option) {
     case IFB200_OPT_FORCE_GENERIC: b->force_generic = value != 0; return IFB200_OK;
-    case IFB200_OPT_THREADS_PER_CTA:
-        if (value != 128 && value != 256) return IFB200_ERR_INVALID_ARGUMENT;
-        b->nt = (int)value; return IFB200_OK;
-    case IFB200_OPT_MIN_CTAS:
-        if (value < 1 || value > (1 << 20)) return IFB200_ERR_INVALID_ARGUMENT;
-        b->min_ctas = (int)value; return IFB200_OK;
-    case IFB200_OPT_GATHER_AHEAD: b->gather_ahead = value != 0; return IFB200_OK;
-    case IFB200_OPT_TILE_KERNEL:
-        if (value < 0 || value > 2) return IFB200_ERR_INVALID_ARGUMENT;
-        b->tile_variant = (int)value; return IFB200_OK;
+    case IFB200_OPT_STRIP_COLUMNS:
+        if (value < 32 || value > 128 || value % 32) return IFB200_ERR_INVALID_ARGUMENT;
+        b->strip_cols = (int)value; return IFB200_OK;
+    case IFB200_OPT_MIN_ITEMS:
+        if (value < 0 || value > (1 << 24)) return IFB200_ERR_INVALID_ARGUMENT;
+        b->min_items = (int)value; return IFB200_OK;
     default: return IFB200_ERR_INVALID_ARGUMENT;
     }
 }
@@ -1195,6 +1243,11 @@ uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b) { return b ? b->lau
 uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b) { return b ? b->fused_jobs : 0; }
 uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b) { return b ? b->generic_jobs : 0; }
 uint64_t ifb200_batch_tile_jobs(const ifb200_batch* b) { return b ? b->tile_jobs : 0; }
+int ifb200_batch_ring_status(const ifb200_batch* b, char* why, size_t cap) {
+    if (!b) return 0;
+    put_err(why, cap, b->ring_ok ? std::string() : b->ring_reason);
+    return b->ring_ok ? 1 : 0;
+}
 
 // ---- drop-in calls with HOST buffers -----------------------------------------------------------
 namespace {

@@ -1,0 +1,463 @@
+// ifb_hv_kernel.cuh -- the hot kernel of the resample path (product code, sm_100a); included by ifb_kernels.cuh inside namespace ifbk.
+//
+// Stands in for zenresize's StreamingResize behind graphics/scaling.rs:93-251: rows stream in, every row is filtered
+// horizontally as it arrives, output rows are emitted as soon as their vertical window is complete.  Down-scales (and 1:1)
+// whose contribution windows keep at most AV <= 6 outputs open per source sample on both axes run here.
+//
+// Decomposition: ONE WARP = one work item = (job, strip of <= NG*32 output columns, band of output rows), and inside it
+// LANE = SOURCE ROW.  A warp walks its band 32 source rows at a time ("row block"); for every row block it streams the strip's
+// source columns left to right:
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) stages boxes of 16 pixels x 32 rows into the warp's own shared-memory ring
+//     (kStages deep, one mbarrier per stage; the same warp issues, waits and consumes: no other synchronisation exists in
+//     this kernel).  The 64-byte swizzle makes the per-lane 16-byte reads of "my row" bank-conflict free.
+//   * H pass: every lane converts its row's pixel through the lane-replicated LUT (one PRMT + one conflict-free LDS per
+//     channel) and multiply-adds it into a ring of AV accumulators: output column X owns slot X mod AV while its window is open.
+//     The weights of a source column are the same for all lanes: one broadcast LDS.128 of a table the CTA keeps in shared memory.
+//     The whole horizontal reduction (7.5 : 1 for 4K -> 512) happens in registers with no exchange between threads.
+//   * When a column completes, its CH values go to the warp's exchange buffer [column][channel][row]; after 32 columns
+//     (a "group") the warp turns around: LANE = OUTPUT COLUMN, and the 32 H-filtered rows of the block are multiply-added, in
+//     row order, into the group's ring of AV vertical accumulators (output row Y owns slot Y mod AV).  A completed output row
+//     goes through the store epilogue and is written as one coalesced 128-byte segment.
+// Every source pixel is read from HBM once (plus strip/band halos), converted once; nothing but source and destination
+// pixels touches HBM.  Arithmetic: the H chain ascends over source columns from +0, the V chain over source rows from +0 --
+// exactly the order of the specification; a slot only ever sees zero weights outside its window, and fmaf(+0, v, acc) == acc.
+//
+// Shared memory (one CTA per SM, kWarps warps):
+//   LUT block, 64 KB, placed so that its shared-window address is a multiple of 64 KB (the layout adapts to wherever the
+//   driver puts dynamic shared memory): row v (256 B): bytes 0..127 = T[v] for the 32 lanes, so the window address of a lookup
+//   is LUT | v << 8 | lane << 2 -- one PRMT, bank-conflict free for any image content.  Bytes 128..255 of the rows ("holes"):
+//   holes 0..127 = the 16 KB linear->sRGB table of the store epilogue, holes 128..255 = the strip's H weights (16 KB).
+//   Around it, per warp: stage ring, exchange buffer, mbarriers.
+#pragma once
+
+#ifndef IFB_HV_EMU
+#include <cuda.h>          // CUtensorMap (type only; the driver entry point is looked up at run time by the engine)
+#endif
+
+struct HvStripDev { int X0, X1, Xf, hslot0, k0, nst, pad0, pad1; };   // columns [X0,X1); first completing column Xf (<= X0) and its slot;
+                                                                      // pixel stream = source columns k0 .. k0 + 16*nst - 1
+struct HvBandDev  { int Y0, Y1, Yf, vslot0, j0, nrows, pad0, pad1; }; // rows [Y0,Y1); first completing row Yf and its slot; source rows j0 .. j0+nrows-1
+struct HvPlanDev {
+    uint32_t in_w, in_h, out_w, out_h;
+    int n_strips, n_bands;
+    const HvStripDev* strips;
+    const HvBandDev* bands;
+    const float* hw;          // [n_strips][cap px][AVP]: weight of the open output column in each ring slot, pixel-stream order
+    const uint8_t* hdone;     // [n_strips][cap px + 32]: output columns completing after this pixel
+    const float* vw;          // [in_h][AVP]
+    const uint8_t* vdone;     // [in_h + 32]
+};
+struct alignas(64) HvTmap { unsigned char bytes[128]; };              // CUtensorMap of one job's input bitmap (u32 pixels, box 16 x 32, SWIZZLE_64B)
+
+template <int AV, int CH> struct HvCfg {
+    static_assert(AV == 4 || AV == 6, "ring depth");
+    static constexpr int kAvp = AV == 4 ? 4 : 8;                      // floats per weight record
+    static constexpr int kCapPx = 16384 / (kAvp * 4);                 // pixels of H weights that fit in the holes
+    static constexpr int kNG = AV == 4 ? 4 : 2;                       // column groups per strip
+    static constexpr int kWarps = CH == 3 ? 8 : 6;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kStages = 3;
+    static constexpr int kStageBytes = 32 * 64;                       // 32 rows x 16 pixels
+    static constexpr int kXPitch = CH * 32 + 1;                       // words per column of the exchange buffer (odd: conflict-free both ways)
+    static constexpr int kXbufBytes = 32 * kXPitch * 4;
+    static constexpr int kWarpBytes = (kStages * kStageBytes + kXbufBytes + 64 + 1023) / 1024 * 1024;
+    // dynamic shared memory for a given low half of the shared-window base (see layout in the kernel)
+    static constexpr uint32_t total_bytes(uint32_t sb_low16) {
+        const uint32_t lut_off = (0x10000u - sb_low16) & 0xffffu;
+        const uint32_t a0_off = ((sb_low16 + 1023u) & ~1023u) - sb_low16;
+        const uint32_t nA = lut_off > a0_off ? (lut_off - a0_off) / kWarpBytes : 0u;
+        const uint32_t nB = nA >= (uint32_t)kWarps ? 0u : (uint32_t)kWarps - nA;
+        return lut_off + 65536u + nB * kWarpBytes;
+    }
+};
+
+// ---------------------------------------------------------------- primitives (tests/cpu_emu provides its own under IFB_HV_EMU)
+#ifndef IFB_HV_EMU
+namespace hv {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_lut(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }          // tables: read-only after setup
+__device__ __forceinline__ uint32_t lds_lut_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_w4(uint32_t a) {
+    float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ float2 lds_w2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32x4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ void warp_sync() { __syncwarp(); }
+__device__ __forceinline__ void cta_sync() { __syncthreads(); }
+__device__ __forceinline__ uint32_t atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
+__device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n"
+                 "IFB_HV_WAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@!p bra IFB_HV_WAIT_%=;\n\t}" ::"r"(addr), "r"(parity) : "memory");
+}
+// one box of 16 pixels x 32 rows at pixel (x, y) of the job's bitmap -> shared memory, completion counted on the mbarrier
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const HvTmap* tm, int x, int y, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(mbar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_box(const HvTmap* tm, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(x), "r"(y) : "memory");
+}
+template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+}  // namespace hv
+#define IFB_HV_DYNAMIC_SMEM(name_) extern __shared__ __align__(1024) unsigned char name_[]
+#endif
+
+#ifndef IFB_HV_PREFETCH_AHEAD
+#define IFB_HV_PREFETCH_AHEAD 8        // L2 prefetch distance in stages (0 = off)
+#endif
+
+// Where a CTA's dynamic shared memory starts in the shared window (the engine sizes the ring kernel's layout with it).
+__global__ void smem_base_probe_kernel(uint32_t* out) {
+    IFB_HV_DYNAMIC_SMEM(probe_smem);
+    if (threadIdx.x == 0) *out = hv::smem_u32(probe_smem);
+}
+
+// Store epilogue with the tables in shared memory: same operations, same order as finish_pixel().
+//   enc(v)  floatspace_to_srgb (color.rs:59-69): linear -> 16 K table in the LUT holes; sRGB space -> uchar_clamp_ff(255 v)
+//   tl(b)   byte_to_float of the working space = the lane's own copy in the replicated LUT
+template <bool SIMPLE>
+__device__ __forceinline__ uint32_t hv_finish_pixel(float b, float g, float r, float a, const uint32_t flags, const JobDev& job,
+                                                    const uint32_t lut, const uint32_t lut_lane, const uint8_t* dst) {
+    const bool linear = flags & JF_LINEAR;
+    auto enc = [&](float v) -> uint32_t {
+        if (linear) {                                          // lut.rs:4-8
+            float s = __fmul_rn(v, 16383.0f);
+            s = fminf(fmaxf(s, 0.0f), 16383.0f);
+            const uint32_t i = (uint32_t)(int)s;
+            return hv::lds_lut_u8(lut + 128u + i + (i & 0x3f80u));
+        }
+        return uchar_clamp_ff(__fmul_rn(255.0f, v));
+    };
+    const bool am = flags & JF_ALPHA;
+    const uint32_t compose = SIMPLE ? 0u : (flags >> JF_COMPOSE_SHIFT) & 3u;
+    uint32_t ob, og, orr, oa;
+    if (compose == 1u) {                                   // BlendWithSelf: scaling.rs:254-287
+        if (a > 0.994f || !am) {
+            ob = enc(b); og = enc(g); orr = enc(r); oa = 255u;
+        } else {
+            const uint32_t d = *reinterpret_cast<const uint32_t*>(dst);
+            const float da = (float)(int)(d >> 24);
+            const float dc = __fmul_rn(__fsub_rn(1.0f, a), __fadd_rn(__fmul_rn(1.0f / 255.0f, da), 0.0f));
+            const float fa = __fadd_rn(a, dc);
+            ob = enc(__fdiv_rn(__fadd_rn(b, __fmul_rn(dc, hv::lds_lut(lut_lane + ((d & 0xffu) << 8)))), fa));
+            og = enc(__fdiv_rn(__fadd_rn(g, __fmul_rn(dc, hv::lds_lut(lut_lane + (((d >> 8) & 0xffu) << 8)))), fa));
+            orr = enc(__fdiv_rn(__fadd_rn(r, __fmul_rn(dc, hv::lds_lut(lut_lane + (((d >> 16) & 0xffu) << 8)))), fa));
+            oa = uchar_clamp_ff(__fmul_rn(fa, 255.0f));
+        }
+    } else if (!am) {                                      // scaling.rs:227-232
+        ob = enc(b); og = enc(g); orr = enc(r); oa = 255u;
+    } else {
+        if (compose == 2u) {                               // BlendWithMatte (scaling.rs:119-148)
+            const float t = __fsub_rn(1.0f, a);
+            b = __fadd_rn(b, __fmul_rn(t, job.matte[0]));
+            g = __fadd_rn(g, __fmul_rn(t, job.matte[1]));
+            r = __fadd_rn(r, __fmul_rn(t, job.matte[2]));
+            a = __fadd_rn(a, __fmul_rn(t, job.matte[3]));
+        }
+        if (a > 0.0f) { b = __fdiv_rn(b, a); g = __fdiv_rn(g, a); r = __fdiv_rn(r, a); }
+        ob = enc(b); og = enc(g); orr = enc(r);
+        oa = uchar_clamp_ff(__fmul_rn(a, 255.0f));
+    }
+    if (!SIMPLE && (flags & JF_CM)) {                      // color_matrix.rs:5-28, on sRGB bytes
+        const float fr = (float)orr, fg = (float)og, fb = (float)ob, fa = (float)oa;
+        const float* m = job.cm;
+        auto row = [&](int c) {
+            float s = __fmul_rn(m[c * 5 + 0], fr);
+            s = __fadd_rn(s, __fmul_rn(m[c * 5 + 1], fg));
+            s = __fadd_rn(s, __fmul_rn(m[c * 5 + 2], fb));
+            s = __fadd_rn(s, __fmul_rn(m[c * 5 + 3], fa));
+            return uchar_clamp_ff(__fadd_rn(s, m[c * 5 + 4]));
+        };
+        orr = row(0); og = row(1); ob = row(2); oa = row(3);
+    }
+    return ob | (og << 8) | (orr << 16) | (oa << 24);
+}
+
+template <int AV, int CH, bool SIMPLE>
+__global__ void __launch_bounds__(HvCfg<AV, CH>::kThreads, 1)
+hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps, Tables tb, HvPlanDev pl, uint32_t n_jobs,
+               uint32_t* __restrict__ counters) {
+    using C = HvCfg<AV, CH>;
+    constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages;
+    IFB_HV_DYNAMIC_SMEM(hv_smem);
+    const uint32_t sb = hv::smem_u32(hv_smem);
+    const uint32_t lut = sb + ((0x10000u - (sb & 0xffffu)) & 0xffffu);     // window address of the LUT block: low 16 bits are zero
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    uint32_t wb;                                                           // this warp's block: stages, exchange buffer, mbarriers
+    {
+        const uint32_t a0 = (sb + 1023u) & ~1023u;
+        const uint32_t nA = lut > a0 ? (lut - a0) / (uint32_t)C::kWarpBytes : 0u;
+        wb = (uint32_t)warp < nA ? a0 + (uint32_t)warp * C::kWarpBytes : lut + 65536u + ((uint32_t)warp - nA) * C::kWarpBytes;
+    }
+    const uint32_t xb = wb + S * C::kStageBytes;
+    const uint32_t mb = xb + C::kXbufBytes;
+    const uint32_t flags0 = jobs[0].flags;                                 // working space and channel count are the same for all jobs of a launch
+
+    // ---- tables: forward LUT replicated for the 32 lanes; linear->sRGB table into holes 0..127
+    {
+        const float* __restrict__ T = (flags0 & JF_LINEAR) ? tb.t_lin : tb.t_srgb;
+        for (int i = t; i < 256 * 32; i += C::kThreads) hv::sts_f32(lut + ((uint32_t)(i >> 5) << 8) + ((uint32_t)(i & 31) << 2), hv::ldg(T + (i >> 5)));
+        const uint32_t* __restrict__ r32 = reinterpret_cast<const uint32_t*>(tb.lut16k);
+        for (int i = t; i < 4096; i += C::kThreads) hv::sts_u32(lut + 128u + (uint32_t)(i * 4) + ((uint32_t)(i * 4) & 0x3f80u), hv::ldg(r32 + i));
+    }
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) hv::mbar_init(mb + 8u * s, 1u);
+        hv::mbar_init_fence();
+    }
+    uint32_t par = 0;                                                      // bit s: parity the next wait on stage s expects
+
+    const uint32_t lut_lane = lut + (uint32_t)lane * 4u;
+    const uint32_t lane4 = ((uint32_t)lane * 4u) | ((lut >> 16) << 8);     // PRMT operand: byte 0 = lane*4, bytes 1..2 = window bits 16..31
+    const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;                // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3
+    const uint32_t my_row = (uint32_t)lane * 64u;
+    const uint32_t n_items = n_jobs * (uint32_t)pl.n_bands;
+    const uint32_t lutw = lut + 128u * 256u + 128u;                        // hole 128: the strip's H weights
+
+    for (int sv = 0; sv < pl.n_strips; ++sv) {
+        const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
+        const HvStripDev sd = pl.strips[s];
+        hv::cta_sync();                                                    // every warp is done with the previous strip's weights (first time: tables filled)
+        {   // H weights of the strip: 16-byte units u -> hole 128 + u/8, offset (u%8)*16
+            const float4* __restrict__ src = reinterpret_cast<const float4*>(pl.hw + (size_t)s * C::kCapPx * AVP);
+            const int n16 = sd.nst * 16 * AVP / 4;
+            for (int u = t; u < n16; u += C::kThreads) hv::sts_f32x4(lutw + ((uint32_t)(u >> 3) << 8) + ((uint32_t)(u & 7) << 4), hv::ldg(src + u));
+        }
+        hv::cta_sync();
+        const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 32);
+        const uint32_t ncols = (uint32_t)(sd.X1 - sd.X0);
+
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = hv::atomic_inc(counters + s);
+            item = hv::bcast0(item);
+            if (item >= n_items) break;
+            const uint32_t job_i = item / (uint32_t)pl.n_bands, band_i = item - job_i * (uint32_t)pl.n_bands;
+            const JobDev& job = jobs[job_i];
+            const HvTmap* tm = tmaps + job_i;
+            const HvBandDev bd = pl.bands[band_i];
+            const uint32_t flags = job.flags;
+            const int nrb = (bd.nrows + 31) >> 5;
+            const int x_origin = sd.k0 + (int)job.in_xoff;
+
+            // ---- TMA pipeline state: stages are numbered row block by row block
+            const int total_stages = nrb * sd.nst;
+            int is_n = 0, is_x = 0, is_y = 0, is_s = 0;                    // next stage to issue: index, stage within row block, row block, ring slot
+            auto issue = [&]() {
+                hv::warp_sync();                                           // every lane has read what the refilled slot held
+                if (lane == 0) {
+                    const uint32_t bar = mb + 8u * (uint32_t)is_s;
+                    hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
+                    hv::tma_load_box(wb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bd.j0 + is_y * 32, bar);
+                }
+                ++is_n; is_s = is_s + 1 == S ? 0 : is_s + 1;
+                if (++is_x == sd.nst) { is_x = 0; ++is_y; }
+            };
+#if IFB_HV_PREFETCH_AHEAD > 0
+            int pf_n = 0, pf_x = 0, pf_y = 0;
+            auto prefetch = [&]() {
+                if (lane == 0) hv::tma_prefetch_box(tm, x_origin + pf_x * 16, bd.j0 + pf_y * 32);
+                ++pf_n;
+                if (++pf_x == sd.nst) { pf_x = 0; ++pf_y; }
+            };
+            for (int i = 0; i < IFB_HV_PREFETCH_AHEAD && pf_n < total_stages; ++i) prefetch();
+#endif
+            for (int i = 0; i < S - 1 && is_n < total_stages; ++i) issue();
+            int cs_s = 0;                                                  // ring slot of the stage being consumed
+
+            float2 accV[NG][CH][NP];
+#pragma unroll
+            for (int gq = 0; gq < NG; ++gq)
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) accV[gq][c][q] = make_float2(0.0f, 0.0f);
+            int Yc = bd.Yf, vslot = bd.vslot0;                             // next output row to complete at the start of the row block, and its slot
+            uint8_t* const out_col = job.out + (size_t)(sd.X0 + lane) * 4;
+            const size_t out_stride = job.out_stride;
+
+            for (int rb = 0; rb < nrb; ++rb) {
+                const int row0 = bd.j0 + rb * 32;
+                const int nr = min(32, bd.nrows - rb * 32);
+                uint32_t VM1, VM2, vtot;
+                {
+                    const uint32_t vd = lane < nr ? (uint32_t)hv::ldg(pl.vdone + row0 + lane) : 0u;
+                    VM1 = hv::ballot(vd >= 1u); VM2 = hv::ballot(vd >= 2u); vtot = hv::warp_sum(vd);
+                }
+                float2 accH[CH][NP];
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) accH[c][q] = make_float2(0.0f, 0.0f);
+                int Xc = sd.Xf, hslot = sd.hslot0;
+                uint32_t colbuf = 0, grp = 0;
+                uint32_t wptr = xb + (uint32_t)lane * 4u;                  // where the next completed column goes
+                uint32_t HM1 = 0, HM2 = 0;
+
+                // first stage of the row block
+                if (is_n < total_stages) issue();
+#if IFB_HV_PREFETCH_AHEAD > 0
+                if (pf_n < total_stages) prefetch();
+#endif
+                hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                par ^= 1u << cs_s;
+                uint32_t sbase = wb + (uint32_t)cs_s * C::kStageBytes + my_row;
+                uint4 raw = hv::lds_u32x4(sbase + swz);                    // chunk 0 (physical chunk = 0 ^ swizzle)
+
+                const int nchunks = sd.nst * 4;
+                for (int cc = 0; cc < nchunks; ++cc) {
+                    // ---- completion masks of the next 32 pixels
+                    if ((cc & 7) == 0) {
+                        const uint32_t hd = (uint32_t)hv::ldg(hdone + cc * 4 + lane);
+                        HM1 = hv::ballot(hd >= 1u); HM2 = hv::ballot(hd >= 2u);
+                    }
+                    // ---- sRGB bytes -> working floats of the chunk's four pixels: window address = LUT | byte << 8 | lane << 2
+                    float p[4][CH];
+                    {
+                        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t v = w4[i];
+                            p[i][0] = hv::lds_lut(hv::prmt(v, lane4, 0x6504));
+                            p[i][1] = hv::lds_lut(hv::prmt(v, lane4, 0x6514));
+                            p[i][2] = hv::lds_lut(hv::prmt(v, lane4, 0x6524));
+                            if (CH == 4) {
+                                // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
+                                const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
+                                p[i][0] = __fmul_rn(p[i][0], af); p[i][1] = __fmul_rn(p[i][1], af); p[i][2] = __fmul_rn(p[i][2], af);
+                                p[i][CH - 1] = af;
+                            }
+                        }
+                    }
+                    // ---- weights of the four source columns, by ring slot (broadcast reads)
+                    float2 wq[4][NP];
+                    {
+                        const uint32_t wa = AV == 4 ? lutw + ((uint32_t)(cc >> 1) << 8) + ((uint32_t)(cc & 1) << 6) : lutw + ((uint32_t)cc << 8);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 q4 = hv::lds_w4(wa + (uint32_t)i * (AVP * 4));
+                            wq[i][0] = make_float2(q4.x, q4.y); wq[i][1] = make_float2(q4.z, q4.w);
+                            if (AV == 6) wq[i][NP - 1] = hv::lds_w2(wa + (uint32_t)i * (AVP * 4) + 16u);
+                        }
+                    }
+                    // ---- the next chunk's pixels: requested now, used one iteration later
+                    if (cc + 1 < nchunks) {
+                        if (((cc + 1) & 3) == 0) {                         // it starts a new stage
+                            cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
+                            if (is_n < total_stages) issue();              // refills the slot consumed two stages ago (its reads are long done)
+#if IFB_HV_PREFETCH_AHEAD > 0
+                            if (pf_n < total_stages) prefetch();
+#endif
+                            hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                            par ^= 1u << cs_s;
+                            sbase = wb + (uint32_t)cs_s * C::kStageBytes + my_row;
+                        }
+                        raw = hv::lds_u32x4(sbase + ((((uint32_t)(cc + 1) & 3u) << 4) ^ swz));
+                    } else if (rb + 1 < nrb) {
+                        cs_s = cs_s + 1 == S ? 0 : cs_s + 1;               // the next row block's first stage is waited for at its top
+                    }
+                    // ---- multiply-adds, pixel by pixel, re-entered after every completion
+                    const uint32_t nib = (HM1 >> ((cc & 7) * 4)) & 15u, nib2 = (HM2 >> ((cc & 7) * 4)) & 15u;
+                    uint32_t start = 0;
+                    do {
+                        const uint32_t m = nib >> start;
+                        const uint32_t stop = m ? start + (uint32_t)__ffs((int)m) : 4u;     // pixels [start, stop) run, then the columns ending at stop-1 complete
+#define IFB_HV_PX(I_) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { const float2 vv = make_float2(p[I_][c], p[I_][c]); \
+                        _Pragma("unroll") for (int q = 0; q < NP; ++q) accH[c][q] = hv::ffma2(wq[I_][q], vv, accH[c][q]); } }
+                        switch (start) {
+                        case 0: IFB_HV_PX(0) if (stop == 1u) break;
+                        case 1: IFB_HV_PX(1) if (stop == 2u) break;
+                        case 2: IFB_HV_PX(2) if (stop == 3u) break;
+                        default: IFB_HV_PX(3)
+                        }
+#undef IFB_HV_PX
+                        if (m) {
+                            uint32_t n_done = 1u;
+                            if ((nib2 >> (stop - 1u)) & 1u) n_done = (uint32_t)hv::ldg(hdone + cc * 4 + (int)stop - 1);
+                            for (uint32_t e = 0; e < n_done; ++e) {
+                                // ---- output column Xc is complete: park it (if it belongs to the strip) and free its slot
+                                const bool keep = (uint32_t)(Xc - sd.X0) < ncols;
+                                switch (hslot) {
+#define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
+                                    float& a_ = (S_ & 1) ? accH[c][(S_ % AV) / 2].y : accH[c][(S_ % AV) / 2].x; \
+                                    if (keep) hv::sts_f32(wptr + (uint32_t)c * 128u, a_); a_ = 0.0f; } } break;
+                                IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5)
+#undef IFB_HV_SLOT
+                                default: break;
+                                }
+                                if (keep) {
+                                    wptr += (uint32_t)C::kXPitch * 4u; ++colbuf;
+                                    if (colbuf == 32u || Xc == sd.X1 - 1) {
+                                        // ---- V pass of the group: lane = output column sd.X0 + 32*grp + lane
+                                        hv::warp_sync();
+                                        const uint32_t xr = xb + (uint32_t)lane * ((uint32_t)C::kXPitch * 4u);
+                                        const bool col_live = (uint32_t)lane < colbuf;
+                                        uint8_t* const out_px = out_col + (size_t)grp * 128u;
+#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { \
+    int Yl = Yc, vs = vslot; \
+    for (int r = 0; r < nr; ++r) { \
+        float2 wv[NP]; \
+        { const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(pl.vw + (size_t)(row0 + r) * AVP)); \
+          wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w); \
+          if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(pl.vw + (size_t)(row0 + r) * AVP + 4)); } \
+        _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
+            const float x_ = hv::lds_f32(xr + (uint32_t)c * 128u + (uint32_t)r * 4u); const float2 vv = make_float2(x_, x_); \
+            _Pragma("unroll") for (int q = 0; q < NP; ++q) accV[(G_) % NG][c][q] = hv::ffma2(wv[q], vv, accV[(G_) % NG][c][q]); } \
+        if ((VM1 >> r) & 1u) { \
+            uint32_t nv = 1u; if ((VM2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r); \
+            for (uint32_t e2 = 0; e2 < nv; ++e2) { \
+                float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f}; \
+                switch (vs) { \
+                IFB_HV_VSLOT(G_, 0) IFB_HV_VSLOT(G_, 1) IFB_HV_VSLOT(G_, 2) IFB_HV_VSLOT(G_, 3) IFB_HV_VSLOT(G_, 4) IFB_HV_VSLOT(G_, 5) \
+                default: break; } \
+                if (Yl >= bd.Y0 && Yl < bd.Y1 && col_live) { \
+                    uint8_t* dst = out_px + (size_t)Yl * out_stride; \
+                    *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst); } \
+                ++Yl; vs = vs + 1 == AV ? 0 : vs + 1; } } } } break;
+#define IFB_HV_VSLOT(G_, S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
+    float& a_ = (S_ & 1) ? accV[(G_) % NG][c][(S_ % AV) / 2].y : accV[(G_) % NG][c][(S_ % AV) / 2].x; f_[c] = a_; a_ = 0.0f; } } break;
+                                        switch (grp) {
+                                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3)
+                                        default: break;
+                                        }
+#undef IFB_HV_VGROUP
+#undef IFB_HV_VSLOT
+                                        hv::warp_sync();
+                                        ++grp; colbuf = 0; wptr = xb + (uint32_t)lane * 4u;
+                                    }
+                                }
+                                ++Xc; hslot = hslot + 1 == AV ? 0 : hslot + 1;
+                            }
+                        }
+                        start = stop;
+                    } while (start < 4u);
+                }
+                // every group of the row block has seen the same rows: commit the vertical position
+                Yc += (int)vtot;
+                vslot = (int)(((uint32_t)vslot + vtot) % (uint32_t)AV);
+            }
+        }
+    }
+}

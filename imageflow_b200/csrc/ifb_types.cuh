@@ -6,10 +6,21 @@ struct JobDev {                 // one scale_and_render call
     uint8_t* out;               // canvas origin already offset to (x, y)
     uint32_t in_stride, out_stride;
     uint32_t flags;             // bit0 linear, bit1 alpha_meaningful, bits2-3 compose, bit4 has colour matrix
+    uint32_t in_xoff;           // ring kernel: pixels between the 16-byte aligned base of its TMA descriptor and `in` (0..3)
     float matte[4];             // premultiplied working-space matte (B,G,R,A positional; scaling.rs:141-143)
     float cm[20];               // cm[c*5 + k]: output channel c (0=r,1=g,2=b,3=a) = sum_k cm[c*5+k]*{r,g,b,a,1} (bias already *255)
 };
 enum : uint32_t { JF_LINEAR = 1u, JF_ALPHA = 2u, JF_COMPOSE_SHIFT = 2, JF_CM = 16u };
+
+// ---------------------------------------------------------------- scalar helper shared by every store epilogue
+// color.rs:101-108 uchar_clamp_ff: trunc(x + 0.5) computed exactly, saturated to [0,255], NaN -> 0
+__device__ __forceinline__ uint32_t uchar_clamp_ff(float x) {
+    if (!(x > 0.0f)) return 0u;
+    if (x >= 255.0f) return 255u;
+    const float fl = floorf(x);
+    const float fr = x - fl;                 // exact
+    return (uint32_t)fl + (fr >= 0.5f ? 1u : 0u);
+}
 
 struct Tables {                 // per-device constant tables
     const float* t_lin;         // ColorContext::byte_to_float, LinearRGB (color.rs:23-48)
@@ -19,22 +30,6 @@ struct Tables {                 // per-device constant tables
 
 struct AxisDev {                // CSR contribution windows of one axis (weights.rs PixelRowWeights)
     const uint32_t* left; const uint32_t* right; const uint32_t* off; const float* w;
-};
-
-struct StripDev { int X0, X1, k0, pad; };       // output columns [X0,X1) read source columns from k0 (multiple of 4)
-struct BandDev  { int Y0, Y1, j0, j1; };        // output rows [Y0,Y1) read source rows j0..j1 inclusive
-
-struct FusedPlanDev {
-    uint32_t in_w, in_h, out_w, out_h;
-    int n_strips, n_bands;
-    uint32_t zero;              // always 0 (run-time constant used to order loads after a scoreboard wait)
-    const uint32_t* vprog;      // [in_h][ProgLayout::kWords]: weight (float bits) of the output row in each ring slot (row y lives in
-                                //   slot y mod AV), then ((first completed y << 8) | (its slot << 4) | count)
-    const StripDev* strips;
-    const BandDev* bands;
-    const float* hw;            // [strip][SH*4*NT]: H weights of thread t by partial plane p = output column mod SH and own column i:
-                                //   p < 2*(SH/2): word 2*(((p/2)*4+i)*NT+t) + (p&1); odd last plane: word 2*(((SH/2)*4+i/2)*NT+t) + (i&1)
-    const uint32_t* hrd;        // [strip][NT] reader u: (first contributing thread) | (count << 12) | ((X mod SH) << 28)
 };
 
 // tile kernels: one CTA works on tow x toh output pixels at a time

@@ -258,7 +258,7 @@ def device_count() -> int:
 class Batch:
     """Device-resident batch executor (ifb200_batch_*): many independent scale_and_render calls whose
     bitmaps already live in HBM of one GPU, enqueued on a CUDA stream."""
-    OPT_FORCE_GENERIC, OPT_THREADS_PER_CTA, OPT_MIN_CTAS, OPT_TILE_KERNEL, OPT_GATHER_AHEAD = 1, 2, 3, 4, 5
+    OPT_FORCE_GENERIC, OPT_STRIP_COLUMNS, OPT_MIN_ITEMS = 1, 2, 3
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
@@ -266,6 +266,12 @@ class Batch:
         _check(lib().ifb200_batch_create(device, C.byref(self._h), buf, 512), buf)
         self.device = device
         self._keep = []
+
+    def ring_status(self):
+        """(usable, reason): whether the streaming ring kernel (the fast path of down-scales) can run on this device"""
+        buf = C.create_string_buffer(256)
+        ok = lib().ifb200_batch_ring_status(self._h, buf, 256)
+        return bool(ok), buf.value.decode()
 
     def set_option(self, option: int, value: int) -> None:
         rc = lib().ifb200_batch_set_option(self._h, option, value)

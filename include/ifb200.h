@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define IFB200_ABI_VERSION_MAJOR 1
-#define IFB200_ABI_VERSION_MINOR 0
+#define IFB200_ABI_VERSION_MINOR 1
 
 /* Error codes.  1..3 map onto the imageflow ErrorKind values raised by scale_and_render
  * (scaling.rs:24-48,145,191,202,240); 10..12 onto WeightsError (weights.rs:494-504). */
@@ -108,6 +108,16 @@ int  ifb200_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t
 int  ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, double* seconds, uint64_t* table_bytes,
                        uint64_t* table_hash, char* err, size_t err_cap);
 
+/* The streaming ring kernel's host tables for one geometry (only in_w, in_h, w, h, filter, sharpen_percent are read), as they
+   would be uploaded: call with buf = NULL for the size.  info->ok == 0: the geometry does not run on the ring kernel.
+   Layout: imageflow_b200/csrc/ifb_hv_kernel.cuh (HvStripDev, HvBandDev, HvPlanDev).  No CUDA call. */
+typedef struct ifb200_hv_plan_info {
+    int32_t ok, av, n_strips, n_bands, cap_px, avp;
+    uint64_t o_strips, o_hw, o_hdone, o_vw, o_vdone, o_bands, total;
+} ifb200_hv_plan_info;
+int  ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_bands, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
+                           char* err, size_t err_cap);
+
 /* ---- drop-in calls: HOST buffers, synchronous (what the Rust adapter calls) ------------------
  * Replaces the bodies of scaling.rs:93-251 (resize_to_canvas / resize_with_matte /
  * resize_and_composite).  err (may be NULL) receives a NUL-terminated message on failure. */
@@ -174,10 +184,9 @@ void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */
 enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
-    IFB200_OPT_THREADS_PER_CTA = 2,    /* fused kernel CTA size: 128 or 256 (strip = 4x that many columns) */
-    IFB200_OPT_MIN_CTAS = 3,           /* split images into row bands until the grid has this many CTAs   */
-    IFB200_OPT_TILE_KERNEL = 4,        /* tile kernel form: 0 default, 1 first (one tile per CTA), 2 second (persistent, tables in shared memory) */
-    IFB200_OPT_GATHER_AHEAD = 5        /* ring kernel: look the next source row up before accumulating the current one (where compiled) */
+    IFB200_OPT_STRIP_COLUMNS = 2,      /* ring kernel: widest strip of output columns one warp works on: 32, 64, 96 or 128 (default) */
+    IFB200_OPT_MIN_ITEMS = 3           /* ring kernel: split images into row bands until a launch has at least this many warp work
+                                          items (0 = as many as the device has warps, the default)        */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */
@@ -186,9 +195,12 @@ uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels
    them, [4] table uploads (allocation + [2] + [3] + cudaMemcpyAsync + events); then counts: [5] table uploads, [6] bytes staged,
    [7] cudaMallocHost calls.  Fills min(n, 8) entries, returns 8. */
 int      ifb200_batch_host_profile(const ifb200_batch* b, double* out, int n);
-uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b);        /* jobs that took the fused kernel */
+uint64_t ifb200_batch_fused_jobs(const ifb200_batch* b);        /* jobs that took the streaming ring kernel */
 uint64_t ifb200_batch_generic_jobs(const ifb200_batch* b);      /* jobs that took the generic pair */
 uint64_t ifb200_batch_tile_jobs(const ifb200_batch* b);         /* jobs that took the tile kernel (up-scales, 1:1) */
+/* 1 when the streaming ring kernel (the fast path for down-scales) can run on this device/driver; 0 when jobs that would take it
+ * fall back to the tile kernel or the generic pair -- `why` (may be NULL) then says what is missing. */
+int      ifb200_batch_ring_status(const ifb200_batch* b, char* why, size_t why_cap);
 
 #ifdef __cplusplus
 }

@@ -164,7 +164,7 @@ def scale_and_render(inp: np.ndarray, canvas: np.ndarray, **kw) -> None:
 
 def resample_stages(inp: np.ndarray, canvas: np.ndarray, **kw):
     d = make_desc(inp, canvas, **kw)
-    v = np.zeros((d.h, d.in_w, 4), np.float32)
+    v = np.zeros((d.in_h, d.w, 4), np.float32)
     hh = np.zeros((d.h, d.w, 4), np.float32)
     rc = lib().ifo_resample_stages(C.byref(d), v.ctypes.data_as(C.POINTER(C.c_float)), hh.ctypes.data_as(C.POINTER(C.c_float)))
     if rc:

@@ -462,11 +462,15 @@ static int resample_core(const ifo_desc* d, float* dbg_v, float* dbg_h) {
     if ((e = wtab_make(&wv, d->filter, d->sharpen_percent, oh, ih))) return e;
     if ((e = wtab_make(&wh, d->filter, d->sharpen_percent, ow, iw))) { wtab_free(&wv); return e; }
 
-    /* ring cache of converted rows: enough for the widest V window */
+    /* Streaming order (the reference pushes rows through zenresize::StreamingResize, scaling.rs:220-249: each pushed row is
+     * filtered horizontally, output rows are emitted as soon as their vertical window is complete):
+     *   H pass  hrow[j][X][c] = fmaf chain over the taps k = left_x .. right_x, ascending, from +0
+     *   V pass  frow[X][c]    = fmaf chain over the rows j = left_y .. right_y, ascending, from +0
+     * ring cache of H-filtered rows: enough for the widest V window */
     uint32_t ring = wv.max_taps + 1;
-    float* cache = (float*)malloc(sizeof(float) * 4 * (size_t)iw * ring);
+    float* cache = (float*)malloc(sizeof(float) * 4 * (size_t)ow * ring);
     int64_t* cached_row = (int64_t*)malloc(sizeof(int64_t) * ring);
-    float* vrow = (float*)malloc(sizeof(float) * 4 * (size_t)iw);
+    float* vrow = (float*)malloc(sizeof(float) * 4 * (size_t)iw);       /* one converted source row */
     float* frow = (float*)malloc(sizeof(float) * 4 * (size_t)ow);
     if (!cache || !cached_row || !vrow || !frow) { free(cache); free(cached_row); free(vrow); free(frow); wtab_free(&wv); wtab_free(&wh); return IFO_ERR_CAPACITY; }
     for (uint32_t i = 0; i < ring; i++) cached_row[i] = -1;
@@ -479,36 +483,32 @@ static int resample_core(const ifo_desc* d, float* dbg_v, float* dbg_h) {
     }
 
     for (uint32_t y = 0; y < oh; y++) {
-        /* ---- V pass: fmaf chain over rows, ascending */
         const uint32_t l = wv.left[y], r = wv.right[y];
         const float* wy = wv.w + wv.off[y];
-        memset(vrow, 0, sizeof(float) * 4 * (size_t)iw);
+        memset(frow, 0, sizeof(float) * 4 * (size_t)ow);
         for (uint32_t j = l; j <= r; j++) {
             uint32_t slot = j % ring;
-            float* cr = cache + (size_t)slot * iw * 4;
-            if (cached_row[slot] != (int64_t)j) { load_row(d->in + (size_t)j * d->in_stride, iw, T, am, cr); cached_row[slot] = j; }
-            const float wgt = wy[j - l];
-            for (size_t i = 0; i < (size_t)iw * 4; i++) vrow[i] = fmaf(wgt, cr[i], vrow[i]);
-        }
-        if (dbg_v) memcpy(dbg_v + (size_t)y * iw * 4, vrow, sizeof(float) * 4 * (size_t)iw);
-        /* ---- H pass: blocked-by-4 sum */
-        for (uint32_t X = 0; X < ow; X++) {
-            const uint32_t hl = wh.left[X], hr = wh.right[X];
-            const float* wx = wh.w + wh.off[X];
-            float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-            for (uint32_t g = hl / 4; g <= hr / 4; g++) {
-                uint32_t k0 = g * 4 > hl ? g * 4 : hl;
-                uint32_t k1 = g * 4 + 3 < hr ? g * 4 + 3 : hr;
-                float p[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-                for (uint32_t k = k0; k <= k1; k++) {
-                    float wgt = wx[k - hl];
-                    const float* v = vrow + (size_t)k * 4;
-                    p[0] = fmaf(wgt, v[0], p[0]); p[1] = fmaf(wgt, v[1], p[1]);
-                    p[2] = fmaf(wgt, v[2], p[2]); p[3] = fmaf(wgt, v[3], p[3]);
+            float* cr = cache + (size_t)slot * ow * 4;
+            if (cached_row[slot] != (int64_t)j) {
+                /* ---- H pass of source row j: sequential fmaf chain per output column */
+                load_row(d->in + (size_t)j * d->in_stride, iw, T, am, vrow);
+                for (uint32_t X = 0; X < ow; X++) {
+                    const uint32_t hl = wh.left[X], hr = wh.right[X];
+                    const float* wx = wh.w + wh.off[X];
+                    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                    for (uint32_t k = hl; k <= hr; k++) {
+                        const float wgt = wx[k - hl];
+                        const float* v = vrow + (size_t)k * 4;
+                        p0 = fmaf(wgt, v[0], p0); p1 = fmaf(wgt, v[1], p1); p2 = fmaf(wgt, v[2], p2); p3 = fmaf(wgt, v[3], p3);
+                    }
+                    cr[4 * X + 0] = p0; cr[4 * X + 1] = p1; cr[4 * X + 2] = p2; cr[4 * X + 3] = p3;
                 }
-                acc[0] = acc[0] + p[0]; acc[1] = acc[1] + p[1]; acc[2] = acc[2] + p[2]; acc[3] = acc[3] + p[3];
+                cached_row[slot] = j;
+                if (dbg_v) memcpy(dbg_v + (size_t)j * ow * 4, cr, sizeof(float) * 4 * (size_t)ow);
             }
-            frow[4 * X + 0] = acc[0]; frow[4 * X + 1] = acc[1]; frow[4 * X + 2] = acc[2]; frow[4 * X + 3] = acc[3];
+            /* ---- V pass: fmaf chain over rows, ascending */
+            const float wgt = wy[j - l];
+            for (size_t i = 0; i < (size_t)ow * 4; i++) frow[i] = fmaf(wgt, cr[i], frow[i]);
         }
         if (dbg_h) memcpy(dbg_h + (size_t)y * ow * 4, frow, sizeof(float) * 4 * (size_t)ow);
         /* ---- store */

@@ -86,9 +86,10 @@ uint8_t ifo_uchar_clamp_ff(float v);                   /* color.rs:101-108 */
 int ifo_scale_and_render(const ifo_desc* d);
 /* same, many images, OpenMP over images (CPU baseline harness). returns first error */
 int ifo_scale_and_render_batch(const ifo_desc* d, size_t n, int threads);
-/* the two intermediate stages, for parity debugging: V-pass result (out_h x in_w x 4 floats)
- * and final premultiplied float pixel rows (out_h x out_w x 4 floats). either may be NULL */
-int ifo_resample_stages(const ifo_desc* d, float* vpass, float* hpass);
+/* the two intermediate stages, for parity debugging: H-pass result (in_h x out_w x 4 floats; rows no output window
+ * touches stay as the caller left them) and the final premultiplied float pixel rows (out_h x out_w x 4 floats).
+ * either may be NULL */
+int ifo_resample_stages(const ifo_desc* d, float* hpass, float* final_rows);
 
 /* color_matrix.rs:5-28; m is row-major [5][5] */
 void ifo_color_matrix(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, const float* m);

@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (ifb200_[a-z0-9_]+)", out))
     assert exported == set(declared)
-    assert L.ifb200_abi_version() == (1 << 16) | 0
+    assert L.ifb200_abi_version() == (1 << 16) | 1
 
 
 def test_desc_struct_layout_matches_header():
@@ -145,11 +145,12 @@ def test_plan_tables_build_on_the_host_for_any_geometry():
     assert one["table_hash"] == four["table_hash"] and one["table_bytes"] == four["table_bytes"] > 0
     assert ifb.plan_probe([], threads=2)["table_bytes"] == 0
     # regression pins (cubic filters only: polynomial f64 arithmetic, no libm): the kernel tables of the benchmark geometries
-    # as the GPU-verified build of round 1 laid them out.  A deliberate change of the table layout updates these constants.
-    pins = {((3840, 2160, 512, 512, 2),): (0x82369c7626e01cfc, 158208),
-            ((7680, 4320, 1920, 1080, 2, 50.0),): (0xd20130431b3e3011, 317552),
+    # as the build whose kernel source passes tests/test_hv_emulation.py lays them out (round 2: streaming H-then-V ring kernel).
+    # A deliberate change of the table layout updates these constants.
+    pins = {((3840, 2160, 512, 512, 2),): (0x916b2b45dfc8e9e9, 106896),
+            ((7680, 4320, 1920, 1080, 2, 50.0),): (0x6751d6d107d68342, 335616),
             ((1920, 1080, 3840, 2160, 14),): (0xe0ce1caa7adbc55b, 0),            # up-scale: tile kernel, no ring tables
-            ((640, 480, 200, 150, 2), (33, 17, 7, 5, 2)): (0x1784450144c6f307, 61232)}
+            ((640, 480, 200, 150, 2), (33, 17, 7, 5, 2)): (0x6eff95bfe6a1a563, 62001)}
     for geo, (h, nbytes) in pins.items():
         r = ifb.plan_probe(list(geo), threads=1, want_hash=True)
         assert (r["table_hash"], r["table_bytes"]) == (h, nbytes), geo

@@ -33,16 +33,14 @@ def _oracle(inp, canvas, **kw):
 
 
 def _gpu_batch(ifb, torch, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen=0.0, linear=True,
-               alpha_meaningful=False, compose=0, matte=(0, 0, 0, 0), color_matrix=None, force_generic=False, nt=256,
-               min_ctas=None, tile_kernel=0, counters=None, gather_ahead=None):
+               alpha_meaningful=False, compose=0, matte=(0, 0, 0, 0), color_matrix=None, force_generic=False, strip_cols=128,
+               min_items=None, counters=None):
     b = ifb.Batch(0)
+    assert b.ring_status()[0], b.ring_status()[1]          # the streaming ring kernel must be usable on the GPU box
     b.set_option(ifb.Batch.OPT_FORCE_GENERIC, int(force_generic))
-    b.set_option(ifb.Batch.OPT_TILE_KERNEL, tile_kernel)
-    if gather_ahead is not None:
-        b.set_option(ifb.Batch.OPT_GATHER_AHEAD, int(gather_ahead))
-    b.set_option(ifb.Batch.OPT_THREADS_PER_CTA, nt)
-    if min_ctas is not None:
-        b.set_option(ifb.Batch.OPT_MIN_CTAS, min_ctas)
+    b.set_option(ifb.Batch.OPT_STRIP_COLUMNS, strip_cols)
+    if min_items is not None:
+        b.set_option(ifb.Batch.OPT_MIN_ITEMS, min_items)
     # device copies with a 64-byte padded pitch like Bitmap::create_u8 (bitmaps.rs:803-804)
     def up(a):
         hh, ww, _ = a.shape
@@ -122,32 +120,32 @@ def test_fused_kernel_is_the_one_that_runs(ifb, torch_mod):
     assert fused == 0
 
 
-@pytest.mark.parametrize("nt,min_ctas", [(128, 1), (256, 1), (256, 4096), (128, 64)])
-def test_fused_decompositions_agree(ifb, torch_mod, nt, min_ctas):
+@pytest.mark.parametrize("strip_cols,min_items", [(32, 1), (128, 1), (128, 4096), (64, 64), (96, 100000)])
+def test_fused_decompositions_agree(ifb, torch_mod, strip_cols, min_items):
     """strip width and row-band count must not change a single bit."""
     inp = util.noise(1280, 720, seed=7, alpha_mode="mixed")
     canvas = np.zeros((180, 320, 4), np.uint8)
     exp = _oracle(inp, canvas, filter=2, alpha_meaningful=True)
-    got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, alpha_meaningful=True, nt=nt, min_ctas=min_ctas)
+    got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, filter=2, alpha_meaningful=True, strip_cols=strip_cols, min_items=min_items)
     assert fused == 1
     assert util.diff_stats(got, exp)[0] == 0
 
 
-@pytest.mark.parametrize("gather_ahead", [0, 1], ids=["plain", "gather_ahead"])
-def test_ring_kernel_forms_bit_exact(ifb, torch_mod, gather_ahead):
-    """the ring kernel with and without the gather-ahead row pipeline (cubic filters, 256 threads): single band, many
-    bands, short bands (fewer source rows than row stages), every store epilogue"""
+def test_ring_kernel_forms_bit_exact(ifb, torch_mod):
+    """the ring kernel: single band, many bands, short bands (fewer source rows than one row block), every store epilogue,
+    both ring depths, the full-size 4K frame"""
     cases = [(1280, 720, 320, 180, 2, True, 0, None, None), (1280, 720, 320, 180, 2, False, 0, None, 4096),
              (960, 540, 128, 128, 2, True, 1, None, None), (1920, 1080, 640, 360, 14, True, 2, 0, None),
              (800, 600, 400, 300, 13, False, 1, 0, 64), (1024, 64, 96, 17, 13, True, 0, None, 4096),
-             (640, 9, 160, 2, 2, True, 0, None, None), (3840, 2160, 512, 512, 2, False, 0, None, None)]
+             (640, 9, 160, 2, 2, True, 0, None, None), (3840, 2160, 512, 512, 2, False, 0, None, None),
+             (3840, 2160, 512, 512, 6, True, 0, None, None), (1537, 1021, 333, 127, 6, False, 1, None, 3000)]
     for (iw, ih, ow, oh, flt, alpha, compose, cmw, min_ctas) in cases:
         inp = util.noise(iw, ih, seed=iw + ih + flt, alpha_mode="mixed" if alpha else "opaque")
         canvas = util.noise(ow, oh, seed=5, alpha_mode="mixed")
         cm = ifb.color_filter_matrix(cmw) if cmw is not None else None
         kw = dict(filter=flt, alpha_meaningful=alpha, compose=compose, matte=(10, 200, 90, 180), color_matrix=cm)
         exp = _oracle(inp, canvas, **kw)
-        got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, min_ctas=min_ctas, gather_ahead=gather_ahead, **kw)
+        got, fused = _gpu_batch(ifb, torch_mod, inp, canvas, min_items=min_ctas, **kw)
         assert fused == 1, (iw, ih, ow, oh)
         assert util.diff_stats(got, exp)[0] == 0, (iw, ih, ow, oh, flt, alpha, compose, min_ctas)
 
@@ -209,10 +207,9 @@ TILE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("tile_kernel", [1, 2], ids=["tile1", "tile2"])
 @pytest.mark.parametrize("case", TILE_CASES, ids=lambda c: "x".join(map(str, c)))
-def test_tile_kernel_forms_bit_exact(ifb, torch_mod, case, tile_kernel):
-    """both forms of the tile kernel, every compile-time case of the second (channels x working space x compositing mode
+def test_tile_kernel_bit_exact(ifb, torch_mod, case):
+    """the tile kernel, every compile-time case (channels x working space x compositing mode
     x colour matrix, general and rgb-only matrices), destination rect inside a larger canvas: bit-exact against the oracle"""
     iw, ih, ow, oh, flt = case
     sepia = ifb.color_filter_matrix(0)
@@ -230,34 +227,10 @@ def test_tile_kernel_forms_bit_exact(ifb, torch_mod, case, tile_kernel):
                   matte=(40, 120, 250, 200), color_matrix=cm)
         exp = _oracle(inp, canvas, **kw)
         cnt = {}
-        got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, tile_kernel=tile_kernel, counters=cnt, **kw)
+        got, _ = _gpu_batch(ifb, torch_mod, inp, canvas, counters=cnt, **kw)
         assert cnt["tile"] == 1, (case, cnt)
         mx, n = util.diff_stats(got, exp)
         assert mx == 0, (case, alpha, linear, compose, cm is not None, mx, n)
-
-
-def test_tile_kernel_forms_agree_at_full_size(ifb, torch_mod):
-    """config 4 (1080p -> 4K Mitchell, sepia, composited over a canvas) at full size: the two forms agree bit for bit"""
-    torch = torch_mod
-    from imageflow_b200 import synth
-    cm = ifb.color_filter_matrix(0)
-    ins = [synth.noise_torch(1920, 1080, seed=700 + i, alpha_mode="mixed") for i in range(3)]
-    cv0 = [synth.noise_torch(3840, 2160, seed=800 + i, alpha_mode="mixed") for i in range(3)]
-    outs = {}
-    for form in (1, 2):
-        b = ifb.Batch(0)
-        b.set_option(ifb.Batch.OPT_TILE_KERNEL, form)
-        cvs = [c.clone() for c in cv0]
-        p = ifb.ScaleAndRenderParams(w=3840, h=2160, interpolation_filter=ifb.Filter(14))
-        b.scale_and_render_many([(ifb.BitmapWindow.from_torch(ins[i], alpha_meaningful=True),
-                                  ifb.BitmapWindow.from_torch(cvs[i], compose=ifb.BitmapCompositing(1)), p, cm) for i in range(3)],
-                                stream=torch.cuda.current_stream().cuda_stream)
-        torch.cuda.synchronize()
-        assert b.tile_jobs == 3
-        b.close()
-        outs[form] = cvs
-    for i in range(3):
-        assert torch.equal(outs[1][i], outs[2][i])
 
 
 def test_dropin_host_call_matches_oracle(ifb):
