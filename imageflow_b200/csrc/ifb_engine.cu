@@ -306,17 +306,20 @@ std::vector<HvBandDev> hv_bands(const Plan& p, int nb) {
     }
     return bands;
 }
-// Band count of a launch: enough work items for every warp of the grid, then the count whose last round of items is fullest,
-// counting what the band halos (the V window is re-read at every band edge) cost.
+// Band count of a launch.  min_items > 0 (IFB200_OPT_MIN_ITEMS): the smallest count that gives that many work items.  Otherwise:
+// enough bands to give every warp of the device one item; and when there is more than one round of items anyway, the count
+// whose last round is fullest, counting what the band halos (the V window is re-read at every band edge) cost.
 int hv_pick_bands(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
     const int max_nb = (int)std::max<uint32_t>(1u, p.out_h / 8u);
+    auto need = [&](size_t items) { return (int)std::min<size_t>((size_t)max_nb, std::max<size_t>(1, (items + jobs_x_strips - 1) / jobs_x_strips)); };
+    if (min_items > 0) return need((size_t)min_items);
+    const int nb0 = need((size_t)warps);
+    if (jobs_x_strips * (size_t)nb0 <= (size_t)warps) return nb0;
     const double halo = (double)p.wv.max_taps / (double)std::max<uint32_t>(p.in_h, 1u);
-    int best = 1; double best_eff = -1.0;
-    for (int nb = 1; nb <= std::min(max_nb, 64); ++nb) {
+    int best = nb0; double best_eff = -1.0;
+    for (int nb = nb0; nb <= std::min(max_nb, nb0 + 7); ++nb) {
         const double items = (double)jobs_x_strips * nb;
-        if (items < (double)min_items && nb < max_nb && nb < 64) continue;
-        const double rounds = std::ceil(items / warps);
-        const double eff = items / warps / rounds / (1.0 + halo * (nb - 1));
+        const double eff = items / warps / std::ceil(items / warps) / (1.0 + halo * (nb - 1));
         if (eff > best_eff + 1e-9) { best_eff = eff; best = nb; }
     }
     return best;
@@ -661,7 +664,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             const HvEntry* he = find_hv(p.av, g.ch);
             const size_t jxs = g.idx.size() * (size_t)ht.n_strips;
             const int warps_all = b->sm_count * he->warps;
-            lay[gi].nb = hv_pick_bands(p, jxs, warps_all, b->min_items > 0 ? b->min_items : warps_all);
+            lay[gi].nb = hv_pick_bands(p, jxs, warps_all, b->min_items);
             lay[gi].bv = hv_bands(p, lay[gi].nb);
             lay[gi].nb = (int)lay[gi].bv.size();
             const size_t items = jxs * lay[gi].nb;

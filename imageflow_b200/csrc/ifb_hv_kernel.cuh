@@ -107,10 +107,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred p;\n"
-                 "IFB_HV_WAIT_%=:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                 "@!p bra IFB_HV_WAIT_%=;\n\t}" ::"r"(addr), "r"(parity) : "memory");
+    // try_wait suspends the thread for a hardware-defined time before it reports failure, so the retry loop is rarely taken;
+    // a transfer that never completes (a bad descriptor) traps after a few seconds instead of hanging the device
+    for (uint32_t tries = 0;; ++tries) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (tries > (1u << 24)) __trap();
+    }
 }
 // one box of 16 pixels x 32 rows at pixel (x, y) of the job's bitmap -> shared memory, completion counted on the mbarrier
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const HvTmap* tm, int x, int y, uint32_t mbar) {

@@ -1,15 +1,14 @@
 """detect_content on the GPU (whitespace_codes_kernel + the host window walk) against the oracle.
 
-Written at the very end of round 1, after the GPU budget was spent: the kernel has not run on a GPU yet.  The host half is
-verified on the CPU (tests/test_whitespace_product.py).  This file sorts last and is marked xfail(strict=False) until its
-first run has been seen: an XPASS in the report is that first run succeeding."""
+The host half is also verified on the CPU (tests/test_whitespace_product.py).  First run on a GPU: the driver's round-1
+GPU test pass (it reported XPASS under the provisional xfail marker this file carried then; the marker is gone)."""
 import numpy as np
 import pytest
 
 import oracle
 from tests.test_whitespace_product import _images
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first GPU run pending (written after the round's GPU budget was spent)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def test_detect_content_matches_oracle():
