@@ -20,6 +20,7 @@ SYMBOLS = [
     "ifb200_batch_create", "ifb200_batch_enqueue", "ifb200_batch_color_matrix", "ifb200_batch_sync",
     "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches", "ifb200_batch_host_profile",
     "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs", "ifb200_batch_ring_status", "ifb200_hv_plan_tables",
+    "ifb200_block_scale_u8", "ifb200_batch_block_scale",
 ]
 
 
@@ -111,6 +112,10 @@ def lib() -> C.CDLL:
     for f in ("ifb200_batch_kernel_launches", "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs"):
         getattr(L, f).argtypes = [C.c_void_p]
         getattr(L, f).restype = C.c_uint64
+    L.ifb200_block_scale_u8.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.ifb200_block_scale_u8.restype = C.c_int
+    L.ifb200_batch_block_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t]
+    L.ifb200_batch_block_scale.restype = C.c_int
     L.ifb200_batch_ring_status.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.ifb200_batch_ring_status.restype = C.c_int
     _lib = L

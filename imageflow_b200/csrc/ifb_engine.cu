@@ -376,6 +376,7 @@ struct ifb200_batch {
     cudaEvent_t ev_fork = nullptr, ev_join[kSideStreams] = {};
     std::mutex mu;
     DevVec<float> t_lin, t_srgb; DevVec<uint8_t> lut16k;
+    DevVec<uint16_t> idct_to_linear; DevVec<uint8_t> idct_to_srgb;     // block scalers' transfer tables (codecs_jpeg_idct_fast.c:103-300)
     Tables tables{};
     using Key = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, int, uint32_t>;
     static constexpr size_t kMaxPlans = 4096;
@@ -864,6 +865,24 @@ void flip_locked(ifb200_batch* b, bool vertical, uint8_t* px, uint32_t w, uint32
     b->launches++;
 }
 
+// flow_scale_spatial[_srgb]_NxN over a plane of 8x8 blocks (codecs_jpeg_idct_fast.c; hook: codec_jpeg_wrapper.c:274-340)
+void block_scale_locked(ifb200_batch* b, const uint8_t* in, uint32_t in_stride, uint32_t blocks_x, uint32_t blocks_y, uint8_t* out, uint32_t out_stride,
+                        int n, int srgb, cudaStream_t st) {
+    if (!in || !out) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null plane pointer");
+    if (n < 1 || n > 7) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "block scalers exist for 1x1 .. 7x7 (got %d)", n);
+    if (blocks_x == 0 || blocks_y == 0) return;
+    if (in_stride < blocks_x * 8ull || out_stride < (uint64_t)blocks_x * (uint32_t)n) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a row of blocks");
+    CUDA_OK(cudaSetDevice(b->device));
+    const uint32_t gx = (blocks_x + 31u) / 32u;
+    for (uint32_t y0 = 0; y0 < blocks_y; y0 += 65535u) {             // grid.y is bounded; planes are not
+        const uint32_t cnt = std::min(65535u, blocks_y - y0);
+        idct_block_scale_kernel<<<dim3(gx, cnt), 256, 0, st>>>(in + (size_t)y0 * 8u * in_stride, in_stride, blocks_x, out + (size_t)y0 * (uint32_t)n * out_stride,
+                                                              out_stride, n, srgb ? 1 : 0, b->idct_to_linear.p, b->idct_to_srgb.p);
+        CUDA_OK(cudaGetLastError());
+        b->launches++;
+    }
+}
+
 // flow/nodes/white_balance.rs:93-121 (WhiteBalanceSrgbMutDef::mutate): histograms, area thresholds, byte maps, remap.
 // threshold < 0 stands for None (-> 0.006f32, white_balance.rs:76-77); both thresholds are the same value (:114).
 void white_balance_locked(ifb200_batch* b, uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, cudaStream_t st) {
@@ -966,6 +985,9 @@ ifb200_batch* create_batch(int device) {
     ifb::byte_to_float_table(true, tl.data()); ifb::byte_to_float_table(false, ts.data()); ifb::linear_to_srgb_table(lut.data());
     b->t_lin.upload(tl); b->t_srgb.upload(ts); b->lut16k.upload(lut);
     b->tables = Tables{b->t_lin.p, b->t_srgb.p, b->lut16k.p};
+    b->idct_to_linear.upload(std::vector<uint16_t>(kIdct_lut_srgb_to_linear, kIdct_lut_srgb_to_linear + 256));
+    b->idct_to_srgb.upload(std::vector<uint8_t>(kIdct_lut_linear_to_srgb, kIdct_lut_linear_to_srgb + 4096));
+    CUDA_OK(cudaMemcpyToSymbol(c_idct, kIdctScalers, sizeof kIdctScalers));
     CUDA_OK(cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device));
     {   // the ring kernel lays its shared memory out around a 64 KB-aligned (in the shared window) lookup table: learn where
         // dynamic shared memory starts in the window, and check that every variant then fits
@@ -1208,6 +1230,15 @@ int ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uin
     });
 }
 
+int ifb200_batch_block_scale(ifb200_batch* b, const uint8_t* dev_in, uint32_t in_stride, uint32_t blocks_x, uint32_t blocks_y, uint8_t* dev_out,
+                             uint32_t out_stride, int n, int srgb, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        block_scale_locked(b, dev_in, in_stride, blocks_x, blocks_y, dev_out, out_stride, n, srgb, stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
+    });
+}
+
 int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
@@ -1379,6 +1410,29 @@ int ifb200_detect_content_bgra8(const uint8_t* px, uint32_t w, uint32_t h, uint3
         ensure(sl.d_cv, sl.cap_cv, pitch * h, st);
         CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, pitch, px, stride, (size_t)w * 4, h, cudaMemcpyHostToDevice, st));
         detect_content_locked(b, sl.d_cv, w, h, (uint32_t)pitch, alpha_meaningful, threshold, st, rect);
+    });
+}
+
+int ifb200_block_scale_u8(const uint8_t* in, uint32_t in_stride, uint32_t blocks_x, uint32_t blocks_y, uint8_t* out, uint32_t out_stride, int n, int srgb,
+                          char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!in || !out) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+        if (n < 1 || n > 7) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "block scalers exist for 1x1 .. 7x7 (got %d)", n);
+        if (blocks_x == 0 || blocks_y == 0) return;
+        if (in_stride < blocks_x * 8ull || out_stride < (uint64_t)blocks_x * (uint32_t)n) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a row of blocks");
+        HostCtx& c = host_ctx();
+        ifb200_batch* b = c.batch;
+        std::lock_guard<std::mutex> lk(b->mu);
+        CUDA_OK(cudaSetDevice(b->device));
+        HostSlot& sl = c.slot[0];
+        cudaStream_t st = sl.stream;
+        const size_t pin = ((size_t)blocks_x * 8 + 63) / 64 * 64, pout = ((size_t)blocks_x * n + 63) / 64 * 64;
+        ensure(sl.d_in, sl.cap_in, pin * blocks_y * 8, st);
+        ensure(sl.d_cv, sl.cap_cv, pout * blocks_y * n, st);
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_in, pin, in, in_stride, (size_t)blocks_x * 8, (size_t)blocks_y * 8, cudaMemcpyHostToDevice, st));
+        block_scale_locked(b, sl.d_in, (uint32_t)pin, blocks_x, blocks_y, sl.d_cv, (uint32_t)pout, n, srgb, st);
+        CUDA_OK(cudaMemcpy2DAsync(out, out_stride, sl.d_cv, pout, (size_t)blocks_x * n, (size_t)blocks_y * n, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaStreamSynchronize(st));
     });
 }
 

@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(256) apply_byte_maps_bgra8_kernel(uint8_t* __r
 // In its own file so that tests/ can also execute this very source under a CPU emulation of the CUDA built-ins it uses.
 #include "ifb_whitespace_kernel.cuh"
 
+// ---------------------------------------------------------------- decode-time JPEG block scalers
+#include "ifb_idct_kernel.cuh"
+
 // ---------------------------------------------------------------- the hot kernel: streaming H-then-V ring kernel (TMA-staged rows)
 #include "ifb_hv_kernel.cuh"
 

@@ -194,6 +194,19 @@ def white_balance_srgb_mut(bitmap: BitmapWindow, threshold: Optional[float] = No
     _check(lib().ifb200_white_balance_srgb_bgra8(bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, -1.0 if threshold is None else float(threshold), buf, 512), buf)
 
 
+def flow_scale_spatial(samples: np.ndarray, n: int, srgb: bool = False) -> np.ndarray:
+    """flow_scale_spatial[_srgb]_{n}x{n} (c_components/lib/codecs_jpeg_idct_fast.c) applied to every 8x8 block of a plane of
+    samples (H x W uint8, both multiples of 8; host memory): returns the (H/8*n) x (W/8*n) plane."""
+    a = np.ascontiguousarray(samples, np.uint8)
+    h, w = a.shape
+    if h % 8 or w % 8:
+        raise FlowError(int(ErrorKind.InvalidArgument), "plane dimensions must be multiples of 8")
+    out = np.zeros((h // 8 * n, w // 8 * n) if 1 <= n <= 7 else (1, 1), np.uint8)
+    buf = C.create_string_buffer(512)
+    _check(lib().ifb200_block_scale_u8(a.ctypes.data, a.strides[0], w // 8, h // 8, out.ctypes.data, out.strides[0], n, int(bool(srgb)), buf, 512), buf)
+    return out
+
+
 def detect_content(bitmap: BitmapWindow, threshold: int = 1):
     """graphics/whitespace.rs:284-331 with a HOST bitmap -> (x1, y1, x2, y2)."""
     rect = (C.c_uint32 * 4)()
@@ -318,6 +331,11 @@ class Batch:
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_transpose(self._h, from_window.ptr, from_window.stride, from_window.w, from_window.h,
                                             to_window.ptr, to_window.stride, self._stream(stream), buf, 512), buf)
+
+    def block_scale(self, dev_in: int, in_stride: int, blocks_x: int, blocks_y: int, dev_out: int, out_stride: int, n: int, srgb: bool, stream=None) -> None:
+        """flow_scale_spatial[_srgb]_{n}x{n} over a device-resident plane of 8x8 sample blocks"""
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_block_scale(self._h, dev_in, in_stride, blocks_x, blocks_y, dev_out, out_stride, n, int(bool(srgb)), self._stream(stream), buf, 512), buf)
 
     def white_balance(self, bitmap: BitmapWindow, threshold: Optional[float] = None, stream=None) -> None:
         """flow/nodes/white_balance.rs:93-121 on a DEVICE bitmap, in place (three kernels, asynchronous on `stream`)."""

@@ -149,6 +149,14 @@ int ifb200_flip_horizontal_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t s
  * threshold < 0 = None (0.006).  [SURVEY.md section 8(f), item 4] */
 int ifb200_white_balance_srgb_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, float threshold, char* err, size_t err_cap);
 
+/* Replaces flow_scale_spatial[_srgb]_{n}x{n} (c_components/lib/codecs_jpeg_idct_fast.c:302-4428; libjpeg hook codec_jpeg_wrapper.c:232-340,
+ * enabled by JpegDownscaleHints, mozjpeg_decoder.rs:593-611) for a whole plane of samples: every 8x8 block of `in` (blocks_x x blocks_y
+ * blocks, row stride in_stride bytes) becomes the n x n block at (bx*n, by*n) of `out`; n = 1..7; srgb != 0 = the linear-light variants.
+ * Bit-identical to the reference functions (integer arithmetic, the reference's own weight and table literals).
+ * [SURVEY.md section 8(f), item 1] */
+int ifb200_block_scale_u8(const uint8_t* in, uint32_t in_stride, uint32_t blocks_x, uint32_t blocks_y, uint8_t* out, uint32_t out_stride,
+                          int n, int srgb, char* err, size_t err_cap);
+
 /* ---- device-resident batch API (the metric path; not in the reference) -----------------------
  * descs[i].in / .canvas are DEVICE pointers on the batch's device; color_matrix stays a HOST pointer.
  * enqueue is asynchronous on `cuda_stream`, a cudaStream_t with the usual CUDA meaning (NULL = the legacy
@@ -170,6 +178,8 @@ int  ifb200_batch_flip_vertical(ifb200_batch* b, uint8_t* dev_px, uint32_t w, ui
                                 void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_flip_horizontal(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride,
                                   void* cuda_stream, char* err, size_t err_cap);
+int  ifb200_batch_block_scale(ifb200_batch* b, const uint8_t* dev_in, uint32_t in_stride, uint32_t blocks_x, uint32_t blocks_y,
+                              uint8_t* dev_out, uint32_t out_stride, int n, int srgb, void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, float threshold,
                                 void* cuda_stream, char* err, size_t err_cap);
 /* graphics/whitespace.rs:284-331 detect_content(&BitmapWindowMut<u8>, threshold) -> RectCorners{x1, y1, x2, y2}: the rectangle the

@@ -252,3 +252,39 @@ def detect_content_from_codes(codes: np.ndarray):
     if rc:
         raise OracleError(rc)
     return tuple(rect), n.value
+
+
+# ---------------------------------------------------------------------------------------------- oracle/_ref: the reference itself
+_REF_IDCT = os.path.join(_HERE, "_ref", "libidct_ref.so")
+
+
+def idct_ref_available() -> bool:
+    """oracle/_ref/libidct_ref.so = /root/reference/c_components/lib/codecs_jpeg_idct_fast.c compiled as it is (oracle/Makefile)."""
+    if not os.path.exists(_REF_IDCT) and os.path.exists("/root/reference/c_components/lib/codecs_jpeg_idct_fast.c"):
+        subprocess.call(["make", "-C", _HERE, "-s", "CC=gcc", "ref"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return os.path.exists(_REF_IDCT)
+
+
+_idct = None
+
+
+def flow_scale_spatial_ref(samples: np.ndarray, n: int, srgb: bool = False) -> np.ndarray:
+    """The reference's own flow_scale_spatial[_srgb]_{n}x{n} called block by block over a plane (H x W uint8, multiples of 8)."""
+    global _idct
+    if _idct is None:
+        _idct = C.CDLL(_REF_IDCT)
+    fn = getattr(_idct, f"flow_scale_spatial_{'srgb_' if srgb else ''}{n}x{n}")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    fn.restype = None
+    a = np.ascontiguousarray(samples, np.uint8)
+    h, w = a.shape
+    out = np.zeros((h // 8 * n, w // 8 * n), np.uint8)
+    rows = (C.c_void_p * n)()
+    blk = np.zeros(64, np.uint8)
+    for by in range(h // 8):
+        for r in range(n):
+            rows[r] = out.ctypes.data + (by * n + r) * out.strides[0]
+        for bx in range(w // 8):
+            blk[:] = a[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8].reshape(64)
+            fn(blk.ctypes.data, rows, bx * n)
+    return out
