@@ -203,8 +203,12 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
     const auto& h = p.wh; const auto& v = p.wv;
     const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4), ng = av == 4 ? 4 : 2;
     const uint32_t col_cap = (uint32_t)std::min(max_cols, ng * 32);
+    // the pixel stream of a strip starts at a multiple of k0_align source columns (16 bytes: TMA box origins stay 16-byte aligned
+    // for bitmaps whose window starts on a 16-byte boundary; IFB200_DEBUG_K0_ALIGN=1 lifts that, for experiments)
+    static const uint32_t k0_align = [] { const char* e = getenv("IFB200_DEBUG_K0_ALIGN"); const int v = e ? atoi(e) : 4; return (uint32_t)(v >= 1 && v <= 16 ? v : 4); }();
+    auto k0_of = [&](uint32_t X0) { return h.left[X0] / k0_align * k0_align; };
     auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1): at most col_cap columns and a pixel stream (whole stages of 16) within the table
-        return X1 - X0 <= col_cap && (h.right[X1 - 1] - h.left[X0] + 1 + 15) / 16 * 16 <= (uint32_t)cap;
+        return X1 - X0 <= col_cap && (h.right[X1 - 1] - k0_of(X0) + 1 + 15) / 16 * 16 <= (uint32_t)cap;
     };
     uint32_t ns = 0;
     for (uint32_t X0 = 0; X0 < h.out_size; ++ns) {
@@ -222,10 +226,10 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
             if (X1 <= X0) { ok = false; break; }
             ok = fits(X0, X1);
             HvStripDev sd{};
-            sd.X0 = (int)X0; sd.X1 = (int)X1; sd.k0 = (int)h.left[X0];
-            sd.nst = (int)((h.right[X1 - 1] - h.left[X0] + 1 + 15) / 16);
+            sd.X0 = (int)X0; sd.X1 = (int)X1; sd.k0 = (int)k0_of(X0);
+            sd.nst = (int)((h.right[X1 - 1] - k0_of(X0) + 1 + 15) / 16);
             uint32_t Xf = X0;                        // first column completing inside the stream: right[Xf] >= k0
-            while (Xf > 0 && h.right[Xf - 1] >= h.left[X0]) --Xf;
+            while (Xf > 0 && h.right[Xf - 1] >= k0_of(X0)) --Xf;
             sd.Xf = (int)Xf; sd.hslot0 = (int)(Xf % (uint32_t)av);
             strips.push_back(sd);
         }
