@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE.json configurations")
+    ap.add_argument("--ncu-traffic", action="store_true", help="measure the kernel's DRAM traffic with ncu and rewrite profiles/traffic_<workload>.json")
     ap.add_argument("--strip-cols", type=int, default=0, help="ring kernel: widest strip of output columns per warp (0 = library default)")
     ap.add_argument("--min-items", type=int, default=-1, help="ring kernel: band split target (-1 = library default)")
     return ap.parse_args()
@@ -119,12 +121,41 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def host_threads() -> int:
-    """all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler instead)"""
+def host_cpu_info() -> dict:
+    """What the CPU arm can really use: the scheduler affinity AND the cgroup CPU quota (a container given 16 CPUs of a 128-thread
+    host still sees 128 in sched_getaffinity), plus the CPU model.  `threads` is what the OpenMP runs are given."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        aff = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        aff = max(1, os.cpu_count() or 1)
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().split()[0])
+            break
+        except Exception:
+            continue
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    eff = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return {"threads": eff, "sched_affinity": aff, "cgroup_cpu_quota": quota, "cpu_model": model}
+
+
+def host_threads() -> int:
+    """host threads for the CPU arm (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler and the cgroup instead)"""
+    return host_cpu_info()["threads"]
 
 
 def algorithmic_bytes_per_image(wl):
@@ -136,61 +167,71 @@ def algorithmic_bytes_per_image(wl):
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_oracle_run(wl, n_images, threads, content, alpha, keep_outputs=False):
-    """Times the CPU oracle (OpenMP over images) on n_images frames of the workload. Returns (seconds, outputs)."""
-    import oracle
-    from imageflow_b200 import synth
-    iw, ih = wl["in_wh"]; ow, oh = wl["out_wh"]
-    L = oracle.lib()
-    ins, outs, descs = [], [], (oracle.Desc * n_images)()
-    cm = oracle.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
-    keep = []
-    distinct = min(n_images, max(2, min(16, n_images)))      # generating frames in numpy is slow: cycle through a few
-    for i in range(n_images):
-        if i < distinct:
-            a = synth.noise_np(iw, ih, seed=i, alpha_mode="mixed" if alpha else "opaque") if content == "noise" else synth.gradient_np(iw, ih)
-        else:
-            a = ins[i % distinct]
-        c = synth.noise_np(ow, oh, seed=100000 + i, alpha_mode="mixed") if (wl["compose"] == 1 and i < distinct) else \
-            (outs[i % distinct].copy() if wl["compose"] == 1 else np.zeros((oh, ow, 4), np.uint8))
-        ins.append(a); outs.append(c)
-        descs[i] = oracle.make_desc(a, c, filter=wl["filter"], sharpen=wl["sharpen"], linear=True, alpha_meaningful=bool(alpha),
-                                    compose=wl["compose"], color_matrix=cm, keep=keep)
-    t0 = time.perf_counter()
-    rc = L.ifo_scale_and_render_batch(descs, n_images, threads)
-    dt = time.perf_counter() - t0
-    if rc:
-        raise RuntimeError(f"oracle failed rc={rc}")
-    return dt, (outs if keep_outputs else None)
+CPU_DISTINCT = 64       # distinct input frames the CPU arm cycles through (64 4K frames = 2.1 GB: far larger than any last-level cache)
+
+
+class CpuArm:
+    """The CPU oracle (OpenMP over images) on frames of the workload.  Inputs are generated once (C generator, same bytes as
+    imageflow_b200.synth) and kept; a run of n images walks them cyclically, every job with its own canvas."""
+
+    def __init__(self, wl, content, alpha, distinct):
+        import oracle
+        from imageflow_b200 import synth
+        self.wl, self.alpha, self.oracle = wl, alpha, oracle
+        iw, ih = wl["in_wh"]; ow, oh = wl["out_wh"]
+        am = "mixed" if alpha else "opaque"
+        self.ins = [oracle.synth_noise(iw, ih, seed=i, alpha_mode=am) if content == "noise" else synth.gradient_np(iw, ih) for i in range(distinct)]
+        self.cv0 = [oracle.synth_noise(ow, oh, seed=100000 + i, alpha_mode="mixed") for i in range(distinct)] if wl["compose"] == 1 else None
+        self.cm = oracle.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
+
+    def run(self, n_images, threads, keep_outputs=False):
+        wl, oracle = self.wl, self.oracle
+        ow, oh = wl["out_wh"]
+        d = len(self.ins)
+        outs = [self.cv0[i % d].copy() if self.cv0 is not None else np.zeros((oh, ow, 4), np.uint8) for i in range(n_images)]
+        descs, keep = (oracle.Desc * n_images)(), []
+        for i in range(n_images):
+            descs[i] = oracle.make_desc(self.ins[i % d], outs[i], filter=wl["filter"], sharpen=wl["sharpen"], linear=True, alpha_meaningful=bool(self.alpha),
+                                        compose=wl["compose"], color_matrix=self.cm, keep=keep)
+        t0 = time.perf_counter()
+        rc = oracle.lib().ifo_scale_and_render_batch(descs, n_images, threads)
+        dt = time.perf_counter() - t0
+        if rc:
+            raise RuntimeError(f"oracle failed rc={rc}")
+        return dt, (outs if keep_outputs else None)
 
 
 def run_reference(args, wl, rank, world):
-    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU implementation of the path on the host cores (rank 0 only).  Every step is the workload's full
+    batch (the same `config` as the GPU arm) unless that would take more than ~12 s per step on this host, then a bounded sample."""
     if rank != 0:
         return
     import oracle
     oracle.build()
-    threads = host_threads()
+    cpu = host_cpu_info()
+    threads = cpu["threads"]
     alpha = wl["alpha"] if args.alpha < 0 else args.alpha
     iw, ih = wl["in_wh"]
-    # size the bounded sample: one probe image per thread, then scale to ~cpu_seconds / (steps+warmup)
-    cpu_oracle_run(wl, threads, threads, args.content, alpha)                     # warm-up (tables, page faults)
-    dt, _ = cpu_oracle_run(wl, 2 * threads, threads, args.content, alpha)
-    budget = max(2.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))
-    n = int(max(2 * threads, min(4096, round(budget / max(dt, 1e-3) * 2 * threads))))
+    B = args.batch or wl["batch"]
+    arm = CpuArm(wl, args.content, alpha, min(B, CPU_DISTINCT))
+    arm.run(min(B, threads), threads)                                            # warm-up (tables, page faults)
+    dt, _ = arm.run(min(B, 2 * threads), threads)
+    per_image = dt / min(B, 2 * threads)
+    n = B if per_image * B <= 12.0 else int(max(2 * threads, 12.0 / per_image))
     for _ in range(args.warmup):
-        cpu_oracle_run(wl, n, threads, args.content, alpha)
+        arm.run(n, threads)
     t = 0.0
     for _ in range(args.steps):
-        d, _ = cpu_oracle_run(wl, n, threads, args.content, alpha)
+        d, _ = arm.run(n, threads)
         t += d
     mpx = n * args.steps * iw * ih / 1e6 / t
-    sample = f"{n} frames of {iw}x{ih} per step (bounded sample of the {wl['batch']}-frame batch), OpenMP over images"
+    sample = (f"{n} frames of {iw}x{ih} per step ({'the full batch' if n == B else f'bounded sample of the {B}-frame batch'}; {min(B, CPU_DISTINCT)} distinct frames, "
+              f"cycled), OpenMP over images on {threads} threads")
     line = {"impl": "reference", "metric": "input Mpixels/s, " + args.workload, "value": mpx, "unit": "Mpx/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, wl, alpha, n),
-            "cpu_baseline": {"value": mpx, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": mpx, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample, "host": cpu},
             "e2e": {"value": mpx, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU restatement of the reference algorithm (oracle/ifb_oracle.c); the Rust reference (zenresize) cannot be built offline"}
     print(json.dumps(line), flush=True)
@@ -207,6 +248,156 @@ def config_dict(args, wl, alpha, batch):
 
 
 # --------------------------------------------------------------------------------------------------
+class DeviceWorkload:
+    """One workload resident in HBM of one GPU: synthetic frames, canvases, the batch object and its descriptors."""
+
+    def __init__(self, args, name, local, batch_override=0):
+        import torch
+        import imageflow_b200 as ifb
+        from imageflow_b200 import synth
+        self.torch, self.ifb, self.name = torch, ifb, name
+        wl = self.wl = dict(WORKLOADS[name])
+        dev = self.dev = torch.device("cuda", local)
+        self.alpha = alpha = wl["alpha"] if args.alpha < 0 else args.alpha
+        B = batch_override or args.batch or wl["batch"]
+        iw, ih = wl["in_wh"]; ow, oh = wl["out_wh"]
+        free, _total = torch.cuda.mem_get_info()
+        per = iw * ih * 4 + 3 * ow * oh * 4
+        if B * per > free * 0.9:
+            B = max(1, int(free * 0.9 // per))
+        self.B = B
+        self.inp = torch.empty((B, ih, iw, 4), dtype=torch.uint8, device=dev)
+        for i in range(B):
+            if args.content == "noise":
+                synth.noise_torch(iw, ih, seed=i, alpha_mode="mixed" if alpha else "opaque", device=dev, out=self.inp[i])
+            else:
+                synth.gradient_torch(iw, ih, device=dev, out=self.inp[i])
+        self.canvas0 = None
+        if wl["compose"] == 1:
+            self.canvas0 = torch.empty((B, oh, ow, 4), dtype=torch.uint8, device=dev)
+            for i in range(B):
+                synth.noise_torch(ow, oh, seed=100000 + i, alpha_mode="mixed", device=dev, out=self.canvas0[i])
+        self.out = torch.zeros((B, oh, ow, 4), dtype=torch.uint8, device=dev)
+        self.cm = ifb.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
+        self.batch = ifb.Batch(local)
+        if args.strip_cols:
+            self.batch.set_option(ifb.Batch.OPT_STRIP_COLUMNS, args.strip_cols)
+        if args.min_items >= 0:
+            self.batch.set_option(ifb.Batch.OPT_MIN_ITEMS, args.min_items)
+        self.params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))
+        jobs = [(ifb.BitmapWindow.from_torch(self.inp[i], alpha_meaningful=bool(alpha)),
+                 ifb.BitmapWindow.from_torch(self.out[i], compose=ifb.BitmapCompositing(wl["compose"])), self.params, self.cm) for i in range(B)]
+        self.descs, self.keep = self.batch.make_descs(jobs)
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def step(self):
+        if self.canvas0 is not None:
+            self.out.copy_(self.canvas0)          # the composite reads the canvas: restore it so every step does identical work
+        self.batch.enqueue(self.descs, self.stream)
+
+    def warm(self, steps, seconds=0.5):
+        t_w, n_w = time.perf_counter(), 0
+        while n_w < max(steps, 3) or time.perf_counter() - t_w < seconds:     # >= 3 steps and >= 0.5 s: clocks ramp up
+            self.step()
+            n_w += 1
+            if n_w % 8 == 0:
+                self.torch.cuda.synchronize()
+
+    def timed(self, steps):
+        """`steps` timed steps; returns (total ms between the bracketing events, per-step kernel ms, host enqueue ms)"""
+        torch = self.torch
+        k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host_ms = []
+        e0.record()
+        for k in range(steps):
+            if self.canvas0 is not None:
+                self.out.copy_(self.canvas0)
+            k_ev[k][0].record()
+            t_h = time.perf_counter()
+            self.batch.enqueue(self.descs, self.stream)
+            host_ms.append((time.perf_counter() - t_h) * 1e3)
+            k_ev[k][1].record()
+        e1.record()
+        return e0, e1, k_ev, host_ms
+
+    def roofline(self, step_ms, host_ms):
+        peak, peak_src = peaks()
+        alg = algorithmic_bytes_per_image(self.wl) * self.B
+        kern_ms = float(np.mean(step_ms))
+        achieved = alg / (kern_ms / 1e3) / 1e9
+        b = self.batch
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_min": float(np.min(step_ms)),
+                "kernel_ms_all": [round(x, 4) for x in step_ms], "host_enqueue_ms": [round(x, 3) for x in host_ms], "algorithmic_bytes_per_launch": alg,
+                "fused_jobs": b.fused_jobs, "generic_jobs": b.generic_jobs, "tile_jobs": b.tile_jobs}
+
+    def check(self, content, n_chk=2):
+        """parity spot check of the first frames against the oracle"""
+        import oracle
+        oracle.build()
+        arm = CpuArm(self.wl, content, self.alpha, n_chk)
+        _, outs = arm.run(n_chk, min(n_chk, os.cpu_count() or 1), keep_outputs=True)
+        if self.canvas0 is not None:       # rerun once from the pristine canvas so that out holds exactly one composite
+            self.out.copy_(self.canvas0)
+            self.batch.enqueue(self.descs, self.stream)
+        self.torch.cuda.synchronize()
+        mx = 0
+        for i in range(n_chk):
+            mx = max(mx, int(np.abs(self.out[i].cpu().numpy().astype(np.int16) - outs[i].astype(np.int16)).max()))
+        return {"images": n_chk, "max_abs_delta_vs_oracle": mx}
+
+    def close(self):
+        self.batch.close()
+        del self.inp, self.out, self.canvas0
+        self.torch.cuda.empty_cache()
+
+
+def git_sha():
+    try:
+        return subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip() or None
+    except Exception:
+        return None
+
+
+def lib_digest():
+    """identifies the binary a traffic measurement belongs to"""
+    import hashlib
+    import imageflow_b200
+    try:
+        return hashlib.sha256(open(imageflow_b200.LIB_PATH, "rb").read()).hexdigest()[:16]
+    except Exception:
+        return None
+
+
+def measure_traffic(args):
+    """--ncu-traffic: one launch of the workload's kernel under ncu (dram bytes read + written), written to
+    profiles/traffic_<workload>.json together with the kernel name and the digest of the library it was taken from."""
+    n = 64 if WORKLOADS[args.workload]["in_wh"][0] <= 3840 else 16
+    csv_path = os.path.join(ROOT, "gpurun_out", f"traffic_{args.workload}.csv")
+    os.makedirs(os.path.dirname(csv_path), exist_ok=True)
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none", "-k", "regex:hv_ring|fused_tile2|generic",
+           "-s", "3", "-c", "1", "--csv", "--log-file", csv_path, sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--batch", str(n),
+           "--steps", "1", "--warmup", "3", "--no-cpu", "--no-e2e", "--no-check", "--no-others"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT)
+    import csv
+    rows = [row for row in csv.reader(open(csv_path)) if len(row) > 5]
+    hdr = rows[0]
+    name_i, metric_i, val_i, unit_i = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    vals, kname = {}, None
+    for row in rows[1:]:
+        kname = row[name_i]
+        v = float(row[val_i].replace(",", ""))
+        u = row[unit_i].lower()
+        mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        vals[row[metric_i]] = v * mult
+    out = {"workload": args.workload, "kernel": kname, "images_per_launch": n, "dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
+           "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"], "git": git_sha(), "lib_sha256_16": lib_digest(),
+           "source": "bench.py --ncu-traffic: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch after 3 warm-up launches"}
+    json.dump(out, open(os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json"), "w"), indent=1)
+    print(json.dumps(out))
+
+
 def main():
     args = parse()
     wl = dict(WORKLOADS[args.workload])
@@ -214,11 +405,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return
+    if args.ncu_traffic:
+        measure_traffic(args)
+        return
 
     import torch
     import torch.distributed as dist
     import imageflow_b200 as ifb
-    from imageflow_b200 import synth
 
     if not torch.cuda.is_available() or ifb.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -226,105 +419,48 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    alpha = wl["alpha"] if args.alpha < 0 else args.alpha
-    B = args.batch or wl["batch"]
     iw, ih = wl["in_wh"]; ow, oh = wl["out_wh"]
-
-    # ---- synthetic inputs, resident in HBM
-    free, _total = torch.cuda.mem_get_info()
-    need = B * (iw * ih * 4 + 2 * ow * oh * 4)
-    if need > free * 0.9:
-        B = max(1, int(free * 0.9 // (iw * ih * 4 + 2 * ow * oh * 4)))
-    inp = torch.empty((B, ih, iw, 4), dtype=torch.uint8, device=dev)
-    for i in range(B):
-        if args.content == "noise":
-            synth.noise_torch(iw, ih, seed=i, alpha_mode="mixed" if alpha else "opaque", device=dev, out=inp[i])
-        else:
-            synth.gradient_torch(iw, ih, device=dev, out=inp[i])
-    canvas0 = None
-    if wl["compose"] == 1:
-        canvas0 = torch.empty((B, oh, ow, 4), dtype=torch.uint8, device=dev)
-        for i in range(B):
-            synth.noise_torch(ow, oh, seed=100000 + i, alpha_mode="mixed", device=dev, out=canvas0[i])
-    out = torch.zeros((B, oh, ow, 4), dtype=torch.uint8, device=dev)
-    cm = ifb.color_filter_matrix(wl["cm"]) if wl["cm"] is not None else None
-
-    batch = ifb.Batch(local)
-    if args.strip_cols:
-        batch.set_option(ifb.Batch.OPT_STRIP_COLUMNS, args.strip_cols)
-    if args.min_items >= 0:
-        batch.set_option(ifb.Batch.OPT_MIN_ITEMS, args.min_items)
-    params = ifb.ScaleAndRenderParams(w=ow, h=oh, sharpen_percent_goal=wl["sharpen"], interpolation_filter=ifb.Filter(wl["filter"]))
-    jobs = [(ifb.BitmapWindow.from_torch(inp[i], alpha_meaningful=bool(alpha)),
-             ifb.BitmapWindow.from_torch(out[i], compose=ifb.BitmapCompositing(wl["compose"])), params, cm) for i in range(B)]
-    descs, keep = batch.make_descs(jobs)
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def step():
-        if canvas0 is not None:
-            out.copy_(canvas0)          # the composite reads the canvas: restore it so every step does identical work
-        batch.enqueue(descs, stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    w = DeviceWorkload(args, args.workload, local)
+    B, alpha = w.B, w.alpha
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # started before the warm-up so that nvidia-smi's start-up cost is not in the timed region
-    t_w = time.perf_counter()
-    n_w = 0
-    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.5:     # >= 3 steps and >= 0.5 s: clocks ramp up
-        step()
-        n_w += 1
-        if n_w % 8 == 0:
-            torch.cuda.synchronize()
+    w.warm(args.warmup)
     barrier()
-    launches0 = batch.kernel_launches
+    launches0 = w.batch.kernel_launches
     if rank == 0:
         sampler.mark()
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    host_ms = []
-    e0.record()
-    for k in range(args.steps):
-        if canvas0 is not None:
-            out.copy_(canvas0)
-        k_ev[k][0].record()
-        t_h = time.perf_counter()
-        batch.enqueue(descs, stream)
-        host_ms.append((time.perf_counter() - t_h) * 1e3)
-        k_ev[k][1].record()
-    e1.record()
+    e0, e1, k_ev, host_ms = w.timed(args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = e0.elapsed_time(e1)
     step_ms = [a.elapsed_time(b) for a, b in k_ev]
-    kern_ms = float(np.mean(step_ms))
-    launches = batch.kernel_launches - launches0
+    launches = w.batch.kernel_launches - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * B * args.steps * iw * ih / 1e6 / (total_ms_max / 1e3)
 
-    # ---- roofline of the dominant kernel (one fused launch per step)
-    peak, peak_src = peaks()
-    alg = algorithmic_bytes_per_image(wl) * B
-    achieved = alg / (kern_ms / 1e3) / 1e9
-    tap_flops = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms, "kernel_ms_min": float(np.min(step_ms)),
-                "kernel_ms_all": [round(x, 4) for x in step_ms], "host_enqueue_ms": [round(x, 3) for x in host_ms], "algorithmic_bytes_per_launch": alg,
-                "fused_jobs": batch.fused_jobs, "generic_jobs": batch.generic_jobs, "tile_jobs": batch.tile_jobs}
+    # ---- roofline of the dominant kernel (one launch per step)
+    roofline = w.roofline(step_ms, host_ms)
     tfile = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile))
-            roofline["traffic"] = tj["dram_bytes_per_launch"] * (B / tj["images_per_launch"])
-            roofline["traffic_source"] = tj.get("source")
+            if tj.get("lib_sha256_16") == lib_digest():      # only a measurement of THIS binary describes this run
+                roofline["traffic"] = tj["dram_bytes_per_launch"] * (B / tj["images_per_launch"])
+                roofline["traffic_source"] = tj.get("source")
+                roofline["traffic_kernel"] = tj.get("kernel")
+            else:
+                roofline["traffic_source"] = f"profiles/traffic_{args.workload}.json was measured on another build of the library (run bench.py --ncu-traffic)"
         except Exception:
             pass
 
@@ -332,72 +468,95 @@ def main():
     check = None
     cpu_baseline = None
     if rank == 0 and not args.no_check:
-        import oracle
-        oracle.build()
-        n_chk = 2
-        _, outs = cpu_oracle_run(wl, n_chk, min(n_chk, os.cpu_count() or 1), args.content, alpha, keep_outputs=True)
-        if canvas0 is not None:       # rerun once from the pristine canvas so that out holds exactly one composite
-            out.copy_(canvas0)
-            batch.enqueue(descs, stream)
-            torch.cuda.synchronize()
-        mx = 0
-        for i in range(n_chk):
-            d = np.abs(out[i].cpu().numpy().astype(np.int16) - outs[i].astype(np.int16))
-            mx = max(mx, int(d.max()))
-        check = {"images": n_chk, "max_abs_delta_vs_oracle": mx}
+        check = w.check(args.content)
     if rank == 0 and world == 1 and not args.no_cpu:
-        import oracle
-        threads = host_threads()
-        cpu_oracle_run(wl, threads, threads, args.content, alpha)                 # warm-up (tables, page faults)
-        dt, _ = cpu_oracle_run(wl, 2 * threads, threads, args.content, alpha)
-        n = int(max(2 * threads, min(4096, round(args.cpu_seconds / max(dt, 1e-3) * 2 * threads))))
-        dt, _ = cpu_oracle_run(wl, n, threads, args.content, alpha)
-        cpu_baseline = {"value": n * iw * ih / 1e6 / dt, "unit": "Mpx/s", "cores": threads, "kind": "port",
-                        "sample": f"{n} frames of {iw}x{ih} ({dt:.1f} s), oracle/ifb_oracle.c OpenMP over images"}
+        cpu = host_cpu_info()
+        threads = cpu["threads"]
+        arm = CpuArm(wl, args.content, alpha, min(B, CPU_DISTINCT))
+        arm.run(min(B, threads), threads)                                        # warm-up (tables, page faults)
+        dt, _ = arm.run(min(B, 2 * threads), threads)
+        n = int(max(2 * threads, min(B, round(args.cpu_seconds / max(dt, 1e-3) * min(B, 2 * threads)))))
+        dt, _ = arm.run(n, threads)
+        cpu_baseline = {"value": n * iw * ih / 1e6 / dt, "unit": "Mpx/s", "cores": threads, "kind": "port", "host": cpu,
+                        "sample": f"{n} frames of {iw}x{ih} ({dt:.1f} s; {min(B, CPU_DISTINCT)} distinct frames, cycled), oracle/ifb_oracle.c OpenMP over images on {threads} threads"}
+        del arm
 
-    # ---- e2e: drop-in C ABI with pinned HOST buffers, copies inside the timed region
+    # ---- e2e: drop-in C ABI with HOST buffers, copies inside the timed region.  Headline = pinned buffers (what a caller that
+    # cares would allocate); `pageable` = plain host memory, which is what imageflow's Bitmap gives the seam today
+    # (aligned_buffer.rs:40-43).  Both are bound by the host link, not by the kernel.
     e2e = None
     if not args.no_e2e:
         ne = max(1, min(args.e2e_images, B))
-        h_in = torch.empty((ne, ih, iw, 4), dtype=torch.uint8).pin_memory()
-        h_in.copy_(inp[:ne])
-        h_out = torch.zeros((ne, oh, ow, 4), dtype=torch.uint8).pin_memory()
-        if canvas0 is not None:
-            h_cv0 = canvas0[:ne].cpu()
         os.environ["IFB200_DEVICE"] = str(local)
-        hjobs = [(ifb.BitmapWindow(h_in[i].data_ptr(), iw, ih, iw * 4, alpha_meaningful=bool(alpha)),
-                  ifb.BitmapWindow(h_out[i].data_ptr(), ow, oh, ow * 4, compose=ifb.BitmapCompositing(wl["compose"])), params) for i in range(ne)]
+        params, cm = w.params, w.cm
 
-        def e2e_step():
-            if canvas0 is not None:
-                h_out.copy_(h_cv0)
-            ifb.scale_and_render_many([(wi, wc, p, cm) for (wi, wc, p) in hjobs])
+        def e2e_leg(pinned):
+            h_in = torch.empty((ne, ih, iw, 4), dtype=torch.uint8)
+            h_out = torch.zeros((ne, oh, ow, 4), dtype=torch.uint8)
+            if pinned:
+                h_in, h_out = h_in.pin_memory(), h_out.pin_memory()
+            h_in.copy_(w.inp[:ne])
+            h_cv0 = w.canvas0[:ne].cpu() if w.canvas0 is not None else None
+            hjobs = [(ifb.BitmapWindow(h_in[i].data_ptr(), iw, ih, iw * 4, alpha_meaningful=bool(alpha)),
+                      ifb.BitmapWindow(h_out[i].data_ptr(), ow, oh, ow * 4, compose=ifb.BitmapCompositing(wl["compose"])), params) for i in range(ne)]
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
+            def e2e_step():
+                if h_cv0 is not None:
+                    h_out.copy_(h_cv0)
+                ifb.scale_and_render_many([(wi, wc, p, cm) for (wi, wc, p) in hjobs])
+
             e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            barrier()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return world * ne * args.steps * iw * ih / 1e6 / float(tt.item()), h_out
+
+        v_pinned, h_out = e2e_leg(True)
         h2d = ne * iw * ih * 4 + (ne * ow * oh * 4 if wl["compose"] == 1 else 0)
-        e2e = {"value": world * ne * args.steps * iw * ih / 1e6 / dt, "unit": "Mpx/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": ne * ow * oh * 4, "images_per_step": ne,
+        e2e = {"value": v_pinned, "unit": "Mpx/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": ne * ow * oh * 4, "images_per_step": ne,
+               "host_memory": "pinned", "bound": "host link (PCIe): the kernel is not what limits this number",
+               "h2d_gb_per_s": v_pinned * 4 / 1e3 / world,
                "api": "ifb200_scale_and_render_many (host buffers; uploads/kernels/downloads pipelined on 3 streams; returns when all results are in host memory)"}
-        if rank == 0 and check is not None and canvas0 is None:
-            mx = int(np.abs(h_out[0].numpy().astype(np.int16) - out[0].cpu().numpy().astype(np.int16)).max())
-            check["e2e_vs_device_max_abs_delta"] = mx
+        if rank == 0 and check is not None and w.canvas0 is None:
+            check["e2e_vs_device_max_abs_delta"] = int(np.abs(h_out[0].numpy().astype(np.int16) - w.out[0].cpu().numpy().astype(np.int16)).max())
+        v_pageable, _ = e2e_leg(False)
+        e2e["pageable"] = {"value": v_pageable, "unit": "Mpx/s", "host_memory": "pageable (what Bitmap buffers are: aligned_buffer.rs:40-43)"}
+
+    # ---- the other configurations of BASELINE.json, short batches on the same GPU (rank 0 of a 1-GPU run): driver-visible numbers
+    others = None
+    if rank == 0 and world == 1 and not args.no_others and args.workload == DEFAULT_WORKLOAD:
+        others = {}
+        w.close()
+        for name, nb in (("c2_4k_to_512_lanczos3", 256), ("c3_8k_to_1080p_robidoux_sharpen", 64), ("c4_1080p_to_4k_mitchell_sepia_over", 128)):
+            try:
+                ow_ = DeviceWorkload(args, name, local, batch_override=nb)
+                ow_.warm(3, seconds=0.3)
+                torch.cuda.synchronize()
+                _e0, _e1, kev, hms = ow_.timed(max(3, args.steps // 2))
+                torch.cuda.synchronize()
+                rf = ow_.roofline([a.elapsed_time(b) for a, b in kev], hms)
+                ck = ow_.check(args.content, 1) if not args.no_check else None
+                others[name] = {"images_per_step": ow_.B, "input_mpx_per_s": ow_.B * ow_.wl["in_wh"][0] * ow_.wl["in_wh"][1] / 1e6 / (rf["kernel_ms"] / 1e3),
+                                "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac", "kernel_ms", "kernel_ms_min", "algorithmic_bytes_per_launch",
+                                                                "fused_jobs", "generic_jobs", "tile_jobs")},
+                                "parity_check": ck}
+                ow_.close()
+            except Exception as e:                      # a failure here must not take the headline down with it
+                others[name] = {"error": str(e)[:300]}
 
     if rank == 0:
         line = {"metric": "input Mpixels/s, " + args.workload, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, wl, alpha, B),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "parity_check": check, "out_mpx_per_s": world * B * args.steps * ow * oh / 1e6 / (total_ms_max / 1e3)}
+                "parity_check": check, "out_mpx_per_s": world * B * args.steps * ow * oh / 1e6 / (total_ms_max / 1e3),
+                "other_workloads": others, "git": git_sha()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <tuple>
 #include <unordered_map>
@@ -39,6 +40,23 @@ struct Err {
     int c_ = (e_ == cudaErrorMemoryAllocation) ? IFB200_ERR_OUT_OF_MEMORY : \
              (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver || e_ == cudaErrorInvalidDevice) ? IFB200_ERR_NO_DEVICE : IFB200_ERR_CUDA; \
     IFB_THROW(c_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+
+// Makes `dev` the calling thread's current device for the lifetime of the object and restores the caller's device afterwards:
+// the library never leaves a caller with a different current device than it came with.
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        cudaError_t e = cudaSetDevice(dev);
+        if (e != cudaSuccess) {
+            char b[256]; snprintf(b, sizeof b, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(e));
+            throw std::runtime_error(b);
+        }
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
 
 // adds the lifetime of the object, in seconds, to `acc` (host-side profile of the enqueue path; inclusive, nesting allowed)
 struct Tick {
@@ -66,6 +84,9 @@ int guarded(char* err, size_t cap, F&& f) {
     } catch (const std::bad_alloc&) {
         put_err(err, cap, "host allocation failed");
         return IFB200_ERR_OUT_OF_MEMORY;
+    } catch (const std::runtime_error& e) {                   // DeviceScope: the device could not be made current
+        put_err(err, cap, e.what());
+        return IFB200_ERR_CUDA;
     } catch (const std::exception& e) {
         put_err(err, cap, e.what());
         return IFB200_ERR_INVALID_STATE;
@@ -432,21 +453,33 @@ struct ifb200_batch {
         arena_chunks.clear(); arena_used = arena_cap = 0;
     }
 
+    // Pinned staging for asynchronous uploads.  A slot is busy until the event recorded after its copy has completed.  Events are
+    // only queried when no free slot is large enough (an enqueue with thousands of cold plans would otherwise query every slot
+    // for every plan), and small requests share 1 MiB slots instead of getting a cudaMallocHost each.
     void* stage(size_t bytes, cudaEvent_t* ev_out) {
         Tick tk(prof.stage);
-        for (auto& s : pinned) {
-            if (s.used && cudaEventQuery(s.ev) == cudaSuccess) s.used = false;
+        auto take = [&]() -> PinnedSlot* {
+            PinnedSlot* best = nullptr;
+            for (auto& s : pinned) if (!s.used && s.cap >= bytes && (!best || s.cap < best->cap)) best = &s;
+            return best;
+        };
+        PinnedSlot* s = take();
+        if (!s) {
+            for (auto& q : pinned) if (q.used && cudaEventQuery(q.ev) == cudaSuccess) q.used = false;
+            s = take();
         }
-        for (auto& s : pinned) if (!s.used && s.cap >= bytes) { s.used = true; *ev_out = s.ev; return s.p; }
-        PinnedSlot s;
-        s.cap = std::max<size_t>(bytes, 1 << 16);
-        CUDA_OK(cudaMallocHost(&s.p, s.cap));
-        CUDA_OK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
-        ++prof.pinned_allocs;
-        s.used = true;
-        pinned.push_back(s);
-        *ev_out = s.ev;
-        return s.p;
+        if (!s) {
+            PinnedSlot n;
+            n.cap = std::max<size_t>(bytes, (size_t)1 << 20);
+            CUDA_OK(cudaMallocHost(&n.p, n.cap));
+            CUDA_OK(cudaEventCreateWithFlags(&n.ev, cudaEventDisableTiming));
+            ++prof.pinned_allocs;
+            pinned.push_back(n);
+            s = &pinned.back();
+        }
+        s->used = true;
+        *ev_out = s->ev;
+        return s->p;
     }
 
     static Key key_of(const ifb200_resample_desc& d) {
@@ -508,7 +541,7 @@ struct ifb200_batch {
             }
         };
         std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker);
+        try { for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker); } catch (...) {}      // fewer threads than wanted: the rest do the work
         worker();
         for (auto& th : pool) th.join();
         for (size_t w = 0; w < work.size(); ++w) {
@@ -523,14 +556,15 @@ void DevBlob::commit(ifb200_batch* b, cudaStream_t st) {
     if (!n) return;
     Tick tk(b->prof.upload);
     ++b->prof.commits; b->prof.staged_bytes += n;
-    p = b->table_alloc(n);
+    if (!ready) CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    uint8_t* dst = b->table_alloc(n);
     cudaEvent_t ev;
     void* pin = b->stage(n, &ev);
     { Tick tm(b->prof.memcpy_); memcpy(pin, host.data(), n); }
-    CUDA_OK(cudaMemcpyAsync(p, pin, n, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(dst, pin, n, cudaMemcpyHostToDevice, st));
     CUDA_OK(cudaEventRecord(ev, st));                     // releases the pinned slot
-    CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventRecord(ready, st));
+    p = dst;                                              // only a blob whose upload was enqueued counts as committed
     up_stream = st;
     host.clear(); host.shrink_to_fit();
 }
@@ -627,7 +661,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     if (n == 0) return;
     Tick tk_all(b->prof.enqueue);
     host_tables();
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     for (size_t i = 0; i < n; ++i) validate(descs[i]);
     { Tick tk(b->prof.plans); b->prebuild_plans(descs, n); }
     // group jobs by (plan, kernel class)
@@ -638,8 +672,9 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         Plan* pp; { Tick tk(b->prof.plans); pp = &b->plan_for(descs[i]); }
         Plan& p = *pp;
         const ifb200_resample_desc& d = descs[i];
-        // TMA rows: the pitch must be a multiple of 16 bytes (any Bitmap::create_u8 buffer: 64-byte padded rows)
-        bool ring = p.hv_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0);
+        // TMA boxes: 16-byte aligned origin (a window that starts at pixel 1..3 of a 16-byte group takes the other kernels) and a
+        // pitch that is a multiple of 16 bytes (any Bitmap::create_u8 buffer: 64-byte padded rows)
+        bool ring = p.hv_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
         const int ch = d.alpha_meaningful ? 4 : 3;
         const bool upscale = p.out_h >= p.in_h && p.out_w >= p.in_w;
         if (ring && !(p.tile_ok && upscale) && !hv_host_ready(p, b->strip_cols)) ring = false;   // windows wider than the weight table
@@ -795,7 +830,7 @@ void color_matrix_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t 
     if (!dev_px || !m) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
     if (w == 0 || h == 0) return;
     if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     cudaEvent_t ev;
     float* hm = static_cast<float*>(b->stage(20 * sizeof(float), &ev));
     for (int c = 0; c < 4; ++c) {
@@ -821,7 +856,7 @@ void apply_matte_locked(ifb200_batch* b, uint8_t* dev_px, uint32_t w, uint32_t h
     if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad stride");
     const uint64_t total = (uint64_t)w * h;
     if (total > 0xffffffffull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap too large");
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     const uint32_t m = (uint32_t)matte[0] | ((uint32_t)matte[1] << 8) | ((uint32_t)matte[2] << 16) | ((uint32_t)matte[3] << 24);
     const unsigned blocks = (unsigned)std::min<uint64_t>((total + 255) / 256, 148ull * 16);
     apply_matte_kernel<<<blocks, 256, 0, st>>>(dev_px, w, h, stride, m, b->tables);
@@ -841,12 +876,15 @@ void transpose_locked(ifb200_batch* b, const uint8_t* from, uint32_t from_stride
     if ((from_stride & 3) || (to_stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "strides must be multiples of 4 bytes");
     if (from_stride < w * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "from_stride(%u) < width(%u)", from_stride / 4, w);
     if (to_stride < h * 4ull) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "to_stride(%u) < height(%u)", to_stride / 4, h);
-    CUDA_OK(cudaSetDevice(b->device));
-    dim3 grid((w + 31) / 32, (h + 31) / 32);
-    if (grid.y > 65535u) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap too tall for transposition (%u rows)", h);
-    transpose_bgra8_kernel<<<grid, dim3(32, 8), 0, st>>>(from, from_stride, w, h, to, to_stride);
-    CUDA_OK(cudaGetLastError());
-    b->launches++;
+    DeviceScope dev_scope_(b->device);
+    const uint32_t rows_per_launch = 65535u * 32u;           // grid.y is bounded; bitmaps are not
+    for (uint32_t y0 = 0; y0 < h; y0 += rows_per_launch) {
+        const uint32_t rows = std::min(rows_per_launch, h - y0);
+        dim3 grid((w + 31) / 32, (rows + 31) / 32);
+        transpose_bgra8_kernel<<<grid, dim3(32, 8), 0, st>>>(from + (size_t)y0 * from_stride, from_stride, w, rows, to + (size_t)y0 * 4, to_stride);
+        CUDA_OK(cudaGetLastError());
+        b->launches++;
+    }
 }
 void flip_locked(ifb200_batch* b, bool vertical, uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, cudaStream_t st) {
     if (!px) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null bitmap pointer");
@@ -856,7 +894,7 @@ void flip_locked(ifb200_batch* b, bool vertical, uint8_t* px, uint32_t w, uint32
     const uint32_t we = v4 ? w / 4 : w;
     const uint64_t elems = vertical ? (uint64_t)(h / 2) * we : (uint64_t)(v4 ? (we + 1) / 2 : we / 2) * h;
     if (elems == 0) return;
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     const unsigned blocks = (unsigned)std::min<uint64_t>((elems + 255) / 256, 148u * 16u);
     if (vertical) {
         if (v4) flip_vertical_bgra8_kernel<uint4><<<blocks, 256, 0, st>>>(px, we, h, stride);
@@ -876,7 +914,7 @@ void block_scale_locked(ifb200_batch* b, const uint8_t* in, uint32_t in_stride, 
     if (n < 1 || n > 7) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "block scalers exist for 1x1 .. 7x7 (got %d)", n);
     if (blocks_x == 0 || blocks_y == 0) return;
     if (in_stride < blocks_x * 8ull || out_stride < (uint64_t)blocks_x * (uint32_t)n) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a row of blocks");
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     const uint32_t gx = (blocks_x + 31u) / 32u;
     for (uint32_t y0 = 0; y0 < blocks_y; y0 += 65535u) {             // grid.y is bounded; planes are not
         const uint32_t cnt = std::min(65535u, blocks_y - y0);
@@ -894,7 +932,7 @@ void white_balance_locked(ifb200_batch* b, uint8_t* px, uint32_t w, uint32_t h, 
     if (w == 0 || h == 0) return;
     if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
     if (threshold != threshold) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "threshold is NaN");
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     const double low = (double)(threshold < 0.0f ? 0.006f : threshold);      // f64::from(f32)
     unsigned long long* hist = nullptr;
     CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&hist), 768 * sizeof(unsigned long long) + 768, st));
@@ -926,20 +964,25 @@ void detect_content_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint3
     if (threshold > 0x7fffffffu) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "threshold out of range");
     rect[0] = 0; rect[1] = 0; rect[2] = w; rect[3] = h;
     if (w < 3 || h < 3) return;                              // whitespace.rs:288-290
-    CUDA_OK(cudaSetDevice(b->device));
+    DeviceScope dev_scope_(b->device);
     const size_t n = (size_t)w * h;
+    cudaEvent_t ev;
+    uint8_t* codes = static_cast<uint8_t*>(b->stage(n, &ev));          // before any device allocation: may throw
     uint8_t* dcodes = nullptr;
     CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dcodes), n, st));
-    dim3 grid((w + 31) / 32, (h + 7) / 8);
-    if (grid.y > 65535u) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bitmap taller than 524280 rows");
-    whitespace_codes_kernel<<<grid, dim3(32, 8), 0, st>>>(px, w, h, stride, alpha_meaningful ? 1u : 0u, (int)threshold, dcodes);
-    CUDA_OK(cudaGetLastError());
-    b->launches++;
-    cudaEvent_t ev;
-    uint8_t* codes = static_cast<uint8_t*>(b->stage(n, &ev));
+    AsyncFree dcodes_guard{dcodes, st};
+    // grid.y is bounded: tall bitmaps go in chunks of rows (a chunk's first and last rows look one row up / down: the kernel
+    // takes the whole bitmap and the chunk's first row)
+    const uint32_t rows_per_launch = 65535u * 8u;
+    for (uint32_t y0 = 0; y0 < h; y0 += rows_per_launch) {
+        const uint32_t rows = std::min(rows_per_launch, h - y0);
+        dim3 grid((w + 31) / 32, (rows + 7) / 8);
+        whitespace_codes_kernel<<<grid, dim3(32, 8), 0, st>>>(px, w, h, stride, alpha_meaningful ? 1u : 0u, (int)threshold, dcodes, y0);
+        CUDA_OK(cudaGetLastError());
+        b->launches++;
+    }
     CUDA_OK(cudaMemcpyAsync(codes, dcodes, n, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(ev, st));
-    CUDA_OK(cudaFreeAsync(dcodes, st));
     CUDA_OK(cudaStreamSynchronize(st));
     if (!ifb::detect_content_from_codes(codes, w, h, rect, nullptr)) IFB_THROW(IFB200_ERR_INVALID_STATE, "whitespace walk failed");
 }
@@ -970,7 +1013,7 @@ ifb200_batch* create_batch(int device) {
     if (e != cudaSuccess || ndev == 0)
         IFB_THROW(IFB200_ERR_NO_DEVICE, "no usable CUDA device (%s); libifb200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, ndev - 1);
-    CUDA_OK(cudaSetDevice(device));
+    DeviceScope dev_scope_(device);
     std::unique_ptr<ifb200_batch> b(new ifb200_batch());
     b->device = device;
     CUDA_OK(cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking));
@@ -1131,7 +1174,7 @@ int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, 
         };
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> pool;
-        for (int t = 1; t < threads; ++t) pool.emplace_back(worker, t);
+        try { for (int t = 1; t < threads; ++t) pool.emplace_back(worker, t); } catch (...) {}           // fewer threads than wanted: the rest do the work
         worker(0);
         for (auto& th : pool) th.join();
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1246,14 +1289,14 @@ int ifb200_batch_block_scale(ifb200_batch* b, const uint8_t* dev_in, uint32_t in
 int ifb200_batch_sync(ifb200_batch* b, char* err, size_t cap) {
     return guarded(err, cap, [&] {
         if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         CUDA_OK(cudaStreamSynchronize(b->own_stream));
     });
 }
 
 void ifb200_batch_destroy(ifb200_batch* b) {
     if (!b) return;
-    try { cudaSetDevice(b->device); cudaDeviceSynchronize(); delete b; } catch (...) {}
+    try { DeviceScope dev_scope_(b->device); cudaDeviceSynchronize(); delete b; } catch (...) {}
 }
 
 int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
@@ -1316,7 +1359,7 @@ int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t 
         validate(*desc);
         HostCtx& c = host_ctx();
         std::lock_guard<std::mutex> lk(c.batch->mu);
-        CUDA_OK(cudaSetDevice(c.batch->device));
+        DeviceScope dev_scope_(c.batch->device);
         host_job_async(c, c.slot[0], *desc);
         CUDA_OK(cudaStreamSynchronize(c.slot[0].stream));
     });
@@ -1328,7 +1371,7 @@ int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, ch
         for (size_t i = 0; i < n; ++i) validate(descs[i]);      // all-or-nothing argument errors, before any pixel moves
         HostCtx& c = host_ctx();
         std::lock_guard<std::mutex> lk(c.batch->mu);
-        CUDA_OK(cudaSetDevice(c.batch->device));
+        DeviceScope dev_scope_(c.batch->device);
         try {
             for (size_t i = 0; i < n; ++i) host_job_async(c, c.slot[i % kHostSlots], descs[i]);
         } catch (...) {
@@ -1348,7 +1391,7 @@ int ifb200_apply_matte_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t strid
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
@@ -1371,7 +1414,7 @@ int ifb200_transpose_bgra8(const uint8_t* from, uint32_t from_stride, uint32_t w
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pin = ((size_t)w * 4 + 63) / 64 * 64, pout = ((size_t)h * 4 + 63) / 64 * 64;
@@ -1407,7 +1450,7 @@ int ifb200_detect_content_bgra8(const uint8_t* px, uint32_t w, uint32_t h, uint3
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
@@ -1427,7 +1470,7 @@ int ifb200_block_scale_u8(const uint8_t* in, uint32_t in_stride, uint32_t blocks
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pin = ((size_t)blocks_x * 8 + 63) / 64 * 64, pout = ((size_t)blocks_x * n + 63) / 64 * 64;
@@ -1448,7 +1491,7 @@ int ifb200_white_balance_srgb_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
@@ -1468,7 +1511,7 @@ static int flip_host(bool vertical, uint8_t* px, uint32_t w, uint32_t h, uint32_
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;
@@ -1490,7 +1533,7 @@ int ifb200_color_matrix_bgra8(uint8_t* px, uint32_t w, uint32_t h, uint32_t stri
         HostCtx& c = host_ctx();
         ifb200_batch* b = c.batch;
         std::lock_guard<std::mutex> lk(b->mu);
-        CUDA_OK(cudaSetDevice(b->device));
+        DeviceScope dev_scope_(b->device);
         HostSlot& sl = c.slot[0];
         cudaStream_t st = sl.stream;
         const size_t pitch = ((size_t)w * 4 + 63) / 64 * 64;

@@ -77,10 +77,12 @@ namespace hv {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float lds_lut(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }          // tables: read-only after setup
 __device__ __forceinline__ uint32_t lds_lut_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+// weight records: volatile, so that they are fetched where the chunk that uses them starts (hoisted to the top of a stage, the 16
+// records of its four chunks would occupy 64 registers)
 __device__ __forceinline__ float4 lds_w4(uint32_t a) {
-    float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+    float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
 }
-__device__ __forceinline__ float2 lds_w2(uint32_t a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ float2 lds_w2(uint32_t a) { float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
     uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory"); return v;
@@ -96,6 +98,11 @@ __device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffff
 __device__ __forceinline__ uint32_t bcast0(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ void warp_sync() { __syncwarp(); }
+__device__ __forceinline__ bool elect_one() {              // true in exactly one lane of the (converged) warp
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(is_leader));
+    return is_leader != 0;
+}
 __device__ __forceinline__ void cta_sync() { __syncthreads(); }
 __device__ __forceinline__ uint32_t atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
@@ -208,10 +215,14 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                uint32_t* __restrict__ counters) {
     using C = HvCfg<AV, CH>;
     constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages;
+    constexpr uint32_t kWStage = 16u * AVP * 4u * 2u;                      // address step of the H weights per stage: 16 records, every other 128 bytes a hole
     IFB_HV_DYNAMIC_SMEM(hv_smem);
     const uint32_t sb = hv::smem_u32(hv_smem);
     const uint32_t lut = sb + ((0x10000u - (sb & 0xffffu)) & 0xffffu);     // window address of the LUT block: low 16 bits are zero
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // A value that is the same in every lane, rebuilt from a warp vote: the compiler then KNOWS it is warp-uniform and keeps it --
+    // and every loop counter, address and branch derived from it -- on the uniform datapath (no divergence bookkeeping).
+    auto uni = [&](uint32_t v) -> uint32_t { return hv::ballot((v >> lane) & 1u); };
     uint32_t wb;                                                           // this warp's block: stages, exchange buffer, mbarriers
     {
         const uint32_t a0 = (sb + 1023u) & ~1023u;
@@ -237,59 +248,66 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
 
     const uint32_t lut_lane = lut + (uint32_t)lane * 4u;
     const uint32_t lane4 = ((uint32_t)lane * 4u) | ((lut >> 16) << 8);     // PRMT operand: byte 0 = lane*4, bytes 1..2 = window bits 16..31
-    const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;                // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3
-    const uint32_t my_row = (uint32_t)lane * 64u;
-    const uint32_t n_items = n_jobs * (uint32_t)pl.n_bands;
+    // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3; this lane's row starts at lane * 64: where chunk k of "my row" lies
+    const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;
+    const uint32_t row_off[4] = {(uint32_t)lane * 64u + (0u ^ swz), (uint32_t)lane * 64u + (16u ^ swz), (uint32_t)lane * 64u + (32u ^ swz), (uint32_t)lane * 64u + (48u ^ swz)};
+    const uint32_t n_bands = (uint32_t)pl.n_bands;
+    const uint32_t n_items = n_jobs * n_bands;
     const uint32_t lutw = lut + 128u * 256u + 128u;                        // hole 128: the strip's H weights
+    const bool leader = hv::elect_one();                                   // the lane that talks to the TMA unit
 
     for (int sv = 0; sv < pl.n_strips; ++sv) {
         const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
-        const HvStripDev sd = pl.strips[s];
         hv::cta_sync();                                                    // every warp is done with the previous strip's weights (first time: tables filled)
+        const HvStripDev sd_ = pl.strips[s];
+        const int sX0 = (int)uni((uint32_t)sd_.X0), sX1 = (int)uni((uint32_t)sd_.X1), sXf = (int)uni((uint32_t)sd_.Xf), sH0 = (int)uni((uint32_t)sd_.hslot0);
+        const int sK0 = (int)uni((uint32_t)sd_.k0), nst = (int)uni((uint32_t)sd_.nst);
         {   // H weights of the strip: 16-byte units u -> hole 128 + u/8, offset (u%8)*16
             const float4* __restrict__ src = reinterpret_cast<const float4*>(pl.hw + (size_t)s * C::kCapPx * AVP);
-            const int n16 = sd.nst * 16 * AVP / 4;
+            const int n16 = nst * 16 * AVP / 4;
             for (int u = t; u < n16; u += C::kThreads) hv::sts_f32x4(lutw + ((uint32_t)(u >> 3) << 8) + ((uint32_t)(u & 7) << 4), hv::ldg(src + u));
         }
         hv::cta_sync();
         const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 32);
-        const uint32_t ncols = (uint32_t)(sd.X1 - sd.X0);
+        const uint32_t ncols = (uint32_t)(sX1 - sX0);
 
         for (;;) {
             uint32_t item = 0;
             if (lane == 0) item = hv::atomic_inc(counters + s);
-            item = hv::bcast0(item);
+            item = uni(hv::bcast0(item));
             if (item >= n_items) break;
-            const uint32_t job_i = item / (uint32_t)pl.n_bands, band_i = item - job_i * (uint32_t)pl.n_bands;
+            const uint32_t job_i = item / n_bands, band_i = item - job_i * n_bands;
             const JobDev& job = jobs[job_i];
             const HvTmap* tm = tmaps + job_i;
-            const HvBandDev bd = pl.bands[band_i];
-            const uint32_t flags = job.flags;
-            const int nrb = (bd.nrows + 31) >> 5;
-            const int x_origin = sd.k0 + (int)job.in_xoff;
+            const HvBandDev bd_ = pl.bands[band_i];
+            const int bY0 = (int)uni((uint32_t)bd_.Y0), bY1 = (int)uni((uint32_t)bd_.Y1), bYf = (int)uni((uint32_t)bd_.Yf), bV0 = (int)uni((uint32_t)bd_.vslot0);
+            const int bJ0 = (int)uni((uint32_t)bd_.j0), bNr = (int)uni((uint32_t)bd_.nrows);
+            const uint32_t flags = uni(job.flags);
+            const int nrb = (bNr + 31) >> 5;
+            const int x_origin = sK0 + (int)uni(job.in_xoff);
 
             // ---- TMA pipeline state: stages are numbered row block by row block
-            const int total_stages = nrb * sd.nst;
+            const int total_stages = nrb * nst;
             int is_n = 0, is_x = 0, is_y = 0, is_s = 0;                    // next stage to issue: index, stage within row block, row block, ring slot
             auto issue = [&]() {
                 hv::warp_sync();                                           // every lane has read what the refilled slot held
-                if (lane == 0) {
+                if (leader) {
                     const uint32_t bar = mb + 8u * (uint32_t)is_s;
                     hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
-                    hv::tma_load_box(wb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bd.j0 + is_y * 32, bar);
+                    hv::tma_load_box(wb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
+#if IFB_HV_PREFETCH_AHEAD > 0
+                    // every fourth stage: one box IFB_HV_PREFETCH_AHEAD stages further on its way into L2 (the descriptor promotes
+                    // every request to its 256-byte line, i.e. to the width of four stages)
+                    if ((is_x & 3) == 0) {
+                        int px = is_x + IFB_HV_PREFETCH_AHEAD, py = is_y;
+                        if (px >= nst) { px -= nst; ++py; }
+                        if (py < nrb) hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32);
+                    }
+#endif
                 }
                 ++is_n; is_s = is_s + 1 == S ? 0 : is_s + 1;
-                if (++is_x == sd.nst) { is_x = 0; ++is_y; }
+                if (++is_x == nst) { is_x = 0; ++is_y; }
             };
-#if IFB_HV_PREFETCH_AHEAD > 0
-            int pf_n = 0, pf_x = 0, pf_y = 0;
-            auto prefetch = [&]() {
-                if (lane == 0) hv::tma_prefetch_box(tm, x_origin + pf_x * 16, bd.j0 + pf_y * 32);
-                ++pf_n;
-                if (++pf_x == sd.nst) { pf_x = 0; ++pf_y; }
-            };
-            for (int i = 0; i < IFB_HV_PREFETCH_AHEAD && pf_n < total_stages; ++i) prefetch();
-#endif
             for (int i = 0; i < S - 1 && is_n < total_stages; ++i) issue();
             int cs_s = 0;                                                  // ring slot of the stage being consumed
 
@@ -300,127 +318,116 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) accV[gq][c][q] = make_float2(0.0f, 0.0f);
-            int Yc = bd.Yf, vslot = bd.vslot0;                             // next output row to complete at the start of the row block, and its slot
-            uint8_t* const out_col = job.out + (size_t)(sd.X0 + lane) * 4;
+            int Yc = bYf, vslot = bV0;                                     // next output row to complete at the start of the row block, and its slot
+            uint8_t* const out_col = job.out + (size_t)(sX0 + lane) * 4;
             const size_t out_stride = job.out_stride;
 
             for (int rb = 0; rb < nrb; ++rb) {
-                const int row0 = bd.j0 + rb * 32;
-                const int nr = min(32, bd.nrows - rb * 32);
+                const int row0 = bJ0 + rb * 32;
+                const int nr = min(32, bNr - rb * 32);
                 uint32_t VM1, VM2, vtot;
                 {
                     const uint32_t vd = lane < nr ? (uint32_t)hv::ldg(pl.vdone + row0 + lane) : 0u;
-                    VM1 = hv::ballot(vd >= 1u); VM2 = hv::ballot(vd >= 2u); vtot = hv::warp_sum(vd);
+                    VM1 = hv::ballot(vd >= 1u); VM2 = hv::ballot(vd >= 2u); vtot = uni(hv::warp_sum(vd));
                 }
                 float2 accH[CH][NP];
 #pragma unroll
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) accH[c][q] = make_float2(0.0f, 0.0f);
-                int Xc = sd.Xf, hslot = sd.hslot0;
+                int Xc = sXf, hslot = sH0;
                 uint32_t colbuf = 0, grp = 0;
                 uint32_t wptr = xb + (uint32_t)lane * 4u;                  // where the next completed column goes
                 uint32_t HM1 = 0, HM2 = 0;
+                uint32_t wst = lutw;                                       // H weights of the current stage
 
-                // first stage of the row block
-                if (is_n < total_stages) issue();
-#if IFB_HV_PREFETCH_AHEAD > 0
-                if (pf_n < total_stages) prefetch();
-#endif
-                hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
-                par ^= 1u << cs_s;
-                uint32_t sbase = wb + (uint32_t)cs_s * C::kStageBytes + my_row;
-                uint4 raw = hv::lds_u32x4(sbase + swz);                    // chunk 0 (physical chunk = 0 ^ swizzle)
-
-                const int nchunks = sd.nst * 4;
-                for (int cc = 0; cc < nchunks; ++cc) {
-                    // ---- completion masks of the next 32 pixels
-                    if ((cc & 7) == 0) {
-                        const uint32_t hd = (uint32_t)hv::ldg(hdone + cc * 4 + lane);
+                for (int st = 0; st < nst; ++st, wst += kWStage) {
+                    // ---- stage top: keep the ring full, wait for this stage's box, pull "my row" (16 pixels) into registers
+                    if (is_n < total_stages) issue();                      // refills the slot consumed two stages ago
+                    hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                    par ^= 1u << cs_s;
+                    uint4 raw[4];
+                    {
+                        const uint32_t sbase = wb + (uint32_t)cs_s * C::kStageBytes;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) raw[k] = hv::lds_u32x4(sbase + row_off[k]);
+                    }
+                    cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
+                    if ((st & 1) == 0) {                                   // completion masks of the next 32 pixels
+                        const uint32_t hd = (uint32_t)hv::ldg(hdone + st * 16 + lane);
                         HM1 = hv::ballot(hd >= 1u); HM2 = hv::ballot(hd >= 2u);
                     }
-                    // ---- sRGB bytes -> working floats of the chunk's four pixels: window address = LUT | byte << 8 | lane << 2
+                    const uint32_t hm = (HM1 >> ((st & 1) * 16)) & 0xffffu, hm2 = (HM2 >> ((st & 1) * 16)) & 0xffffu;
+
+                    // ---- the stage's sixteen pixels: straight-line code, entered at pixel `pos` (0 at the top of a stage).  A chunk of
+                    // four pixels starts by converting them (12 table look-ups) and fetching their weight records; a chunk without a
+                    // completing column then runs 24 packed multiply-adds and falls into the next chunk; otherwise each pixel checks
+                    // its bit of the completion mask and, if set, leaves for the (single) completion code, which re-enters the
+                    // sequence behind that pixel.  Everything that steers this is warp-uniform.
                     float p[4][CH];
-                    {
-                        const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t v = w4[i];
-                            p[i][0] = hv::lds_lut(hv::prmt(v, lane4, 0x6504));
-                            p[i][1] = hv::lds_lut(hv::prmt(v, lane4, 0x6514));
-                            p[i][2] = hv::lds_lut(hv::prmt(v, lane4, 0x6524));
-                            if (CH == 4) {
-                                // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
-                                const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
-                                p[i][0] = __fmul_rn(p[i][0], af); p[i][1] = __fmul_rn(p[i][1], af); p[i][2] = __fmul_rn(p[i][2], af);
-                                p[i][CH - 1] = af;
-                            }
-                        }
-                    }
-                    // ---- weights of the four source columns, by ring slot (broadcast reads)
                     float2 wq[4][NP];
-                    {
-                        const uint32_t wa = AV == 4 ? lutw + ((uint32_t)(cc >> 1) << 8) + ((uint32_t)(cc & 1) << 6) : lutw + ((uint32_t)cc << 8);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 q4 = hv::lds_w4(wa + (uint32_t)i * (AVP * 4));
-                            wq[i][0] = make_float2(q4.x, q4.y); wq[i][1] = make_float2(q4.z, q4.w);
-                            if (AV == 6) wq[i][NP - 1] = hv::lds_w2(wa + (uint32_t)i * (AVP * 4) + 16u);
-                        }
-                    }
-                    // ---- the next chunk's pixels: requested now, used one iteration later
-                    if (cc + 1 < nchunks) {
-                        if (((cc + 1) & 3) == 0) {                         // it starts a new stage
-                            cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
-                            if (is_n < total_stages) issue();              // refills the slot consumed two stages ago (its reads are long done)
-#if IFB_HV_PREFETCH_AHEAD > 0
-                            if (pf_n < total_stages) prefetch();
-#endif
-                            hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
-                            par ^= 1u << cs_s;
-                            sbase = wb + (uint32_t)cs_s * C::kStageBytes + my_row;
-                        }
-                        raw = hv::lds_u32x4(sbase + ((((uint32_t)(cc + 1) & 3u) << 4) ^ swz));
-                    } else if (rb + 1 < nrb) {
-                        cs_s = cs_s + 1 == S ? 0 : cs_s + 1;               // the next row block's first stage is waited for at its top
-                    }
-                    // ---- multiply-adds, pixel by pixel, re-entered after every completion
-                    const uint32_t nib = (HM1 >> ((cc & 7) * 4)) & 15u, nib2 = (HM2 >> ((cc & 7) * 4)) & 15u;
-                    uint32_t start = 0;
-                    do {
-                        const uint32_t m = nib >> start;
-                        const uint32_t stop = m ? start + (uint32_t)__ffs((int)m) : 4u;     // pixels [start, stop) run, then the columns ending at stop-1 complete
+                    uint32_t pos = 0;
+#define IFB_HV_TOP(K_) { \
+    const uint32_t w4_[4] = {raw[K_].x, raw[K_].y, raw[K_].z, raw[K_].w}; \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
+        const uint32_t v = w4_[i]; \
+        p[i][0] = hv::lds_lut(hv::prmt(v, lane4, 0x6504)); p[i][1] = hv::lds_lut(hv::prmt(v, lane4, 0x6514)); p[i][2] = hv::lds_lut(hv::prmt(v, lane4, 0x6524)); \
+        if (CH == 4) { /* alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered */ \
+            const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f); \
+            p[i][0] = __fmul_rn(p[i][0], af); p[i][1] = __fmul_rn(p[i][1], af); p[i][2] = __fmul_rn(p[i][2], af); p[i][CH - 1] = af; } } \
+    const uint32_t wa_ = wst + (AV == 4 ? (uint32_t)((K_) >> 1) * 256u + (uint32_t)((K_) & 1) * 64u : (uint32_t)(K_) * 256u); \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
+        const float4 q4 = hv::lds_w4(wa_ + (uint32_t)i * (AVP * 4)); \
+        wq[i][0] = make_float2(q4.x, q4.y); wq[i][1] = make_float2(q4.z, q4.w); \
+        if (AV == 6) wq[i][NP - 1] = hv::lds_w2(wa_ + (uint32_t)i * (AVP * 4) + 16u); } }
 #define IFB_HV_PX(I_) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { const float2 vv = make_float2(p[I_][c], p[I_][c]); \
                         _Pragma("unroll") for (int q = 0; q < NP; ++q) accH[c][q] = hv::ffma2(wq[I_][q], vv, accH[c][q]); } }
-                        switch (start) {
-                        case 0: IFB_HV_PX(0) if (stop == 1u) break;
-                        case 1: IFB_HV_PX(1) if (stop == 2u) break;
-                        case 2: IFB_HV_PX(2) if (stop == 3u) break;
-                        default: IFB_HV_PX(3)
-                        }
+#define IFB_HV_CHUNK(K_, LA_, LB_, LC_, LD_, LNEXT_) \
+    LA_: IFB_HV_TOP(K_) \
+         if (((hm >> (4 * (K_))) & 15u) == 0u) { IFB_HV_PX(0) IFB_HV_PX(1) IFB_HV_PX(2) IFB_HV_PX(3) goto LNEXT_; } \
+         IFB_HV_PX(0) if ((hm >> (4 * (K_) + 0)) & 1u) { pos = 4 * (K_) + 1; goto hv_complete; } \
+    LB_: IFB_HV_PX(1) if ((hm >> (4 * (K_) + 1)) & 1u) { pos = 4 * (K_) + 2; goto hv_complete; } \
+    LC_: IFB_HV_PX(2) if ((hm >> (4 * (K_) + 2)) & 1u) { pos = 4 * (K_) + 3; goto hv_complete; } \
+    LD_: IFB_HV_PX(3) if ((hm >> (4 * (K_) + 3)) & 1u) { pos = 4 * (K_) + 4; goto hv_complete; } \
+         goto LNEXT_;
+                hv_dispatch:
+                    switch (pos) {
+                    case 0: goto hv_p0; case 1: goto hv_p1; case 2: goto hv_p2; case 3: goto hv_p3;
+                    case 4: goto hv_p4; case 5: goto hv_p5; case 6: goto hv_p6; case 7: goto hv_p7;
+                    case 8: goto hv_p8; case 9: goto hv_p9; case 10: goto hv_p10; case 11: goto hv_p11;
+                    case 12: goto hv_p12; case 13: goto hv_p13; case 14: goto hv_p14; case 15: goto hv_p15;
+                    default: goto hv_stage_done;
+                    }
+                    IFB_HV_CHUNK(0, hv_p0, hv_p1, hv_p2, hv_p3, hv_p4)
+                    IFB_HV_CHUNK(1, hv_p4, hv_p5, hv_p6, hv_p7, hv_p8)
+                    IFB_HV_CHUNK(2, hv_p8, hv_p9, hv_p10, hv_p11, hv_p12)
+                    IFB_HV_CHUNK(3, hv_p12, hv_p13, hv_p14, hv_p15, hv_stage_done)
+#undef IFB_HV_CHUNK
+#undef IFB_HV_TOP
 #undef IFB_HV_PX
-                        if (m) {
-                            uint32_t n_done = 1u;
-                            if ((nib2 >> (stop - 1u)) & 1u) n_done = (uint32_t)hv::ldg(hdone + cc * 4 + (int)stop - 1);
-                            for (uint32_t e = 0; e < n_done; ++e) {
-                                // ---- output column Xc is complete: park it (if it belongs to the strip) and free its slot
-                                const bool keep = (uint32_t)(Xc - sd.X0) < ncols;
-                                switch (hslot) {
+                hv_complete:
+                    {   // ---- the output columns whose last source column is pixel pos-1 of this stage are complete
+                        uint32_t n_done = 1u;
+                        if ((hm2 >> (pos - 1u)) & 1u) n_done = uni((uint32_t)hv::ldg(hdone + st * 16 + (int)pos - 1));
+                        for (uint32_t e = 0; e < n_done; ++e) {
+                            // ---- output column Xc: park it (if it belongs to the strip) and free its slot
+                            const bool keep = (uint32_t)(Xc - sX0) < ncols;
+                            switch (hslot) {
 #define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-                                    float& a_ = (S_ & 1) ? accH[c][(S_ % AV) / 2].y : accH[c][(S_ % AV) / 2].x; \
-                                    if (keep) hv::sts_f32(wptr + (uint32_t)c * 128u, a_); a_ = 0.0f; } } break;
-                                IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5)
+                                float& a_ = (S_ & 1) ? accH[c][(S_ % AV) / 2].y : accH[c][(S_ % AV) / 2].x; \
+                                if (keep) hv::sts_f32(wptr + (uint32_t)c * 128u, a_); a_ = 0.0f; } } break;
+                            IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5)
 #undef IFB_HV_SLOT
-                                default: break;
-                                }
-                                if (keep) {
-                                    wptr += (uint32_t)C::kXPitch * 4u; ++colbuf;
-                                    if (colbuf == 32u || Xc == sd.X1 - 1) {
-                                        // ---- V pass of the group: lane = output column sd.X0 + 32*grp + lane
-                                        hv::warp_sync();
-                                        const uint32_t xr = xb + (uint32_t)lane * ((uint32_t)C::kXPitch * 4u);
-                                        const bool col_live = (uint32_t)lane < colbuf;
-                                        uint8_t* const out_px = out_col + (size_t)grp * 128u;
+                            default: break;
+                            }
+                            if (keep) {
+                                wptr += (uint32_t)C::kXPitch * 4u; ++colbuf;
+                                if (colbuf == 32u || Xc == sX1 - 1) {
+                                    // ---- V pass of the group: lane = output column sX0 + 32*grp + lane
+                                    hv::warp_sync();
+                                    const uint32_t xr = xb + (uint32_t)lane * ((uint32_t)C::kXPitch * 4u);
+                                    const bool col_live = (uint32_t)lane < colbuf;
+                                    uint8_t* const out_px = out_col + (size_t)grp * 128u;
 #define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { \
     int Yl = Yc, vs = vslot; \
     for (int r = 0; r < nr; ++r) { \
@@ -432,33 +439,33 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             const float x_ = hv::lds_f32(xr + (uint32_t)c * 128u + (uint32_t)r * 4u); const float2 vv = make_float2(x_, x_); \
             _Pragma("unroll") for (int q = 0; q < NP; ++q) accV[(G_) % NG][c][q] = hv::ffma2(wv[q], vv, accV[(G_) % NG][c][q]); } \
         if ((VM1 >> r) & 1u) { \
-            uint32_t nv = 1u; if ((VM2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r); \
+            uint32_t nv = 1u; if ((VM2 >> r) & 1u) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r)); \
             for (uint32_t e2 = 0; e2 < nv; ++e2) { \
                 float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f}; \
                 switch (vs) { \
                 IFB_HV_VSLOT(G_, 0) IFB_HV_VSLOT(G_, 1) IFB_HV_VSLOT(G_, 2) IFB_HV_VSLOT(G_, 3) IFB_HV_VSLOT(G_, 4) IFB_HV_VSLOT(G_, 5) \
                 default: break; } \
-                if (Yl >= bd.Y0 && Yl < bd.Y1 && col_live) { \
+                if (Yl >= bY0 && Yl < bY1 && col_live) { \
                     uint8_t* dst = out_px + (size_t)Yl * out_stride; \
                     *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst); } \
                 ++Yl; vs = vs + 1 == AV ? 0 : vs + 1; } } } } break;
 #define IFB_HV_VSLOT(G_, S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
     float& a_ = (S_ & 1) ? accV[(G_) % NG][c][(S_ % AV) / 2].y : accV[(G_) % NG][c][(S_ % AV) / 2].x; f_[c] = a_; a_ = 0.0f; } } break;
-                                        switch (grp) {
-                                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3)
-                                        default: break;
-                                        }
+                                    switch (grp) {
+                                    IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3)
+                                    default: break;
+                                    }
 #undef IFB_HV_VGROUP
 #undef IFB_HV_VSLOT
-                                        hv::warp_sync();
-                                        ++grp; colbuf = 0; wptr = xb + (uint32_t)lane * 4u;
-                                    }
+                                    hv::warp_sync();
+                                    ++grp; colbuf = 0; wptr = xb + (uint32_t)lane * 4u;
                                 }
-                                ++Xc; hslot = hslot + 1 == AV ? 0 : hslot + 1;
                             }
+                            ++Xc; hslot = hslot + 1 == AV ? 0 : hslot + 1;
                         }
-                        start = stop;
-                    } while (start < 4u);
+                    }
+                    goto hv_dispatch;
+                hv_stage_done:;
                 }
                 // every group of the row block has seen the same rows: commit the vertical position
                 Yc += (int)vtot;

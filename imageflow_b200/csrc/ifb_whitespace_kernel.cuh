@@ -12,9 +12,10 @@ __device__ __forceinline__ uint32_t ws_gray(uint32_t bgra, bool alpha_meaningful
     return min((v + 524287u) / 524288u, 255u);
 }
 __global__ void __launch_bounds__(256) whitespace_codes_kernel(const uint8_t* __restrict__ px, uint32_t w, uint32_t h, uint32_t stride,
-                                                               uint32_t alpha_meaningful, int threshold, uint8_t* __restrict__ codes) {
+                                                               uint32_t alpha_meaningful, int threshold, uint8_t* __restrict__ codes, uint32_t row0) {
+    // row0: first image row of this launch (grid.y is bounded, bitmaps are not: tall ones take several launches)
     __shared__ uint8_t g[10][36];
-    const int x0 = (int)blockIdx.x * 32 - 1, y0 = (int)blockIdx.y * 8 - 1;       // image position of g[0][0]
+    const int x0 = (int)blockIdx.x * 32 - 1, y0 = (int)(row0 + blockIdx.y * 8) - 1;       // image position of g[0][0]
     for (int i = threadIdx.y * 32 + threadIdx.x; i < 10 * 34; i += 256) {
         const int ty = i / 34, tx = i - ty * 34, x = x0 + tx, y = y0 + ty;
         uint32_t v = 0;
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) whitespace_codes_kernel(const uint8_t* __
         g[ty][tx] = (uint8_t)v;
     }
     __syncthreads();
-    const int x = (int)blockIdx.x * 32 + threadIdx.x, y = (int)blockIdx.y * 8 + threadIdx.y;
+    const int x = (int)blockIdx.x * 32 + threadIdx.x, y = (int)(row0 + blockIdx.y * 8) + threadIdx.y;
     if (x >= (int)w || y >= (int)h) return;
     uint32_t code = 0xFFu;
     if (x > 0 && y > 0 && x + 1 < (int)w && y + 1 < (int)h) {

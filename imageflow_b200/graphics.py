@@ -298,14 +298,26 @@ class Batch:
         keep = []
         for i, j in enumerate(jobs):
             _fill_desc(arr[i], j[0], j[1], j[2], j[3] if len(j) > 3 else None, keep)
+        keep.append([(j[0]._keep, j[1]._keep) for j in jobs])          # the bitmaps stay alive until sync() / close()
         return arr, keep
 
     STREAM_OWN = C.c_void_p(-1)
 
     @classmethod
     def _stream(cls, stream):
-        """None -> the batch's own stream (IFB200_STREAM_OWN); an int is a cudaStream_t (0 = legacy default stream)."""
-        return cls.STREAM_OWN if stream is None else C.c_void_p(stream)
+        """An int is a cudaStream_t (0 = the legacy default stream); "own" = the batch's private non-blocking stream
+        (IFB200_STREAM_OWN, the one sync() waits for).  None = the stream the caller's tensors live on: torch's current stream
+        when torch is loaded with CUDA -- work enqueued there is ordered after whatever produced the inputs and before whatever
+        reads the outputs -- otherwise the batch's own stream."""
+        if stream == "own":
+            return cls.STREAM_OWN
+        if stream is None:
+            import sys
+            torch = sys.modules.get("torch")
+            if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            return cls.STREAM_OWN
+        return C.c_void_p(stream)
 
     def enqueue(self, descs, stream=None, keep=None) -> None:
         if keep:
@@ -364,6 +376,10 @@ class Batch:
     def sync(self) -> None:
         buf = C.create_string_buffer(512)
         _check(lib().ifb200_batch_sync(self._h, buf, 512), buf)
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+            torch.cuda.synchronize(self.device)          # work enqueued on torch's streams (the default for stream=None)
         self._keep.clear()
 
     def host_profile(self) -> dict:

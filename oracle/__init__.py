@@ -172,6 +172,16 @@ def resample_stages(inp: np.ndarray, canvas: np.ndarray, **kw):
     return v, hh
 
 
+def synth_noise(w: int, h: int, seed: int = 0, alpha_mode: str = "opaque") -> np.ndarray:
+    """imageflow_b200.synth.noise_np, generated by the C library (same bytes, ~100x faster)"""
+    a = np.empty((h, w, 4), np.uint8)
+    L = lib()
+    L.ifo_synth_noise.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.ifo_synth_noise.restype = None
+    L.ifo_synth_noise(a.ctypes.data, w, h, a.strides[0], seed & 0xFFFFFFFF, int(alpha_mode != "opaque"))
+    return a
+
+
 def color_matrix(px: np.ndarray, m) -> None:
     m = np.ascontiguousarray(m, np.float32).reshape(25)
     h, w = px.shape[0], px.shape[1]

@@ -562,6 +562,26 @@ int ifo_scale_and_render_batch(const ifo_desc* d, size_t n, int threads) {
     return err;
 }
 
+/* imageflow_b200/synth.py noise_np, byte for byte (bench.py's CPU arm needs thousands of frames: numpy is too slow for that) */
+static uint32_t synth_mix(uint32_t v) { v ^= v >> 16; v *= 0x7FEB352Du; v ^= v >> 15; v *= 0x846CA68Bu; v ^= v >> 16; return v; }
+void ifo_synth_noise(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, uint32_t seed, int alpha_mixed) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (long y = 0; y < (long)h; y++) {
+        uint8_t* r = px + (size_t)y * stride;
+        for (uint32_t x = 0; x < w; x++) {
+            uint32_t base = synth_mix((x * 0x9E3779B1u) ^ ((uint32_t)y * 0x85EBCA77u) ^ (0x1F2E3D4Cu + seed));
+            uint8_t a = 255;
+            if (alpha_mixed) {
+                uint32_t h2 = synth_mix(base ^ 0xA5A5A5A5u), sel = (h2 >> 24) & 3u;
+                a = sel == 0 ? 0 : sel == 1 ? 255 : (uint8_t)((h2 >> 8) & 0xFF);
+            }
+            r[4 * x] = (uint8_t)base; r[4 * x + 1] = (uint8_t)(base >> 8); r[4 * x + 2] = (uint8_t)(base >> 16); r[4 * x + 3] = a;
+        }
+    }
+}
+
 int ifo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -124,6 +124,9 @@ void ifo_whitespace_codes(const uint8_t* px, uint32_t w, uint32_t h, uint32_t st
  * same number of evaluated centres as ifo_detect_content on the bitmap the map was made from. */
 int ifo_detect_content_from_codes(const uint8_t* codes, uint32_t w, uint32_t h, uint32_t rect_out[4], uint64_t* centres_out);
 
+/* imageflow_b200/synth.py noise frames, generated at memory speed (bench.py's CPU arm) */
+void ifo_synth_noise(uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, uint32_t seed, int alpha_mixed);
+
 int ifo_max_threads(void);
 
 #ifdef __cplusplus

@@ -109,6 +109,7 @@ static inline uint32_t warp_sum(uint32_t v) {
     return s;
 }
 static inline void warp_sync() { wbar(); }
+static inline bool elect_one() { return lid() == 0; }
 static inline void cta_sync() { emu::block_barrier->arrive_and_wait(); }
 static inline uint32_t atomic_inc(uint32_t* p) { return __atomic_fetch_add(p, 1u, __ATOMIC_SEQ_CST); }
 // mbarrier: the issuing lane copies synchronously, so a wait only has to order the warp behind its own lane 0; the phase

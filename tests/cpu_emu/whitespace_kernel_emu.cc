@@ -40,7 +40,7 @@ extern "C" void emu_whitespace_codes(const uint8_t* px, uint32_t w, uint32_t h, 
                 for (unsigned ty = 0; ty < 8; ++ty)
                     for (unsigned tx = 0; tx < 32; ++tx) {
                         emu::threadIdx = {tx, ty, 0};
-                        ifbk::whitespace_codes_kernel(px, w, h, stride, alpha_meaningful, threshold, codes);
+                        ifbk::whitespace_codes_kernel(px, w, h, stride, alpha_meaningful, threshold, codes, 0u);
                     }
         }
 }

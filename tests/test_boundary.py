@@ -177,7 +177,7 @@ def test_descriptor_arrays_are_filled_in_place_like_single_descriptors():
                                      scale_in_colorspace=ifb.WorkingFloatspace(int(rng.integers(0, 2))))
         jobs.append((a, b, p, ifb.color_filter_matrix(0)) if i % 5 == 0 else (a, b, p))
     arr, keep = ifb.Batch.make_descs(ifb.Batch.__new__(ifb.Batch), jobs)
-    assert len(keep) == 40
+    assert len(keep) == 41                                    # 40 colour matrices + the list that keeps the bitmaps alive
     sz, off = C.sizeof(ifb.ResampleDesc), ifb.ResampleDesc.color_matrix.offset
     for i, j in enumerate(jobs):
         one = bytearray(bytes(graphics._desc(*j)))
