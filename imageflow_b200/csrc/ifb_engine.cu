@@ -222,8 +222,8 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
     auto ht = std::make_unique<HvTables>();
     ht->max_cols = max_cols;
     const auto& h = p.wh; const auto& v = p.wv;
-    const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4), ng = av == 4 ? 4 : 2;
-    const uint32_t col_cap = (uint32_t)std::min(max_cols, ng * 32);
+    const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4);
+    const uint32_t col_cap = (uint32_t)max_cols;             // the caller has clipped it to what the kernel variant can hold (hv_cols)
     // the pixel stream of a strip starts at a multiple of k0_align source columns (16 bytes: TMA box origins stay 16-byte aligned
     // for bitmaps whose window starts on a 16-byte boundary; IFB200_DEBUG_K0_ALIGN=1 lifts that, for experiments)
     static const uint32_t k0_align = [] { const char* e = getenv("IFB200_DEBUG_K0_ALIGN"); const int v = e ? atoi(e) : 4; return (uint32_t)(v >= 1 && v <= 16 ? v : 4); }();
@@ -315,52 +315,58 @@ HvTables& hv_tables(ifb200_batch* bt, cudaStream_t st, Plan& p, int max_cols) {
     return ht;
 }
 
-// Row bands of one launch: output rows split evenly, each band with the source rows its windows need.
-std::vector<HvBandDev> hv_bands(const Plan& p, int nb) {
+// Row bands of one launch: a warp works on a PAIR of bands (two streams), so 2 * pairs bands: output rows split evenly, each
+// band with the source rows its windows need; bands beyond the last output row are empty (a stream that does nothing).
+std::vector<HvBandDev> hv_bands(const Plan& p, int pairs) {
     const auto& v = p.wv;
+    const int nb = 2 * pairs;
     std::vector<HvBandDev> bands;
     for (int i = 0; i < nb; ++i) {
         const uint32_t Y0 = (uint32_t)((uint64_t)p.out_h * i / nb), Y1 = (uint32_t)((uint64_t)p.out_h * (i + 1) / nb);
-        if (Y1 <= Y0) continue;
         HvBandDev b{};
-        b.Y0 = (int)Y0; b.Y1 = (int)Y1; b.j0 = (int)v.left[Y0]; b.nrows = (int)(v.right[Y1 - 1] - v.left[Y0] + 1);
-        uint32_t Yf = Y0;
-        while (Yf > 0 && v.right[Yf - 1] >= v.left[Y0]) --Yf;
-        b.Yf = (int)Yf; b.vslot0 = (int)(Yf % (uint32_t)p.av);
+        if (Y1 > Y0) {
+            b.Y0 = (int)Y0; b.Y1 = (int)Y1; b.j0 = (int)v.left[Y0]; b.nrows = (int)(v.right[Y1 - 1] - v.left[Y0] + 1);
+            uint32_t Yf = Y0;
+            while (Yf > 0 && v.right[Yf - 1] >= v.left[Y0]) --Yf;
+            b.Yf = (int)Yf; b.vslot0 = (int)(Yf % (uint32_t)p.av);
+        }
         bands.push_back(b);
     }
     return bands;
 }
-// Band count of a launch.  min_items > 0 (IFB200_OPT_MIN_ITEMS): the smallest count that gives that many work items.  Otherwise:
-// enough bands to give every warp of the device one item; and when there is more than one round of items anyway, the count
+// Band pairs of a launch.  min_items > 0 (IFB200_OPT_MIN_ITEMS): the smallest count that gives that many work items.  Otherwise:
+// enough pairs to give every warp of the device one item; and when there is more than one round of items anyway, the count
 // whose last round is fullest, counting what the band halos (the V window is re-read at every band edge) cost.
-int hv_pick_bands(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
-    const int max_nb = (int)std::max<uint32_t>(1u, p.out_h / 8u);
-    auto need = [&](size_t items) { return (int)std::min<size_t>((size_t)max_nb, std::max<size_t>(1, (items + jobs_x_strips - 1) / jobs_x_strips)); };
+int hv_pick_pairs(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
+    const int max_np = (int)std::max<uint32_t>(1u, p.out_h / 16u);
+    auto need = [&](size_t items) { return (int)std::min<size_t>((size_t)max_np, std::max<size_t>(1, (items + jobs_x_strips - 1) / jobs_x_strips)); };
     if (min_items > 0) return need((size_t)min_items);
-    const int nb0 = need((size_t)warps);
-    if (jobs_x_strips * (size_t)nb0 <= (size_t)warps) return nb0;
+    const int np0 = need((size_t)warps);
+    if (jobs_x_strips * (size_t)np0 <= (size_t)warps) return np0;
     const double halo = (double)p.wv.max_taps / (double)std::max<uint32_t>(p.in_h, 1u);
-    int best = nb0; double best_eff = -1.0;
-    for (int nb = nb0; nb <= std::min(max_nb, nb0 + 7); ++nb) {
-        const double items = (double)jobs_x_strips * nb;
-        const double eff = items / warps / std::ceil(items / warps) / (1.0 + halo * (nb - 1));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = nb; }
+    int best = np0; double best_eff = -1.0;
+    for (int np = np0; np <= std::min(max_np, np0 + 7); ++np) {
+        const double items = (double)jobs_x_strips * np;
+        const double eff = items / warps / std::ceil(items / warps) / (1.0 + halo * (2 * np - 1));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = np; }
     }
     return best;
 }
+// widest strip the kernel variant (ring depth, channels) can hold, clipped by IFB200_OPT_STRIP_COLUMNS
+int hv_cols(int av, int ch, int option);
 
 // ------------------------------------------------------------------------------------------------
 // ring kernel dispatch table
 using HvFn = void (*)(const JobDev*, const HvTmap*, Tables, HvPlanDev, uint32_t, uint32_t*);
-struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps; uint32_t (*smem)(uint32_t); };
-template <int AV, int CH> uint32_t hv_smem_bytes(uint32_t sb_low16) { return HvCfg<AV, CH>::total_bytes(sb_low16); }
-#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, hv_smem_bytes<AV_, CH_>}
+struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps, max_cols; uint32_t (*smem)(uint32_t); };
+template <int AV, int CH> uint32_t hv_smem_bytes(uint32_t sb_low16) { return hv_total_bytes<AV, CH>(sb_low16); }
+#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, HvCfg<AV_, CH_>::kNG * HvCfg<AV_, CH_>::kCG, hv_smem_bytes<AV_, CH_>}
 const HvEntry kHv[] = {IFB_HV(4, 3), IFB_HV(4, 4), IFB_HV(6, 3), IFB_HV(6, 4)};
 const HvEntry* find_hv(int av, int ch) {
     for (const auto& e : kHv) if (e.av == av && e.ch == ch) return &e;
     return nullptr;
 }
+int hv_cols(int av, int ch, int option) { return std::min(option, find_hv(av, ch)->max_cols); }
 
 // tile kernel (second form) dispatch: compiled per (channels, working space, compositing mode, colour matrix).
 // Without meaningful alpha the compositing mode changes nothing (scaling.rs:227-232, :262), so those share compose 0.
@@ -408,7 +414,7 @@ struct ifb200_batch {
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
-    bool force_generic = false; int strip_cols = 128; int min_items = 0;
+    bool force_generic = false; int strip_cols = 64; int min_items = 0;
     int sm_count = 148;
     // ring kernel: where dynamic shared memory starts in the shared window (probed once), whether TMA descriptors can be made
     uint32_t smem_base_low16 = 0x400u;
@@ -500,7 +506,7 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
         build_hv(*p);
         build_tile(*p);
-        if (p->hv_ok) hv_host_ready(*p, strip_cols);
+        if (p->hv_ok) { hv_host_ready(*p, hv_cols(p->av, 3, strip_cols)); hv_host_ready(*p, hv_cols(p->av, 4, strip_cols)); }
         return p;
     }
     Plan& plan_for(const ifb200_resample_desc& d) {
@@ -677,7 +683,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         bool ring = p.hv_ok && b->ring_ok && !b->force_generic && (d.in_stride % 16 == 0) && ((uintptr_t)d.in % 16 == 0);
         const int ch = d.alpha_meaningful ? 4 : 3;
         const bool upscale = p.out_h >= p.in_h && p.out_w >= p.in_w;
-        if (ring && !(p.tile_ok && upscale) && !hv_host_ready(p, b->strip_cols)) ring = false;   // windows wider than the weight table
+        if (ring && !(p.tile_ok && upscale) && !hv_host_ready(p, hv_cols(p.av, ch, b->strip_cols))) ring = false;   // windows wider than the weight table
         // the ring kernel streams every source row once and wins whenever rows outnumber outputs (down-scales);
         // for up-scales / 1:1 the tile kernel does less work per source pixel
         const bool prefer_tile = p.tile_ok && !b->force_generic && (!ring || upscale);
@@ -700,14 +706,14 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         lay[gi].jobs = take(g.idx.size() * sizeof(JobDev));
         if (g.kind == 1) {
             Plan& p = *g.plan;
-            const HvTables& ht = *p.by_cols.at(b->strip_cols);
             const HvEntry* he = find_hv(p.av, g.ch);
+            const HvTables& ht = *p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols));
             const size_t jxs = g.idx.size() * (size_t)ht.n_strips;
             const int warps_all = b->sm_count * he->warps;
-            lay[gi].nb = hv_pick_bands(p, jxs, warps_all, b->min_items);
-            lay[gi].bv = hv_bands(p, lay[gi].nb);
+            const int pairs = hv_pick_pairs(p, jxs, warps_all, b->min_items);
+            lay[gi].bv = hv_bands(p, pairs);
             lay[gi].nb = (int)lay[gi].bv.size();
-            const size_t items = jxs * lay[gi].nb;
+            const size_t items = jxs * pairs;
             lay[gi].grid = (int)std::min<size_t>((size_t)b->sm_count, (items + he->warps - 1) / he->warps);
             lay[gi].tmaps = take(g.idx.size() * sizeof(HvTmap));
             lay[gi].bands = take(lay[gi].bv.size() * sizeof(HvBandDev));
@@ -728,7 +734,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         }
         if (g.kind == 1) {
             memcpy(hbuf + lay[gi].bands, lay[gi].bv.data(), lay[gi].bv.size() * sizeof(HvBandDev));
-            memset(hbuf + lay[gi].counters, 0, (size_t)g.plan->by_cols.at(b->strip_cols)->n_strips * sizeof(uint32_t));
+            memset(hbuf + lay[gi].counters, 0, (size_t)g.plan->by_cols.at(hv_cols(g.plan->av, g.ch, b->strip_cols))->n_strips * sizeof(uint32_t));
         }
     }
     uint8_t* dbuf = nullptr;
@@ -782,7 +788,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             }
             b->tile_jobs += nj;
         } else if (g.kind == 1) {
-            HvTables& ht = hv_tables(b, st, p, b->strip_cols);
+            HvTables& ht = hv_tables(b, st, p, hv_cols(p.av, g.ch, b->strip_cols));
             const HvEntry* he = find_hv(p.av, g.ch);
             HvPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;
@@ -1156,7 +1162,7 @@ int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, 
         auto worker = [&](int me) {
             try {
                 for (size_t i; (i = next.fetch_add(1)) < n;) {
-                    auto p = ifb200_batch::build_plan_host(descs[i], 128);
+                    auto p = ifb200_batch::build_plan_host(descs[i], 64);
                     uint64_t b = 0;
                     for (auto& kv : p->by_cols) b += kv.second->blob.host.size();
                     bytes += b;
@@ -1186,16 +1192,18 @@ int ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads, 
 }
 
 // The ring kernel's host tables for one geometry (tests: tests/cpu_emu runs the kernel's source over them on the CPU; no CUDA call).
-int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_bands, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
+int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_pairs, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
                           char* err, size_t err_cap) {
     return guarded(err, err_cap, [&] {
         if (!d || !info) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
-        if (strip_cols < 32 || strip_cols > 128 || strip_cols % 32 || n_bands < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band count");
+        if (strip_cols < 16 || strip_cols > 64 || strip_cols % 16 || n_pairs < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band-pair count");
         memset(info, 0, sizeof *info);
         auto p = ifb200_batch::build_plan_host(*d, strip_cols);
-        if (!p->hv_ok || !p->by_cols.count(strip_cols)) return;          // info->ok stays 0: not a ring-kernel geometry
-        HvTables& ht = *p->by_cols.at(strip_cols);
-        const std::vector<HvBandDev> bands = hv_bands(*p, n_bands);
+        if (!p->hv_ok) return;                                            // info->ok stays 0: not a ring-kernel geometry
+        const int cols = hv_cols(p->av, d->alpha_meaningful ? 4 : 3, strip_cols);
+        if (!p->by_cols.count(cols)) return;
+        HvTables& ht = *p->by_cols.at(cols);
+        const std::vector<HvBandDev> bands = hv_bands(*p, n_pairs);
         const size_t o_bands = (ht.blob.host.size() + 255) / 256 * 256;
         info->ok = 1; info->av = p->av; info->n_strips = ht.n_strips; info->n_bands = (int32_t)bands.size();
         info->avp = p->av == 4 ? 4 : 8; info->cap_px = 16384 / (info->avp * 4);
@@ -1305,7 +1313,7 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     switch (option) {
     case IFB200_OPT_FORCE_GENERIC: b->force_generic = value != 0; return IFB200_OK;
     case IFB200_OPT_STRIP_COLUMNS:
-        if (value < 32 || value > 128 || value % 32) return IFB200_ERR_INVALID_ARGUMENT;
+        if (value < 16 || value > 64 || value % 16) return IFB200_ERR_INVALID_ARGUMENT;
         b->strip_cols = (int)value; return IFB200_OK;
     case IFB200_OPT_MIN_ITEMS:
         if (value < 0 || value > (1 << 24)) return IFB200_ERR_INVALID_ARGUMENT;

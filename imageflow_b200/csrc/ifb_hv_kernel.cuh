@@ -4,20 +4,23 @@
 // horizontally as it arrives, output rows are emitted as soon as their vertical window is complete.  Down-scales (and 1:1)
 // whose contribution windows keep at most AV <= 6 outputs open per source sample on both axes run here.
 //
-// Decomposition: ONE WARP = one work item = (job, strip of <= NG*32 output columns, band of output rows), and inside it
-// LANE = SOURCE ROW.  A warp walks its band 32 source rows at a time ("row block"); for every row block it streams the strip's
-// source columns left to right:
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) stages boxes of 16 pixels x 32 rows into the warp's own shared-memory ring
-//     (kStages deep, one mbarrier per stage; the same warp issues, waits and consumes: no other synchronisation exists in
+// Decomposition: ONE WARP = one work item = (job, strip of <= NG*16 output columns, PAIR of bands of output rows), and inside it
+// LANE = SOURCE ROW of each of the two bands ("streams" A and B): a lane filters row r of band A and row r of band B side by side.
+// A warp walks its bands 32 source rows at a time ("row block"); for every row block it streams the strip's source columns left to right:
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) stages one box of 16 pixels x 32 rows per stream into the warp's own shared-memory
+//     ring (kStages deep, one mbarrier per stage; the same warp issues, waits and consumes: no other synchronisation exists in
 //     this kernel).  The 64-byte swizzle makes the per-lane 16-byte reads of "my row" bank-conflict free.
-//   * H pass: every lane converts its row's pixel through the lane-replicated LUT (one PRMT + one conflict-free LDS per
-//     channel) and multiply-adds it into a ring of AV accumulators: output column X owns slot X mod AV while its window is open.
-//     The weights of a source column are the same for all lanes: one broadcast LDS.128 of a table the CTA keeps in shared memory.
-//     The whole horizontal reduction (7.5 : 1 for 4K -> 512) happens in registers with no exchange between threads.
-//   * When a column completes, its CH values go to the warp's exchange buffer [column][channel][row]; after 32 columns
-//     (a "group") the warp turns around: LANE = OUTPUT COLUMN, and the 32 H-filtered rows of the block are multiply-added, in
-//     row order, into the group's ring of AV vertical accumulators (output row Y owns slot Y mod AV).  A completed output row
-//     goes through the store epilogue and is written as one coalesced 128-byte segment.
+//   * H pass: every lane converts its two pixels through the lane-replicated LUT (one PRMT + one conflict-free LDS per channel)
+//     and multiply-adds them into two rings of AV accumulators: output column X owns slot X mod AV while its window is open.
+//     The weights of a source column are the same for all lanes and both streams: one broadcast LDS.128 per source column of a
+//     table the CTA keeps in shared memory.  The whole horizontal reduction (7.5 : 1 for 4K -> 512) happens in registers with no
+//     exchange between threads; what steers it (which column completes where) is warp-uniform and costs once for both streams.
+//   * When a column completes, its CH values of both streams go to the warp's exchange buffer [stream][column][channel][row];
+//     after 16 columns (a "group") the warp turns around: LANE = (stream, OUTPUT COLUMN), and the 32 H-filtered rows of the block
+//     are multiply-added, in row order, into the group's ring of AV vertical accumulators (output row Y owns slot Y mod AV).  A
+//     completed output row goes through the store epilogue and is written as a coalesced 64-byte segment per stream.
+// Two streams per lane instead of twice the warps: the same shared memory per SM, but the weight fetches, the completion
+// bookkeeping and every branch are paid once for two rows, and each warp carries two independent dependency chains.
 // Every source pixel is read from HBM once (plus strip/band halos), converted once; nothing but source and destination
 // pixels touches HBM.  Arithmetic: the H chain ascends over source columns from +0, the V chain over source rows from +0 --
 // exactly the order of the specification; a slot only ever sees zero weights outside its window, and fmaf(+0, v, acc) == acc.
@@ -27,7 +30,8 @@
 //   driver puts dynamic shared memory): row v (256 B): bytes 0..127 = T[v] for the 32 lanes, so the window address of a lookup
 //   is LUT | v << 8 | lane << 2 -- one PRMT, bank-conflict free for any image content.  Bytes 128..255 of the rows ("holes"):
 //   holes 0..127 = the 16 KB linear->sRGB table of the store epilogue, holes 128..255 = the strip's H weights (16 KB).
-//   Around it, per warp: stage ring, exchange buffer, mbarriers.
+//   Around it, per warp: stage ring, the two halves of the exchange buffer, mbarriers (hv_layout() packs them into the space
+//   before and after the LUT block).
 #pragma once
 
 #ifndef IFB_HV_EMU
@@ -53,29 +57,62 @@ template <int AV, int CH> struct HvCfg {
     static_assert(AV == 4 || AV == 6, "ring depth");
     static constexpr int kAvp = AV == 4 ? 4 : 8;                      // floats per weight record
     static constexpr int kCapPx = 16384 / (kAvp * 4);                 // pixels of H weights that fit in the holes
-    static constexpr int kNG = AV == 4 ? 4 : 2;                       // column groups per strip
+    static constexpr int kCG = 16;                                    // output columns per group (x 2 streams = 32 lanes in the V pass)
+    static constexpr int kNG = AV == 4 ? 4 : (CH == 3 ? 3 : 2);       // column groups per strip (V accumulators: NG * AV * CH registers)
     static constexpr int kWarps = CH == 3 ? 8 : 6;
     static constexpr int kThreads = kWarps * 32;
-    static constexpr int kStages = 3;
-    static constexpr int kStageBytes = 32 * 64;                       // 32 rows x 16 pixels
+    static constexpr int kStages = 2;
+    static constexpr int kBoxBytes = 32 * 64;                         // one stream's box: 32 rows x 16 pixels
+    static constexpr int kStageBytes = 2 * kBoxBytes;                 // streams A and B
     static constexpr int kXPitch = CH * 32 + 1;                       // words per column of the exchange buffer (odd: conflict-free both ways)
-    static constexpr int kXbufBytes = 32 * kXPitch * 4;
-    static constexpr int kWarpBytes = (kStages * kStageBytes + kXbufBytes + 64 + 1023) / 1024 * 1024;
-    // dynamic shared memory for a given low half of the shared-window base (see layout in the kernel)
-    static constexpr uint32_t total_bytes(uint32_t sb_low16) {
-        const uint32_t lut_off = (0x10000u - sb_low16) & 0xffffu;
-        const uint32_t a0_off = ((sb_low16 + 1023u) & ~1023u) - sb_low16;
-        const uint32_t nA = lut_off > a0_off ? (lut_off - a0_off) / kWarpBytes : 0u;
-        const uint32_t nB = nA >= (uint32_t)kWarps ? 0u : (uint32_t)kWarps - nA;
-        return lut_off + 65536u + nB * kWarpBytes;
-    }
+    static constexpr int kXHalfBytes = kCG * kXPitch * 4;             // one stream's half; == 64 (mod 128), see hv_layout
+    static_assert(kXHalfBytes % 128 == 64, "the B half must sit 16 banks away from the A half");
 };
+
+// Shared-memory packing for a given low half of the shared-window base (the LUT block must start on a 64 KB boundary of the
+// window, which splits dynamic shared memory into a region before it and one after it).  Blocks, first fit, in this order: every
+// warp's stage ring (512-byte aligned: the swizzle pattern repeats every 512 bytes), then every warp's exchange-buffer halves
+// (A on a 128-byte boundary, B 64 bytes past one: the V pass reads both halves in one request and they must use different
+// banks), then the mbarriers.  Returns the bytes of dynamic shared memory needed; fills the window OFFSETS (from the dynamic
+// shared-memory base) of warp `warp`'s blocks when the pointers are given.
+template <int AV, int CH>
+__host__ __device__ constexpr uint32_t hv_layout(uint32_t sb_low16, int warp, uint32_t* st_off, uint32_t* xa_off, uint32_t* xb_off, uint32_t* mb_off) {
+    using C = HvCfg<AV, CH>;
+    const uint32_t lut_off = (0x10000u - sb_low16) & 0xffffu;
+    uint32_t cur_a = 0, end_a = lut_off, cur_b = lut_off + 65536u;    // offsets; window address = sb + offset, and sb_low16 fixes alignment
+    auto place = [&](uint32_t bytes, uint32_t align, uint32_t phase) -> uint32_t {
+        // smallest offset >= cursor with (sb_low16 + offset) % align == phase
+        auto fit = [&](uint32_t cur) { const uint32_t w = sb_low16 + cur; const uint32_t r = (w % align + align - phase) % align; return cur + (r ? align - r : 0u); };
+        const uint32_t a = fit(cur_a);
+        if (a + bytes <= end_a) { cur_a = a + bytes; return a; }
+        const uint32_t b = fit(cur_b);
+        cur_b = b + bytes;
+        return b;
+    };
+    for (int w = 0; w < C::kWarps; ++w) { const uint32_t o = place((uint32_t)C::kStages * C::kStageBytes, 512u, 0u); if (w == warp && st_off) *st_off = o; }
+    for (int w = 0; w < C::kWarps; ++w) {
+        const uint32_t oa = place((uint32_t)C::kXHalfBytes, 128u, 0u);
+        const uint32_t ob = place((uint32_t)C::kXHalfBytes, 128u, 64u);
+        if (w == warp) { if (xa_off) *xa_off = oa; if (xb_off) *xb_off = ob; }
+    }
+    for (int w = 0; w < C::kWarps; ++w) { const uint32_t o = place(8u * C::kStages, 8u, 0u); if (w == warp && mb_off) *mb_off = o; }
+    return cur_b;
+}
+template <int AV, int CH> constexpr uint32_t hv_total_bytes(uint32_t sb_low16) { return hv_layout<AV, CH>(sb_low16, -1, nullptr, nullptr, nullptr, nullptr); }
 
 // ---------------------------------------------------------------- primitives (tests/cpu_emu provides its own under IFB_HV_EMU)
 #ifndef IFB_HV_EMU
 namespace hv {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float lds_lut(uint32_t a) { float v; asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }          // tables: read-only after setup
+// table look-ups: volatile, so that a chunk's 24 look-ups stay in its chunk (hoisted to the top of the stage they would need 96 registers)
+__device__ __forceinline__ float lds_lut(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+// the look-up of byte SEL of a packed pixel: window address = PRMT(pixel, lane4, selector) = LUT | byte << 8 | lane << 2, built and used in
+// one statement (the address never occupies a register beyond the load)
+template <uint32_t SEL> __device__ __forceinline__ float lut_gather(uint32_t px, uint32_t lane4) {
+    float v;
+    asm volatile("{\n\t.reg .b32 a;\n\tprmt.b32 a, %1, %2, %3;\n\tld.shared.f32 %0, [a];\n\t}" : "=f"(v) : "r"(px), "r"(lane4), "n"(SEL));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_lut_u8(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 // weight records: volatile, so that they are fetched where the chunk that uses them starts (hoisted to the top of a stage, the 16
 // records of its four chunks would occupy 64 registers)
@@ -214,8 +251,9 @@ __global__ void __launch_bounds__(HvCfg<AV, CH>::kThreads, 1)
 hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps, Tables tb, HvPlanDev pl, uint32_t n_jobs,
                uint32_t* __restrict__ counters) {
     using C = HvCfg<AV, CH>;
-    constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages;
+    constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages, CG = C::kCG;
     constexpr uint32_t kWStage = 16u * AVP * 4u * 2u;                      // address step of the H weights per stage: 16 records, every other 128 bytes a hole
+    constexpr uint32_t kXCol = (uint32_t)C::kXPitch * 4u;                  // bytes per column of the exchange buffer
     IFB_HV_DYNAMIC_SMEM(hv_smem);
     const uint32_t sb = hv::smem_u32(hv_smem);
     const uint32_t lut = sb + ((0x10000u - (sb & 0xffffu)) & 0xffffu);     // window address of the LUT block: low 16 bits are zero
@@ -223,14 +261,12 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
     // A value that is the same in every lane, rebuilt from a warp vote: the compiler then KNOWS it is warp-uniform and keeps it --
     // and every loop counter, address and branch derived from it -- on the uniform datapath (no divergence bookkeeping).
     auto uni = [&](uint32_t v) -> uint32_t { return hv::ballot((v >> lane) & 1u); };
-    uint32_t wb;                                                           // this warp's block: stages, exchange buffer, mbarriers
+    uint32_t stb, xa, xb, mb;                                              // this warp's stage ring, exchange-buffer halves, mbarriers (window addresses)
     {
-        const uint32_t a0 = (sb + 1023u) & ~1023u;
-        const uint32_t nA = lut > a0 ? (lut - a0) / (uint32_t)C::kWarpBytes : 0u;
-        wb = (uint32_t)warp < nA ? a0 + (uint32_t)warp * C::kWarpBytes : lut + 65536u + ((uint32_t)warp - nA) * C::kWarpBytes;
+        uint32_t o_st = 0, o_xa = 0, o_xb = 0, o_mb = 0;
+        hv_layout<AV, CH>(sb & 0xffffu, warp, &o_st, &o_xa, &o_xb, &o_mb);
+        stb = sb + o_st; xa = sb + o_xa; xb = sb + o_xb; mb = sb + o_mb;
     }
-    const uint32_t xb = wb + S * C::kStageBytes;
-    const uint32_t mb = xb + C::kXbufBytes;
     const uint32_t flags0 = jobs[0].flags;                                 // working space and channel count are the same for all jobs of a launch
 
     // ---- tables: forward LUT replicated for the 32 lanes; linear->sRGB table into holes 0..127
@@ -251,10 +287,15 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
     // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3; this lane's row starts at lane * 64: where chunk k of "my row" lies
     const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;
     const uint32_t row_off[4] = {(uint32_t)lane * 64u + (0u ^ swz), (uint32_t)lane * 64u + (16u ^ swz), (uint32_t)lane * 64u + (32u ^ swz), (uint32_t)lane * 64u + (48u ^ swz)};
-    const uint32_t n_bands = (uint32_t)pl.n_bands;
-    const uint32_t n_items = n_jobs * n_bands;
+    const uint32_t n_pairs = (uint32_t)pl.n_bands >> 1;
+    const uint32_t n_items = n_jobs * n_pairs;
     const uint32_t lutw = lut + 128u * 256u + 128u;                        // hole 128: the strip's H weights
     const bool leader = hv::elect_one();                                   // the lane that talks to the TMA unit
+    // V pass role of this lane: stream (lane >> 4), column (lane & 15) of the group
+    const bool laneB = lane >= CG;
+    const uint32_t cl = (uint32_t)lane & (uint32_t)(CG - 1);
+    const uint32_t xr = (laneB ? xb : xa) + cl * kXCol;
+    const uint32_t xwa = xa + (uint32_t)lane * 4u, xwb = xb + (uint32_t)lane * 4u;   // H pass role: row `lane` of column 0
 
     for (int sv = 0; sv < pl.n_strips; ++sv) {
         const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
@@ -276,14 +317,16 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             if (lane == 0) item = hv::atomic_inc(counters + s);
             item = uni(hv::bcast0(item));
             if (item >= n_items) break;
-            const uint32_t job_i = item / n_bands, band_i = item - job_i * n_bands;
+            const uint32_t job_i = item / n_pairs, pair_i = item - job_i * n_pairs;
             const JobDev& job = jobs[job_i];
             const HvTmap* tm = tmaps + job_i;
-            const HvBandDev bd_ = pl.bands[band_i];
-            const int bY0 = (int)uni((uint32_t)bd_.Y0), bY1 = (int)uni((uint32_t)bd_.Y1), bYf = (int)uni((uint32_t)bd_.Yf), bV0 = (int)uni((uint32_t)bd_.vslot0);
-            const int bJ0 = (int)uni((uint32_t)bd_.j0), bNr = (int)uni((uint32_t)bd_.nrows);
+            const HvBandDev ba_ = pl.bands[2u * pair_i], bb_ = pl.bands[2u * pair_i + 1u];
+            const int aJ0 = (int)uni((uint32_t)ba_.j0), aNr = (int)uni((uint32_t)ba_.nrows), bJ0 = (int)uni((uint32_t)bb_.j0), bNr = (int)uni((uint32_t)bb_.nrows);
+            // this lane's stream in the V pass
+            const HvBandDev& bm_ = laneB ? bb_ : ba_;
+            const int mY0 = bm_.Y0, mY1 = bm_.Y1, mJ0 = bm_.j0, mNr = bm_.nrows;
             const uint32_t flags = uni(job.flags);
-            const int nrb = (bNr + 31) >> 5;
+            const int nrb = (max(aNr, bNr) + 31) >> 5;
             const int x_origin = sK0 + (int)uni(job.in_xoff);
 
             // ---- TMA pipeline state: stages are numbered row block by row block
@@ -293,15 +336,17 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 hv::warp_sync();                                           // every lane has read what the refilled slot held
                 if (leader) {
                     const uint32_t bar = mb + 8u * (uint32_t)is_s;
+                    const uint32_t dst = stb + (uint32_t)is_s * C::kStageBytes;
                     hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
-                    hv::tma_load_box(wb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
+                    hv::tma_load_box(dst, tm, x_origin + is_x * 16, aJ0 + is_y * 32, bar);
+                    hv::tma_load_box(dst + C::kBoxBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
 #if IFB_HV_PREFETCH_AHEAD > 0
-                    // every fourth stage: one box IFB_HV_PREFETCH_AHEAD stages further on its way into L2 (the descriptor promotes
+                    // every fourth stage: the boxes IFB_HV_PREFETCH_AHEAD stages further on their way into L2 (the descriptor promotes
                     // every request to its 256-byte line, i.e. to the width of four stages)
                     if ((is_x & 3) == 0) {
                         int px = is_x + IFB_HV_PREFETCH_AHEAD, py = is_y;
                         if (px >= nst) { px -= nst; ++py; }
-                        if (py < nrb) hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32);
+                        if (py < nrb) { hv::tma_prefetch_box(tm, x_origin + px * 16, aJ0 + py * 32); hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32); }
                     }
 #endif
                 }
@@ -318,39 +363,43 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) accV[gq][c][q] = make_float2(0.0f, 0.0f);
-            int Yc = bYf, vslot = bV0;                                     // next output row to complete at the start of the row block, and its slot
-            uint8_t* const out_col = job.out + (size_t)(sX0 + lane) * 4;
+            int Yc = bm_.Yf, vslot = bm_.vslot0;                           // this lane's stream: next output row to complete at the start of the row block, its slot
+            uint8_t* const out_col = job.out + (size_t)(sX0 + (int)cl) * 4;
             const size_t out_stride = job.out_stride;
 
             for (int rb = 0; rb < nrb; ++rb) {
-                const int row0 = bJ0 + rb * 32;
-                const int nr = min(32, bNr - rb * 32);
-                uint32_t VM1, VM2, vtot;
+                const int nr = min(32, max(aNr, bNr) - rb * 32);           // rows of the row block (the longer stream's)
+                const int row0 = mJ0 + rb * 32, mnr = min(32, max(0, mNr - rb * 32));      // this lane's stream
+                uint32_t vm1, vm2, vtot;                                   // this lane's stream: rows completing output rows
                 {
-                    const uint32_t vd = lane < nr ? (uint32_t)hv::ldg(pl.vdone + row0 + lane) : 0u;
-                    VM1 = hv::ballot(vd >= 1u); VM2 = hv::ballot(vd >= 2u); vtot = uni(hv::warp_sum(vd));
+                    const int ra = aJ0 + rb * 32 + lane, rbb = bJ0 + rb * 32 + lane;
+                    const uint32_t vda = lane < aNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + ra) : 0u;
+                    const uint32_t vdb = lane < bNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + rbb) : 0u;
+                    const uint32_t a1 = hv::ballot(vda >= 1u), a2 = hv::ballot(vda >= 2u), b1 = hv::ballot(vdb >= 1u), b2 = hv::ballot(vdb >= 2u);
+                    const uint32_t ta = hv::warp_sum(vda), tbb = hv::warp_sum(vdb);
+                    vm1 = laneB ? b1 : a1; vm2 = laneB ? b2 : a2; vtot = laneB ? tbb : ta;
                 }
-                float2 accH[CH][NP];
+                float2 accA[CH][NP], accB[CH][NP];
 #pragma unroll
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) accH[c][q] = make_float2(0.0f, 0.0f);
+                    for (int q = 0; q < NP; ++q) { accA[c][q] = make_float2(0.0f, 0.0f); accB[c][q] = make_float2(0.0f, 0.0f); }
                 int Xc = sXf, hslot = sH0;
                 uint32_t colbuf = 0, grp = 0;
-                uint32_t wptr = xb + (uint32_t)lane * 4u;                  // where the next completed column goes
+                uint32_t woff = 0;                                         // where the next completed column goes: colbuf * kXCol
                 uint32_t HM1 = 0, HM2 = 0;
                 uint32_t wst = lutw;                                       // H weights of the current stage
 
                 for (int st = 0; st < nst; ++st, wst += kWStage) {
-                    // ---- stage top: keep the ring full, wait for this stage's box, pull "my row" (16 pixels) into registers
-                    if (is_n < total_stages) issue();                      // refills the slot consumed two stages ago
+                    // ---- stage top: keep the ring full, wait for this stage's boxes, pull "my rows" (2 x 16 pixels) into registers
+                    if (is_n < total_stages) issue();
                     hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                     par ^= 1u << cs_s;
-                    uint4 raw[4];
+                    uint4 rawA[4], rawB[4];
                     {
-                        const uint32_t sbase = wb + (uint32_t)cs_s * C::kStageBytes;
+                        const uint32_t sbase = stb + (uint32_t)cs_s * C::kStageBytes;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) raw[k] = hv::lds_u32x4(sbase + row_off[k]);
+                        for (int k = 0; k < 4; ++k) { rawA[k] = hv::lds_u32x4(sbase + row_off[k]); rawB[k] = hv::lds_u32x4(sbase + C::kBoxBytes + row_off[k]); }
                     }
                     cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
                     if ((st & 1) == 0) {                                   // completion masks of the next 32 pixels
@@ -359,29 +408,32 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     }
                     const uint32_t hm = (HM1 >> ((st & 1) * 16)) & 0xffffu, hm2 = (HM2 >> ((st & 1) * 16)) & 0xffffu;
 
-                    // ---- the stage's sixteen pixels: straight-line code, entered at pixel `pos` (0 at the top of a stage).  A chunk of
-                    // four pixels starts by converting them (12 table look-ups) and fetching their weight records; a chunk without a
-                    // completing column then runs 24 packed multiply-adds and falls into the next chunk; otherwise each pixel checks
-                    // its bit of the completion mask and, if set, leaves for the (single) completion code, which re-enters the
-                    // sequence behind that pixel.  Everything that steers this is warp-uniform.
-                    float p[4][CH];
+                    // ---- the stage's sixteen pixel columns: straight-line code, entered at column `pos` (0 at the top of a stage).  A chunk
+                    // of four columns starts by converting its 2 x 4 pixels (24 table look-ups) and fetching the four weight records;
+                    // a chunk without a completing output column then runs 48 packed multiply-adds and falls into the next chunk;
+                    // otherwise each column checks its bit of the completion mask and, if set, leaves for the (single) completion
+                    // code, which re-enters the sequence behind that column.  Everything that steers this is warp-uniform.
+                    float pA[4][CH], pB[4][CH];
                     float2 wq[4][NP];
                     uint32_t pos = 0;
-#define IFB_HV_TOP(K_) { \
-    const uint32_t w4_[4] = {raw[K_].x, raw[K_].y, raw[K_].z, raw[K_].w}; \
+#define IFB_HV_CONV(P_, RAW_) { \
+    const uint32_t w4_[4] = {RAW_.x, RAW_.y, RAW_.z, RAW_.w}; \
     _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
         const uint32_t v = w4_[i]; \
-        p[i][0] = hv::lds_lut(hv::prmt(v, lane4, 0x6504)); p[i][1] = hv::lds_lut(hv::prmt(v, lane4, 0x6514)); p[i][2] = hv::lds_lut(hv::prmt(v, lane4, 0x6524)); \
+        P_[i][0] = hv::lut_gather<0x6504>(v, lane4); P_[i][1] = hv::lut_gather<0x6514>(v, lane4); P_[i][2] = hv::lut_gather<0x6524>(v, lane4); \
         if (CH == 4) { /* alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered */ \
             const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f); \
-            p[i][0] = __fmul_rn(p[i][0], af); p[i][1] = __fmul_rn(p[i][1], af); p[i][2] = __fmul_rn(p[i][2], af); p[i][CH - 1] = af; } } \
+            P_[i][0] = __fmul_rn(P_[i][0], af); P_[i][1] = __fmul_rn(P_[i][1], af); P_[i][2] = __fmul_rn(P_[i][2], af); P_[i][CH - 1] = af; } } }
+#define IFB_HV_TOP(K_) { \
+    IFB_HV_CONV(pA, rawA[K_]) IFB_HV_CONV(pB, rawB[K_]) \
     const uint32_t wa_ = wst + (AV == 4 ? (uint32_t)((K_) >> 1) * 256u + (uint32_t)((K_) & 1) * 64u : (uint32_t)(K_) * 256u); \
     _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
         const float4 q4 = hv::lds_w4(wa_ + (uint32_t)i * (AVP * 4)); \
         wq[i][0] = make_float2(q4.x, q4.y); wq[i][1] = make_float2(q4.z, q4.w); \
         if (AV == 6) wq[i][NP - 1] = hv::lds_w2(wa_ + (uint32_t)i * (AVP * 4) + 16u); } }
-#define IFB_HV_PX(I_) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { const float2 vv = make_float2(p[I_][c], p[I_][c]); \
-                        _Pragma("unroll") for (int q = 0; q < NP; ++q) accH[c][q] = hv::ffma2(wq[I_][q], vv, accH[c][q]); } }
+#define IFB_HV_PX(I_) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
+    const float2 va_ = make_float2(pA[I_][c], pA[I_][c]), vb_ = make_float2(pB[I_][c], pB[I_][c]); \
+    _Pragma("unroll") for (int q = 0; q < NP; ++q) { accA[c][q] = hv::ffma2(wq[I_][q], va_, accA[c][q]); accB[c][q] = hv::ffma2(wq[I_][q], vb_, accB[c][q]); } } }
 #define IFB_HV_CHUNK(K_, LA_, LB_, LC_, LD_, LNEXT_) \
     LA_: IFB_HV_TOP(K_) \
          if (((hm >> (4 * (K_))) & 15u) == 0u) { IFB_HV_PX(0) IFB_HV_PX(1) IFB_HV_PX(2) IFB_HV_PX(3) goto LNEXT_; } \
@@ -404,9 +456,10 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     IFB_HV_CHUNK(3, hv_p12, hv_p13, hv_p14, hv_p15, hv_stage_done)
 #undef IFB_HV_CHUNK
 #undef IFB_HV_TOP
+#undef IFB_HV_CONV
 #undef IFB_HV_PX
                 hv_complete:
-                    {   // ---- the output columns whose last source column is pixel pos-1 of this stage are complete
+                    {   // ---- the output columns whose last source column is column pos-1 of this stage are complete (in both streams)
                         uint32_t n_done = 1u;
                         if ((hm2 >> (pos - 1u)) & 1u) n_done = uni((uint32_t)hv::ldg(hdone + st * 16 + (int)pos - 1));
                         for (uint32_t e = 0; e < n_done; ++e) {
@@ -414,38 +467,41 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                             const bool keep = (uint32_t)(Xc - sX0) < ncols;
                             switch (hslot) {
 #define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-                                float& a_ = (S_ & 1) ? accH[c][(S_ % AV) / 2].y : accH[c][(S_ % AV) / 2].x; \
-                                if (keep) hv::sts_f32(wptr + (uint32_t)c * 128u, a_); a_ = 0.0f; } } break;
+                                float& a_ = (S_ & 1) ? accA[c][(S_ % AV) / 2].y : accA[c][(S_ % AV) / 2].x; \
+                                float& b_ = (S_ & 1) ? accB[c][(S_ % AV) / 2].y : accB[c][(S_ % AV) / 2].x; \
+                                if (keep) { hv::sts_f32(xwa + woff + (uint32_t)c * 128u, a_); hv::sts_f32(xwb + woff + (uint32_t)c * 128u, b_); } \
+                                a_ = 0.0f; b_ = 0.0f; } } break;
                             IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5)
 #undef IFB_HV_SLOT
                             default: break;
                             }
                             if (keep) {
-                                wptr += (uint32_t)C::kXPitch * 4u; ++colbuf;
-                                if (colbuf == 32u || Xc == sX1 - 1) {
-                                    // ---- V pass of the group: lane = output column sX0 + 32*grp + lane
+                                woff += kXCol; ++colbuf;
+                                if (colbuf == (uint32_t)CG || Xc == sX1 - 1) {
+                                    // ---- V pass of the group: lane = (stream, output column sX0 + 16*grp + cl)
                                     hv::warp_sync();
-                                    const uint32_t xr = xb + (uint32_t)lane * ((uint32_t)C::kXPitch * 4u);
-                                    const bool col_live = (uint32_t)lane < colbuf;
-                                    uint8_t* const out_px = out_col + (size_t)grp * 128u;
+                                    const bool col_live = cl < colbuf;
+                                    uint8_t* const out_px = out_col + (size_t)grp * (CG * 4);
 #define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { \
     int Yl = Yc, vs = vslot; \
     for (int r = 0; r < nr; ++r) { \
         float2 wv[NP]; \
-        { const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(pl.vw + (size_t)(row0 + r) * AVP)); \
-          wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w); \
-          if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(pl.vw + (size_t)(row0 + r) * AVP + 4)); } \
+        if (r < mnr) { \
+            const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(pl.vw + (size_t)(row0 + r) * AVP)); \
+            wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w); \
+            if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(pl.vw + (size_t)(row0 + r) * AVP + 4)); \
+        } else { _Pragma("unroll") for (int q = 0; q < NP; ++q) wv[q] = make_float2(0.0f, 0.0f); } \
         _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
             const float x_ = hv::lds_f32(xr + (uint32_t)c * 128u + (uint32_t)r * 4u); const float2 vv = make_float2(x_, x_); \
             _Pragma("unroll") for (int q = 0; q < NP; ++q) accV[(G_) % NG][c][q] = hv::ffma2(wv[q], vv, accV[(G_) % NG][c][q]); } \
-        if ((VM1 >> r) & 1u) { \
-            uint32_t nv = 1u; if ((VM2 >> r) & 1u) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r)); \
+        if ((vm1 >> r) & 1u) { \
+            uint32_t nv = 1u; if ((vm2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r); \
             for (uint32_t e2 = 0; e2 < nv; ++e2) { \
                 float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f}; \
                 switch (vs) { \
                 IFB_HV_VSLOT(G_, 0) IFB_HV_VSLOT(G_, 1) IFB_HV_VSLOT(G_, 2) IFB_HV_VSLOT(G_, 3) IFB_HV_VSLOT(G_, 4) IFB_HV_VSLOT(G_, 5) \
                 default: break; } \
-                if (Yl >= bY0 && Yl < bY1 && col_live) { \
+                if (Yl >= mY0 && Yl < mY1 && col_live) { \
                     uint8_t* dst = out_px + (size_t)Yl * out_stride; \
                     *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst); } \
                 ++Yl; vs = vs + 1 == AV ? 0 : vs + 1; } } } } break;
@@ -458,7 +514,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
 #undef IFB_HV_VGROUP
 #undef IFB_HV_VSLOT
                                     hv::warp_sync();
-                                    ++grp; colbuf = 0; wptr = xb + (uint32_t)lane * 4u;
+                                    ++grp; colbuf = 0; woff = 0;
                                 }
                             }
                             ++Xc; hslot = hslot + 1 == AV ? 0 : hslot + 1;
@@ -467,7 +523,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     goto hv_dispatch;
                 hv_stage_done:;
                 }
-                // every group of the row block has seen the same rows: commit the vertical position
+                // every group of the row block has seen the same rows: commit the vertical position of this lane's stream
                 Yc += (int)vtot;
                 vslot = (int)(((uint32_t)vslot + vtot) % (uint32_t)AV);
             }

@@ -109,13 +109,13 @@ int  ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads,
                        uint64_t* table_hash, char* err, size_t err_cap);
 
 /* The streaming ring kernel's host tables for one geometry (only in_w, in_h, w, h, filter, sharpen_percent are read), as they
-   would be uploaded: call with buf = NULL for the size.  info->ok == 0: the geometry does not run on the ring kernel.
+   would be uploaded (alpha_meaningful selects the 3- or 4-channel kernel variant's strip width): call with buf = NULL for the size.  info->ok == 0: the geometry does not run on the ring kernel.
    Layout: imageflow_b200/csrc/ifb_hv_kernel.cuh (HvStripDev, HvBandDev, HvPlanDev).  No CUDA call. */
 typedef struct ifb200_hv_plan_info {
     int32_t ok, av, n_strips, n_bands, cap_px, avp;
     uint64_t o_strips, o_hw, o_hdone, o_vw, o_vdone, o_bands, total;
 } ifb200_hv_plan_info;
-int  ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_bands, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
+int  ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_band_pairs, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,
                            char* err, size_t err_cap);
 
 /* ---- drop-in calls: HOST buffers, synchronous (what the Rust adapter calls) ------------------
@@ -194,9 +194,9 @@ void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */
 enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
-    IFB200_OPT_STRIP_COLUMNS = 2,      /* ring kernel: widest strip of output columns one warp works on: 32, 64, 96 or 128 (default) */
-    IFB200_OPT_MIN_ITEMS = 3           /* ring kernel: split images into row bands until a launch has at least this many warp work
-                                          items (0 = as many as the device has warps, the default)        */
+    IFB200_OPT_STRIP_COLUMNS = 2,      /* ring kernel: widest strip of output columns one warp works on: 16, 32, 48 or 64 (default) */
+    IFB200_OPT_MIN_ITEMS = 3           /* ring kernel: split images into pairs of row bands until a launch has at least this many warp
+                                          work items (0 = as many as the device has warps, the default)    */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */

@@ -115,13 +115,13 @@ def load_hv(so):
     return L
 
 
-def hv_plan(ifb, iw, ih, ow, oh, filter, sharpen=0.0, strip_cols=128, n_bands=1):
+def hv_plan(ifb, iw, ih, ow, oh, filter, sharpen=0.0, strip_cols=64, n_bands=1, alpha=False):
     """(info, blob) of ifb200_hv_plan_tables, or (info, None) when the geometry is not a ring-kernel geometry"""
     from imageflow_b200._lib import ResampleDesc
     L = ifb.lib()
     L.ifb200_hv_plan_tables.restype = C.c_int
     L.ifb200_hv_plan_tables.argtypes = [C.POINTER(ResampleDesc), C.c_int, C.c_int, C.POINTER(HvPlanInfo), C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
-    d = ResampleDesc(); d.in_w, d.in_h, d.w, d.h, d.filter, d.sharpen_percent = iw, ih, ow, oh, filter, sharpen
+    d = ResampleDesc(); d.in_w, d.in_h, d.w, d.h, d.filter, d.sharpen_percent, d.alpha_meaningful = iw, ih, ow, oh, filter, sharpen, int(alpha)
     info = HvPlanInfo(); err = C.create_string_buffer(256)
     rc = L.ifb200_hv_plan_tables(C.byref(d), strip_cols, n_bands, C.byref(info), None, 0, err, 256)
     assert rc == 0, err.value
@@ -134,7 +134,7 @@ def hv_plan(ifb, iw, ih, ow, oh, filter, sharpen=0.0, strip_cols=128, n_bands=1)
 
 
 def run_hv(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen=0.0, linear=True, alpha_meaningful=False, compose=0,
-           matte=(0, 0, 0, 0), color_matrix=None, grid=1, jobs_repeat=1, strip_cols=128, n_bands=1, sb_low16=0x400, in_xoff=0):
+           matte=(0, 0, 0, 0), color_matrix=None, grid=1, jobs_repeat=1, strip_cols=64, n_bands=1, sb_low16=0x400, in_xoff=0):
     """One launch of the emulated hv_ring_kernel for `jobs_repeat` identical jobs (each on its own copy of the canvas); mirrors
     enqueue_locked / make_job (ifb_engine.cu).  in_xoff: the input window starts that many pixels into a wider bitmap (the TMA
     descriptor's base is then the 16-byte aligned address before it).  Returns the result canvases, or None if the geometry is not
@@ -142,7 +142,7 @@ def run_hv(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen
     ih, iw = inp.shape[:2]
     w = canvas.shape[1] - x if w is None else w
     h = canvas.shape[0] - y if h is None else h
-    info, blob = hv_plan(ifb, iw, ih, w, h, filter, sharpen, strip_cols, n_bands)
+    info, blob = hv_plan(ifb, iw, ih, w, h, filter, sharpen, strip_cols, n_bands, alpha_meaningful)      # n_bands = band PAIRS
     if blob is None:
         return None
     t_lin, t_srgb, lut = (np.zeros(256, np.float32), np.zeros(256, np.float32), np.zeros(16384, np.uint8))

@@ -84,6 +84,7 @@ static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
     return r;
 }
+template <uint32_t SEL> static inline float lut_gather(uint32_t px, uint32_t lane4) { return lds_lut(prmt(px, lane4, SEL)); }
 static inline float2 ffma2(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
 static inline uint32_t ballot(bool p) {
     emu::warp_scratch[wid()][lid()] = p ? 1u : 0u;
@@ -140,8 +141,9 @@ static inline void tma_load_box(uint32_t dst, const void* tmv, int x, int y, uin
             std::memcpy(emu::at(a, 16), px, 16);
         }
     Mbar m = ld<Mbar>(mbar);
-    if (m.pending != 2048u) emu::bad_access++;
-    m.pending = 0; m.phase ^= 1u;
+    if (m.pending < 2048u) emu::bad_access++;
+    m.pending -= 2048u;
+    if (m.pending == 0u) m.phase ^= 1u;
     st(mbar, m);
 }
 static inline void tma_prefetch_box(const void*, int, int) {}
@@ -162,7 +164,7 @@ using namespace ifbk;
 static_assert(sizeof(EmuTmap) == 128 && sizeof(HvTmapDecl) == 128, "descriptor size");
 using KernelFn = void (*)(const JobDev*, const HvTmapDecl*, Tables, HvPlanDev, uint32_t, uint32_t*);
 struct Pick { KernelFn fn; int threads; uint32_t (*smem)(uint32_t); };
-template <int AV, int CH> static uint32_t smem_of(uint32_t low16) { return HvCfg<AV, CH>::total_bytes(low16); }
+template <int AV, int CH> static uint32_t smem_of(uint32_t low16) { return hv_total_bytes<AV, CH>(low16); }
 static Pick pick(int av, int ch, int simple) {
 #define IFB_PICK(AV_, CH_) if (av == AV_ && ch == CH_) return Pick{simple ? hv_ring_kernel<AV_, CH_, true> : hv_ring_kernel<AV_, CH_, false>, HvCfg<AV_, CH_>::kThreads, smem_of<AV_, CH_>};
     IFB_PICK(4, 3) IFB_PICK(4, 4) IFB_PICK(6, 3) IFB_PICK(6, 4)

@@ -14,15 +14,15 @@ CASES = [
     (960, 540, 128, 128, 2, dict(n_bands=3, jobs_repeat=2)),                 # config-2 ratios (7.5 x 4.2), bands
     (960, 540, 128, 128, 6, dict(alpha=True, n_bands=2)),                    # Lanczos3: ring depth 6
     (800, 600, 400, 300, 2, dict(alpha=True, compose=1, cm="sepia")),        # 2x, composite over the canvas, colour matrix
-    (1280, 96, 320, 24, 2, dict(strip_cols=32, alpha=True, compose=2)),      # many strips, matte
-    (260, 250, 61, 59, 2, dict(in_xoff=3, n_bands=4)),                       # ragged sizes, unaligned window origin, short bands
-    (33, 17, 7, 5, 2, dict(alpha=True, in_xoff=1)),                          # smaller than one TMA box
+    (1280, 96, 320, 24, 2, dict(strip_cols=16, alpha=True, compose=2)),      # many strips, matte
+    (260, 250, 61, 59, 2, dict(in_xoff=4, n_bands=4)),                       # ragged sizes, unaligned window origin, short bands
+    (33, 17, 7, 5, 2, dict(alpha=True, in_xoff=8)),                          # smaller than one TMA box
     (8, 8, 1, 1, 2, dict(alpha=True)),
-    (256, 256, 256, 256, 2, dict(strip_cols=64, sb_low16=0x1400)),           # 1:1, another shared-memory origin
+    (256, 256, 256, 256, 2, dict(strip_cols=32, sb_low16=0x1400)),           # 1:1, another shared-memory origin
     (512, 384, 128, 96, 14, dict(linear=False, n_bands=2)),                  # Mitchell in sRGB space
     (1024, 64, 96, 17, 13, dict(alpha=True, sharpen=50.0)),                  # CatmullRom, sharpen
     (128, 128, 37, 41, 24, dict()),                                          # Box
-    (400, 300, 100, 75, 4, dict(alpha=True, linear=False, strip_cols=32)),   # Ginseng (ring depth 6), sRGB space
+    (400, 300, 100, 75, 4, dict(alpha=True, linear=False, strip_cols=16)),   # Ginseng (ring depth 6), sRGB space
 ]
 
 
