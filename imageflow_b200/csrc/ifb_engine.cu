@@ -217,9 +217,15 @@ void build_tile(Plan& p) {
 
 template <class F> void hv_for_av(int av, F&& f) { if (av == 4) f(std::integral_constant<int, 4>{}); else f(std::integral_constant<int, 6>{}); }
 
-// host half: strips, per-strip H weights by ring slot in pixel-stream order, completion counts, V weights by ring slot
-std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
+// host half: strips, per-strip H weights by ring slot in pixel-stream order, completion counts + V-pass marks, V weights by ring slot
+//
+// A strip's pixel stream is walked by the kernel in chunks of four source columns.  Output columns that complete are parked in the
+// warp's exchange buffer (room for cg columns) and the V pass of the parked columns (a "group") runs at the END of a chunk that
+// carries a mark (bit 7 of the completion byte of the chunk's last column): the marks are placed here, as late as the buffer allows,
+// and a strip may hold at most ng groups (the kernel keeps one set of vertical accumulators per group in registers).
+std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
     auto ht = std::make_unique<HvTables>();
+    const int max_cols = cols_key & 0xffff, ng = cols_key >> 16, cg = 16;   // hv_cols(): widest strip | groups the kernel variant holds << 16
     ht->max_cols = max_cols;
     const auto& h = p.wh; const auto& v = p.wv;
     const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4);
@@ -228,13 +234,28 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
     // for bitmaps whose window starts on a 16-byte boundary; IFB200_DEBUG_K0_ALIGN=1 lifts that, for experiments)
     static const uint32_t k0_align = [] { const char* e = getenv("IFB200_DEBUG_K0_ALIGN"); const int v = e ? atoi(e) : 4; return (uint32_t)(v >= 1 && v <= 16 ? v : 4); }();
     auto k0_of = [&](uint32_t X0) { return h.left[X0] / k0_align * k0_align; };
-    auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1): at most col_cap columns and a pixel stream (whole stages of 16) within the table
-        return X1 - X0 <= col_cap && (h.right[X1 - 1] - k0_of(X0) + 1 + 15) / 16 * 16 <= (uint32_t)cap;
+    // V-pass marks of [X0,X1): chunk indices after which a V pass runs; returns false if some chunk completes more than cg columns
+    auto marks_of = [&](uint32_t X0, uint32_t X1, std::vector<uint32_t>* marks) {
+        const uint32_t k0 = k0_of(X0);
+        uint32_t parked = 0, X = X0, groups = 0;
+        const uint32_t nchunks = (h.right[X1 - 1] - k0 + 1 + 15) / 16 * 4;
+        for (uint32_t c = 0; c < nchunks; ++c) {
+            uint32_t m = 0;
+            while (X < X1 && h.right[X] <= k0 + c * 4 + 3) { ++m; ++X; }
+            if (m > (uint32_t)cg) return false;
+            if (parked + m > (uint32_t)cg) { if (marks) marks->push_back(c - 1); ++groups; parked = 0; }
+            parked += m;
+        }
+        if (parked) { if (marks) marks->push_back(nchunks - 1); ++groups; }
+        return groups <= (uint32_t)ng;
+    };
+    auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1): at most col_cap columns in at most ng groups, and a pixel stream (whole stages of 16, plus the chunk the kernel's pipeline reads ahead) within the table
+        return X1 - X0 <= col_cap && (h.right[X1 - 1] - k0_of(X0) + 1 + 15) / 16 * 16 + 16 <= (uint32_t)cap && marks_of(X0, X1, nullptr);
     };
     uint32_t ns = 0;
     for (uint32_t X0 = 0; X0 < h.out_size; ++ns) {
         uint32_t X1 = X0 + 1;
-        if (!fits(X0, X1)) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: one output column reads %u source columns (> %d)", h.right[X0] - h.left[X0] + 1, cap);
+        if (!fits(X0, X1)) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: one output column reads %u source columns (> %d)", h.right[X0] - h.left[X0] + 1, cap - 16);
         while (X1 < h.out_size && fits(X0, X1 + 1)) ++X1;
         X0 = X1;
     }
@@ -249,40 +270,39 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int max_cols) {
             HvStripDev sd{};
             sd.X0 = (int)X0; sd.X1 = (int)X1; sd.k0 = (int)k0_of(X0);
             sd.nst = (int)((h.right[X1 - 1] - k0_of(X0) + 1 + 15) / 16);
-            uint32_t Xf = X0;                        // first column completing inside the stream: right[Xf] >= k0
-            while (Xf > 0 && h.right[Xf - 1] >= k0_of(X0)) --Xf;
-            sd.Xf = (int)Xf; sd.hslot0 = (int)(Xf % (uint32_t)av);
+            sd.Xf = (int)X0; sd.hslot0 = (int)(X0 % (uint32_t)av);     // only the strip's own columns are accumulated: the first to complete is X0
             strips.push_back(sd);
         }
         if (ok) break;
         if (ns > h.out_size) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: strip partition failed");
     }
     ht->n_strips = (int)ns;
-    const size_t hd_stride = (size_t)cap + 32;
-    ht->blob.reserve(ns * (sizeof(HvStripDev) + (size_t)cap * avp * 4 + hd_stride) + (size_t)p.in_h * (avp * 4 + 1) + 4096);
+    const size_t hd_stride = (size_t)cap + 64;
+    ht->blob.reserve(ns * (sizeof(HvStripDev) + (size_t)cap * avp * 4 + hd_stride) + ((size_t)p.in_h + 32) * (avp * 4 + 1) + 4096);
     ht->o_strips = ht->blob.add(strips);
     ht->o_hw = ht->blob.add_zeroed((size_t)ns * cap * avp * sizeof(float));
     ht->o_hdone = ht->blob.add_zeroed((size_t)ns * hd_stride);
-    ht->o_vw = ht->blob.add_zeroed((size_t)p.in_h * avp * sizeof(float));
+    ht->o_vw = ht->blob.add_zeroed(((size_t)p.in_h + 32) * avp * sizeof(float));   // 32 rows of zeros behind the last: a row block may end below the bitmap
     ht->o_vdone = ht->blob.add_zeroed((size_t)p.in_h + 32);
     float* const hw = ht->blob.host_at<float>(ht->o_hw);
     uint8_t* const hdone = ht->blob.host_at<uint8_t>(ht->o_hdone);
     float* const vw = ht->blob.host_at<float>(ht->o_vw);
     uint8_t* const vdone = ht->blob.host_at<uint8_t>(ht->o_vdone);
+    std::vector<uint32_t> marks;
     for (uint32_t s = 0; s < ns; ++s) {
         const HvStripDev& sd = strips[s];
-        const uint32_t k0 = (uint32_t)sd.k0, kend = k0 + (uint32_t)sd.nst * 16u - 1u;
-        for (uint32_t X = (uint32_t)sd.Xf; X < h.out_size && h.left[X] <= kend; ++X) {
+        const uint32_t k0 = (uint32_t)sd.k0;
+        for (uint32_t X = (uint32_t)sd.X0; X < (uint32_t)sd.X1; ++X) {
             const float* w = h.w.data() + h.offset[X];
             const uint32_t slot = X % (uint32_t)av;
-            for (uint32_t k = std::max(h.left[X], k0); k <= std::min(h.right[X], kend); ++k)
-                hw[((size_t)s * cap + (k - k0)) * avp + slot] = w[k - h.left[X]];
-            if (h.right[X] >= k0 && h.right[X] <= kend) {
-                uint8_t& d = hdone[(size_t)s * hd_stride + (h.right[X] - k0)];
-                if (d == 255) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: too many columns complete at once");
-                ++d;
-            }
+            for (uint32_t k = h.left[X]; k <= h.right[X]; ++k) hw[((size_t)s * cap + (k - k0)) * avp + slot] = w[k - h.left[X]];
+            uint8_t& d = hdone[(size_t)s * hd_stride + (h.right[X] - k0)];
+            if (d == 127) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: too many columns complete at once");
+            ++d;
         }
+        marks.clear();
+        marks_of((uint32_t)sd.X0, (uint32_t)sd.X1, &marks);
+        for (uint32_t c : marks) hdone[(size_t)s * hd_stride + c * 4 + 3] |= 0x80u;
     }
     for (uint32_t y = 0; y < v.out_size; ++y) {
         const float* w = v.w.data() + v.offset[y];
@@ -352,21 +372,22 @@ int hv_pick_pairs(const Plan& p, size_t jobs_x_strips, int warps, int min_items)
     }
     return best;
 }
-// widest strip the kernel variant (ring depth, channels) can hold, clipped by IFB200_OPT_STRIP_COLUMNS
+// key of a plan's ring tables: widest strip the kernel variant (ring depth, channels) can hold, clipped by IFB200_OPT_STRIP_COLUMNS,
+// | the number of column groups the variant keeps vertical accumulators for << 16
 int hv_cols(int av, int ch, int option);
 
 // ------------------------------------------------------------------------------------------------
 // ring kernel dispatch table
 using HvFn = void (*)(const JobDev*, const HvTmap*, Tables, HvPlanDev, uint32_t, uint32_t*);
-struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps, max_cols; uint32_t (*smem)(uint32_t); };
+struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps, max_cols, ng; uint32_t (*smem)(uint32_t); };
 template <int AV, int CH> uint32_t hv_smem_bytes(uint32_t sb_low16) { return hv_total_bytes<AV, CH>(sb_low16); }
-#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, HvCfg<AV_, CH_>::kNG * HvCfg<AV_, CH_>::kCG, hv_smem_bytes<AV_, CH_>}
+#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, HvCfg<AV_, CH_>::kMaxCols, HvCfg<AV_, CH_>::kNG, hv_smem_bytes<AV_, CH_>}
 const HvEntry kHv[] = {IFB_HV(4, 3), IFB_HV(4, 4), IFB_HV(6, 3), IFB_HV(6, 4)};
 const HvEntry* find_hv(int av, int ch) {
     for (const auto& e : kHv) if (e.av == av && e.ch == ch) return &e;
     return nullptr;
 }
-int hv_cols(int av, int ch, int option) { return std::min(option, find_hv(av, ch)->max_cols); }
+int hv_cols(int av, int ch, int option) { const HvEntry* e = find_hv(av, ch); return std::min(option, e->max_cols) | (e->ng << 16); }
 
 // tile kernel (second form) dispatch: compiled per (channels, working space, compositing mode, colour matrix).
 // Without meaningful alpha the compositing mode changes nothing (scaling.rs:227-232, :262), so those share compose 0.

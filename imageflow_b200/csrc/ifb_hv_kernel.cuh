@@ -58,7 +58,9 @@ template <int AV, int CH> struct HvCfg {
     static constexpr int kAvp = AV == 4 ? 4 : 8;                      // floats per weight record
     static constexpr int kCapPx = 16384 / (kAvp * 4);                 // pixels of H weights that fit in the holes
     static constexpr int kCG = 16;                                    // output columns per group (x 2 streams = 32 lanes in the V pass)
-    static constexpr int kNG = AV == 4 ? 4 : (CH == 3 ? 3 : 2);       // column groups per strip (V accumulators: NG * AV * CH registers)
+    static constexpr int kMaxCols = AV == 4 ? 64 : (CH == 3 ? 48 : 32);   // widest strip (output columns)
+    static constexpr int kNG = kMaxCols / kCG + 1;                    // column groups per strip (V accumulators: NG * AV * CH registers); groups end on
+                                                                      // chunk boundaries and are not always full, hence one more than the columns need
     static constexpr int kWarps = CH == 3 ? 8 : 6;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kStages = 2;
@@ -252,7 +254,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                uint32_t* __restrict__ counters) {
     using C = HvCfg<AV, CH>;
     constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages, CG = C::kCG;
-    constexpr uint32_t kWStage = 16u * AVP * 4u * 2u;                      // address step of the H weights per stage: 16 records, every other 128 bytes a hole
+    constexpr uint32_t kRec = (uint32_t)AVP * 4u;                          // bytes per H weight record (one source column)
     constexpr uint32_t kXCol = (uint32_t)C::kXPitch * 4u;                  // bytes per column of the exchange buffer
     IFB_HV_DYNAMIC_SMEM(hv_smem);
     const uint32_t sb = hv::smem_u32(hv_smem);
@@ -284,9 +286,9 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
 
     const uint32_t lut_lane = lut + (uint32_t)lane * 4u;
     const uint32_t lane4 = ((uint32_t)lane * 4u) | ((lut >> 16) << 8);     // PRMT operand: byte 0 = lane*4, bytes 1..2 = window bits 16..31
-    // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3; this lane's row starts at lane * 64: where chunk k of "my row" lies
+    // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3; this lane's row starts at lane * 64: chunk k of "my row" lies at
+    // lane * 64 + ((k << 4) ^ swz)
     const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;
-    const uint32_t row_off[4] = {(uint32_t)lane * 64u + (0u ^ swz), (uint32_t)lane * 64u + (16u ^ swz), (uint32_t)lane * 64u + (32u ^ swz), (uint32_t)lane * 64u + (48u ^ swz)};
     const uint32_t n_pairs = (uint32_t)pl.n_bands >> 1;
     const uint32_t n_items = n_jobs * n_pairs;
     const uint32_t lutw = lut + 128u * 256u + 128u;                        // hole 128: the strip's H weights
@@ -301,16 +303,17 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
         hv::cta_sync();                                                    // every warp is done with the previous strip's weights (first time: tables filled)
         const HvStripDev sd_ = pl.strips[s];
-        const int sX0 = (int)uni((uint32_t)sd_.X0), sX1 = (int)uni((uint32_t)sd_.X1), sXf = (int)uni((uint32_t)sd_.Xf), sH0 = (int)uni((uint32_t)sd_.hslot0);
+        const int sX0 = (int)uni((uint32_t)sd_.X0);
+        const uint32_t sH0 = uni((uint32_t)sd_.hslot0);
         const int sK0 = (int)uni((uint32_t)sd_.k0), nst = (int)uni((uint32_t)sd_.nst);
         {   // H weights of the strip: 16-byte units u -> hole 128 + u/8, offset (u%8)*16
             const float4* __restrict__ src = reinterpret_cast<const float4*>(pl.hw + (size_t)s * C::kCapPx * AVP);
-            const int n16 = nst * 16 * AVP / 4;
+            const int n16 = (nst * 16 + 4) * AVP / 4;                      // + one chunk: the pipeline fetches one record ahead
             for (int u = t; u < n16; u += C::kThreads) hv::sts_f32x4(lutw + ((uint32_t)(u >> 3) << 8) + ((uint32_t)(u & 7) << 4), hv::ldg(src + u));
         }
         hv::cta_sync();
-        const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 32);
-        const uint32_t ncols = (uint32_t)(sX1 - sX0);
+        const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 64);
+        const uint32_t nchunks = (uint32_t)nst * 4u;
 
         for (;;) {
             uint32_t item = 0;
@@ -324,9 +327,10 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             const int aJ0 = (int)uni((uint32_t)ba_.j0), aNr = (int)uni((uint32_t)ba_.nrows), bJ0 = (int)uni((uint32_t)bb_.j0), bNr = (int)uni((uint32_t)bb_.nrows);
             // this lane's stream in the V pass
             const HvBandDev& bm_ = laneB ? bb_ : ba_;
-            const int mY0 = bm_.Y0, mY1 = bm_.Y1, mJ0 = bm_.j0, mNr = bm_.nrows;
+            const int mY0 = bm_.Y0, mY1 = bm_.Y1, mJ0 = bm_.j0;
             const uint32_t flags = uni(job.flags);
-            const int nrb = (max(aNr, bNr) + 31) >> 5;
+            const int nrmax = max(aNr, bNr);
+            const int nrb = (nrmax + 31) >> 5;
             const int x_origin = sK0 + (int)uni(job.in_xoff);
 
             // ---- TMA pipeline state: stages are numbered row block by row block
@@ -368,8 +372,8 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             const size_t out_stride = job.out_stride;
 
             for (int rb = 0; rb < nrb; ++rb) {
-                const int nr = min(32, max(aNr, bNr) - rb * 32);           // rows of the row block (the longer stream's)
-                const int row0 = mJ0 + rb * 32, mnr = min(32, max(0, mNr - rb * 32));      // this lane's stream
+                const int nr = min(32, nrmax - rb * 32);                   // rows of the row block (the longer stream's)
+                const int row0 = mJ0 + rb * 32;                            // this lane's stream
                 uint32_t vm1, vm2, vtot;                                   // this lane's stream: rows completing output rows
                 {
                     const int ra = aJ0 + rb * 32 + lane, rbb = bJ0 + rb * 32 + lane;
@@ -384,145 +388,156 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
                     for (int q = 0; q < NP; ++q) { accA[c][q] = make_float2(0.0f, 0.0f); accB[c][q] = make_float2(0.0f, 0.0f); }
-                int Xc = sXf, hslot = sH0;
-                uint32_t colbuf = 0, grp = 0;
-                uint32_t woff = 0;                                         // where the next completed column goes: colbuf * kXCol
-                uint32_t HM1 = 0, HM2 = 0;
-                uint32_t wst = lutw;                                       // H weights of the current stage
+                uint32_t hslot = sH0, colbuf = 0, grp = 0, gX = 0;         // ring slot of the next column to complete; columns parked since the last V pass; group; its first column
+                uint32_t xwA = xwa, xwB = xwb;                             // where this lane parks its value of the next completed column
+                uint32_t wcur = lutw;                                      // H weight records of the current chunk
 
-                for (int st = 0; st < nst; ++st, wst += kWStage) {
-                    // ---- stage top: keep the ring full, wait for this stage's boxes, pull "my rows" (2 x 16 pixels) into registers
-                    if (is_n < total_stages) issue();
-                    hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
-                    par ^= 1u << cs_s;
-                    uint4 rawA[4], rawB[4];
-                    {
-                        const uint32_t sbase = stb + (uint32_t)cs_s * C::kStageBytes;
+                // ---- first stage of the row block
+                if (is_n < total_stages) issue();
+                hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                par ^= 1u << cs_s;
+                uint32_t sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
+                uint4 rawA = hv::lds_u32x4(sbase + swz), rawB = hv::lds_u32x4(sbase + C::kBoxBytes + swz);
+                uint32_t hd_next = (uint32_t)hv::ldg(hdone + lane);
+                uint32_t HM1 = 0, HM2 = 0, HMV = 0;
+
+                // The pixel loop is software-pipelined by one source column: while column i is multiply-added, column i+1 is being
+                // converted (its six table look-ups are in flight) and its weight record fetched.
+                float P0A[CH], P0B[CH], P1A[CH], P1B[CH];
+                float2 W0[NP], W1[NP];
+                auto conv = [&](float (&P)[CH], const uint32_t v) {
+                    P[0] = hv::lut_gather<0x6504>(v, lane4); P[1] = hv::lut_gather<0x6514>(v, lane4); P[2] = hv::lut_gather<0x6524>(v, lane4);
+                    if (CH == 4) {                                         // alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered
+                        const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f);
+                        P[0] = __fmul_rn(P[0], af); P[1] = __fmul_rn(P[1], af); P[2] = __fmul_rn(P[2], af); P[CH - 1] = af;
+                    }
+                };
+                auto wload = [&](float2 (&W)[NP], const uint32_t a) {
+                    const float4 q4 = hv::lds_w4(a);
+                    W[0] = make_float2(q4.x, q4.y); W[1] = make_float2(q4.z, q4.w);
+                    if (AV == 6) W[NP - 1] = hv::lds_w2(a + 16u);
+                };
+                auto mac = [&](const float (&PA)[CH], const float (&PB)[CH], const float2 (&W)[NP]) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { rawA[k] = hv::lds_u32x4(sbase + row_off[k]); rawB[k] = hv::lds_u32x4(sbase + C::kBoxBytes + row_off[k]); }
+                    for (int c = 0; c < CH; ++c) {
+                        const float2 va_ = make_float2(PA[c], PA[c]), vb_ = make_float2(PB[c], PB[c]);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) { accA[c][q] = hv::ffma2(W[q], va_, accA[c][q]); accB[c][q] = hv::ffma2(W[q], vb_, accB[c][q]); }
                     }
-                    cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
-                    if ((st & 1) == 0) {                                   // completion masks of the next 32 pixels
-                        const uint32_t hd = (uint32_t)hv::ldg(hdone + st * 16 + lane);
-                        HM1 = hv::ballot(hd >= 1u); HM2 = hv::ballot(hd >= 2u);
-                    }
-                    const uint32_t hm = (HM1 >> ((st & 1) * 16)) & 0xffffu, hm2 = (HM2 >> ((st & 1) * 16)) & 0xffffu;
+                };
+                wload(W0, wcur); conv(P0A, rawA.x); conv(P0B, rawB.x);
 
-                    // ---- the stage's sixteen pixel columns: straight-line code, entered at column `pos` (0 at the top of a stage).  A chunk
-                    // of four columns starts by converting its 2 x 4 pixels (24 table look-ups) and fetching the four weight records;
-                    // a chunk without a completing output column then runs 48 packed multiply-adds and falls into the next chunk;
-                    // otherwise each column checks its bit of the completion mask and, if set, leaves for the (single) completion
-                    // code, which re-enters the sequence behind that column.  Everything that steers this is warp-uniform.
-                    float pA[4][CH], pB[4][CH];
-                    float2 wq[4][NP];
-                    uint32_t pos = 0;
-#define IFB_HV_CONV(P_, RAW_) { \
-    const uint32_t w4_[4] = {RAW_.x, RAW_.y, RAW_.z, RAW_.w}; \
-    _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
-        const uint32_t v = w4_[i]; \
-        P_[i][0] = hv::lut_gather<0x6504>(v, lane4); P_[i][1] = hv::lut_gather<0x6514>(v, lane4); P_[i][2] = hv::lut_gather<0x6524>(v, lane4); \
-        if (CH == 4) { /* alpha table entry == a * (1/255f) (color.rs:38): computed, not gathered */ \
-            const float af = __fmul_rn(__uint2float_rn(v >> 24), 1.0f / 255.0f); \
-            P_[i][0] = __fmul_rn(P_[i][0], af); P_[i][1] = __fmul_rn(P_[i][1], af); P_[i][2] = __fmul_rn(P_[i][2], af); P_[i][CH - 1] = af; } } }
-#define IFB_HV_TOP(K_) { \
-    IFB_HV_CONV(pA, rawA[K_]) IFB_HV_CONV(pB, rawB[K_]) \
-    const uint32_t wa_ = wst + (AV == 4 ? (uint32_t)((K_) >> 1) * 256u + (uint32_t)((K_) & 1) * 64u : (uint32_t)(K_) * 256u); \
-    _Pragma("unroll") for (int i = 0; i < 4; ++i) { \
-        const float4 q4 = hv::lds_w4(wa_ + (uint32_t)i * (AVP * 4)); \
-        wq[i][0] = make_float2(q4.x, q4.y); wq[i][1] = make_float2(q4.z, q4.w); \
-        if (AV == 6) wq[i][NP - 1] = hv::lds_w2(wa_ + (uint32_t)i * (AVP * 4) + 16u); } }
-#define IFB_HV_PX(I_) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-    const float2 va_ = make_float2(pA[I_][c], pA[I_][c]), vb_ = make_float2(pB[I_][c], pB[I_][c]); \
-    _Pragma("unroll") for (int q = 0; q < NP; ++q) { accA[c][q] = hv::ffma2(wq[I_][q], va_, accA[c][q]); accB[c][q] = hv::ffma2(wq[I_][q], vb_, accB[c][q]); } } }
-#define IFB_HV_CHUNK(K_, LA_, LB_, LC_, LD_, LNEXT_) \
-    LA_: IFB_HV_TOP(K_) \
-         if (((hm >> (4 * (K_))) & 15u) == 0u) { IFB_HV_PX(0) IFB_HV_PX(1) IFB_HV_PX(2) IFB_HV_PX(3) goto LNEXT_; } \
-         IFB_HV_PX(0) if ((hm >> (4 * (K_) + 0)) & 1u) { pos = 4 * (K_) + 1; goto hv_complete; } \
-    LB_: IFB_HV_PX(1) if ((hm >> (4 * (K_) + 1)) & 1u) { pos = 4 * (K_) + 2; goto hv_complete; } \
-    LC_: IFB_HV_PX(2) if ((hm >> (4 * (K_) + 2)) & 1u) { pos = 4 * (K_) + 3; goto hv_complete; } \
-    LD_: IFB_HV_PX(3) if ((hm >> (4 * (K_) + 3)) & 1u) { pos = 4 * (K_) + 4; goto hv_complete; } \
-         goto LNEXT_;
-                hv_dispatch:
-                    switch (pos) {
-                    case 0: goto hv_p0; case 1: goto hv_p1; case 2: goto hv_p2; case 3: goto hv_p3;
-                    case 4: goto hv_p4; case 5: goto hv_p5; case 6: goto hv_p6; case 7: goto hv_p7;
-                    case 8: goto hv_p8; case 9: goto hv_p9; case 10: goto hv_p10; case 11: goto hv_p11;
-                    case 12: goto hv_p12; case 13: goto hv_p13; case 14: goto hv_p14; case 15: goto hv_p15;
-                    default: goto hv_stage_done;
+                for (uint32_t c = 0; c < nchunks; ++c) {
+                    if ((c & 7u) == 0u) {                                  // completion masks of the next 32 source columns; the bytes after them are on their way
+                        HM1 = hv::ballot((hd_next & 0x7fu) >= 1u); HM2 = hv::ballot((hd_next & 0x7fu) >= 2u); HMV = hv::ballot((hd_next & 0x80u) != 0u);
+                        hd_next = (uint32_t)hv::ldg(hdone + (c + 8u) * 4u + (uint32_t)lane);
                     }
-                    IFB_HV_CHUNK(0, hv_p0, hv_p1, hv_p2, hv_p3, hv_p4)
-                    IFB_HV_CHUNK(1, hv_p4, hv_p5, hv_p6, hv_p7, hv_p8)
-                    IFB_HV_CHUNK(2, hv_p8, hv_p9, hv_p10, hv_p11, hv_p12)
-                    IFB_HV_CHUNK(3, hv_p12, hv_p13, hv_p14, hv_p15, hv_stage_done)
-#undef IFB_HV_CHUNK
-#undef IFB_HV_TOP
-#undef IFB_HV_CONV
-#undef IFB_HV_PX
-                hv_complete:
-                    {   // ---- the output columns whose last source column is column pos-1 of this stage are complete (in both streams)
-                        uint32_t n_done = 1u;
-                        if ((hm2 >> (pos - 1u)) & 1u) n_done = uni((uint32_t)hv::ldg(hdone + st * 16 + (int)pos - 1));
-                        for (uint32_t e = 0; e < n_done; ++e) {
-                            // ---- output column Xc: park it (if it belongs to the strip) and free its slot
-                            const bool keep = (uint32_t)(Xc - sX0) < ncols;
-                            switch (hslot) {
-#define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-                                float& a_ = (S_ & 1) ? accA[c][(S_ % AV) / 2].y : accA[c][(S_ % AV) / 2].x; \
-                                float& b_ = (S_ & 1) ? accB[c][(S_ % AV) / 2].y : accB[c][(S_ % AV) / 2].x; \
-                                if (keep) { hv::sts_f32(xwa + woff + (uint32_t)c * 128u, a_); hv::sts_f32(xwb + woff + (uint32_t)c * 128u, b_); } \
-                                a_ = 0.0f; b_ = 0.0f; } } break;
-                            IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5)
+                    const uint32_t sh = (c & 7u) * 4u;
+                    const uint32_t hm = HM1 >> sh, hm2 = HM2 >> sh, hmv = HMV >> sh;
+                    const uint32_t wnext = wcur + (AV == 4 ? ((c & 1u) ? 192u : 64u) : 256u);
+                    const bool more = c + 1u < nchunks;
+
+                    // a completed output column: both streams park their CH values in the exchange buffer, the ring slot is cleared
+#define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) { \
+        float& a_ = (S_ & 1) ? accA[ch_][(S_ % AV) / 2].y : accA[ch_][(S_ % AV) / 2].x; \
+        float& b_ = (S_ & 1) ? accB[ch_][(S_ % AV) / 2].y : accB[ch_][(S_ % AV) / 2].x; \
+        hv::sts_f32(xwA + (uint32_t)ch_ * 128u, a_); hv::sts_f32(xwB + (uint32_t)ch_ * 128u, b_); a_ = 0.0f; b_ = 0.0f; } } break;
+#define IFB_HV_FLUSH(I_) if ((hm >> (I_)) & 1u) { \
+        uint32_t n_ = 1u; \
+        if ((hm2 >> (I_)) & 1u) n_ = uni((uint32_t)hv::ldg(hdone + c * 4u + (I_)) & 0x7fu); \
+        _Pragma("unroll 1") do { \
+            switch (hslot) { IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5) default: break; } \
+            xwA += kXCol; xwB += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
+        } while (--n_); }
+
+                    // ---- source column 0 of the chunk (column 1 on its way)
+                    wload(W1, wcur + kRec); conv(P1A, rawA.y); conv(P1B, rawB.y);
+                    mac(P0A, P0B, W0);
+                    IFB_HV_FLUSH(0)
+                    // ---- column 1
+                    wload(W0, wcur + 2u * kRec); conv(P0A, rawA.z); conv(P0B, rawB.z);
+                    mac(P1A, P1B, W1);
+                    IFB_HV_FLUSH(1)
+                    // ---- column 2; the next chunk's sixteen bytes per stream replace this one's (all four columns are converted or in registers)
+                    wload(W1, wcur + 3u * kRec); conv(P1A, rawA.w); conv(P1B, rawB.w);
+                    if (more) {
+                        if ((c & 3u) == 3u) {                              // next stage: refill the slot just emptied, wait for the next one
+                            cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
+                            if (is_n < total_stages) issue();
+                            hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                            par ^= 1u << cs_s;
+                            sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
+                        }
+                        const uint32_t o_ = sbase + ((((c + 1u) & 3u) << 4) ^ swz);
+                        rawA = hv::lds_u32x4(o_); rawB = hv::lds_u32x4(o_ + C::kBoxBytes);
+                    }
+                    mac(P0A, P0B, W0);
+                    IFB_HV_FLUSH(2)
+                    // ---- column 3 (column 0 of the next chunk on its way)
+                    wload(W0, wnext); conv(P0A, rawA.x); conv(P0B, rawB.x);
+                    mac(P1A, P1B, W1);
+                    IFB_HV_FLUSH(3)
+#undef IFB_HV_FLUSH
 #undef IFB_HV_SLOT
-                            default: break;
-                            }
-                            if (keep) {
-                                woff += kXCol; ++colbuf;
-                                if (colbuf == (uint32_t)CG || Xc == sX1 - 1) {
-                                    // ---- V pass of the group: lane = (stream, output column sX0 + 16*grp + cl)
-                                    hv::warp_sync();
-                                    const bool col_live = cl < colbuf;
-                                    uint8_t* const out_px = out_col + (size_t)grp * (CG * 4);
-#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { \
-    int Yl = Yc, vs = vslot; \
-    for (int r = 0; r < nr; ++r) { \
-        float2 wv[NP]; \
-        if (r < mnr) { \
-            const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(pl.vw + (size_t)(row0 + r) * AVP)); \
-            wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w); \
-            if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(pl.vw + (size_t)(row0 + r) * AVP + 4)); \
-        } else { _Pragma("unroll") for (int q = 0; q < NP; ++q) wv[q] = make_float2(0.0f, 0.0f); } \
-        _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-            const float x_ = hv::lds_f32(xr + (uint32_t)c * 128u + (uint32_t)r * 4u); const float2 vv = make_float2(x_, x_); \
-            _Pragma("unroll") for (int q = 0; q < NP; ++q) accV[(G_) % NG][c][q] = hv::ffma2(wv[q], vv, accV[(G_) % NG][c][q]); } \
-        if ((vm1 >> r) & 1u) { \
-            uint32_t nv = 1u; if ((vm2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r); \
-            for (uint32_t e2 = 0; e2 < nv; ++e2) { \
-                float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f}; \
-                switch (vs) { \
-                IFB_HV_VSLOT(G_, 0) IFB_HV_VSLOT(G_, 1) IFB_HV_VSLOT(G_, 2) IFB_HV_VSLOT(G_, 3) IFB_HV_VSLOT(G_, 4) IFB_HV_VSLOT(G_, 5) \
-                default: break; } \
-                if (Yl >= mY0 && Yl < mY1 && col_live) { \
-                    uint8_t* dst = out_px + (size_t)Yl * out_stride; \
-                    *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst); } \
-                ++Yl; vs = vs + 1 == AV ? 0 : vs + 1; } } } } break;
-#define IFB_HV_VSLOT(G_, S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int c = 0; c < CH; ++c) { \
-    float& a_ = (S_ & 1) ? accV[(G_) % NG][c][(S_ % AV) / 2].y : accV[(G_) % NG][c][(S_ % AV) / 2].x; f_[c] = a_; a_ = 0.0f; } } break;
-                                    switch (grp) {
-                                    IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3)
-                                    default: break;
-                                    }
-#undef IFB_HV_VGROUP
+                    wcur = wnext;
+
+                    if ((hmv >> 3) & 1u) {
+                        // ---- V pass of the columns parked since the last one (a "group", at most CG of them; the host put the mark where the
+                        // group is full or the strip ends): lane = (stream, output column sX0 + gX + cl).  The 32 H-filtered rows of the
+                        // block are multiply-added, in row order, into the group's ring of AV vertical accumulators (output row Y owns
+                        // slot Y mod AV); a completed output row goes through the store epilogue.
+                        hv::warp_sync();
+                        const bool col_live = cl < colbuf;
+                        uint8_t* const out_px = out_col + (size_t)gX * 4;
+                        auto vgroup = [&](float2 (&acc)[CH][NP]) {
+                            int Yl = Yc, vs = vslot;
+                            const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP;
+                            for (int r = 0; r < nr; ++r, vwp += AVP) {
+                                float2 wv[NP];
+                                {
+                                    const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(vwp));
+                                    wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w);
+                                    if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(vwp + 4));
+                                }
+#pragma unroll
+                                for (int ch_ = 0; ch_ < CH; ++ch_) {
+                                    const float x_ = hv::lds_f32(xr + (uint32_t)ch_ * 128u + (uint32_t)r * 4u);
+                                    const float2 vv = make_float2(x_, x_);
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) acc[ch_][q] = hv::ffma2(wv[q], vv, acc[ch_][q]);
+                                }
+                                if ((vm1 >> r) & 1u) {
+                                    uint32_t nv = 1u;
+                                    if ((vm2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r);
+                                    for (uint32_t e2 = 0; e2 < nv; ++e2) {
+                                        float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                                        switch (vs) {
+#define IFB_HV_VSLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) { \
+        float& a_ = (S_ & 1) ? acc[ch_][(S_ % AV) / 2].y : acc[ch_][(S_ % AV) / 2].x; f_[ch_] = a_; a_ = 0.0f; } } break;
+                                        IFB_HV_VSLOT(0) IFB_HV_VSLOT(1) IFB_HV_VSLOT(2) IFB_HV_VSLOT(3) IFB_HV_VSLOT(4) IFB_HV_VSLOT(5)
 #undef IFB_HV_VSLOT
-                                    hv::warp_sync();
-                                    ++grp; colbuf = 0; woff = 0;
+                                        default: break;
+                                        }
+                                        if (Yl >= mY0 && Yl < mY1 && col_live) {
+                                            uint8_t* dst = out_px + (size_t)Yl * out_stride;
+                                            *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
+                                        }
+                                        ++Yl; vs = vs + 1 == AV ? 0 : vs + 1;
+                                    }
                                 }
                             }
-                            ++Xc; hslot = hslot + 1 == AV ? 0 : hslot + 1;
+                        };
+                        switch (grp) {
+#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) vgroup(accV[(G_) % NG]); break;
+                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3) IFB_HV_VGROUP(4) IFB_HV_VGROUP(5) IFB_HV_VGROUP(6) IFB_HV_VGROUP(7)
+#undef IFB_HV_VGROUP
+                        default: break;
                         }
+                        hv::warp_sync();
+                        ++grp; gX += colbuf; colbuf = 0; xwA = xwa; xwB = xwb;
                     }
-                    goto hv_dispatch;
-                hv_stage_done:;
                 }
+                cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
                 // every group of the row block has seen the same rows: commit the vertical position of this lane's stream
                 Yc += (int)vtot;
                 vslot = (int)(((uint32_t)vslot + vtot) % (uint32_t)AV);

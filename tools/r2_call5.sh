@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round 2, fifth GPU call: ring kernel v4 (chunk loop, one-column software pipeline, host-planned V-pass groups).
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+T0=$SECONDS
+TAG=${1:-c5}
+note() { echo "[$((SECONDS-T0))s] $*" | tee -a gpurun_out/$TAG.log; }
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/${TAG}_parity.log 2>&1; note "parity rc=$? $(tail -3 gpurun_out/${TAG}_parity.log | tr '\n' ' ' | head -c 900)"
+timeout 300 python bench.py --steps 6 --no-cpu --no-e2e --no-others > gpurun_out/${TAG}_bench_c2.json 2>gpurun_out/${TAG}_bench_c2.err; note "bench c2 $(python tools/kms.py gpurun_out/${TAG}_bench_c2.json)"
+timeout 200 python bench.py --steps 4 --no-cpu --no-e2e --no-others --workload c2_4k_to_512_lanczos3 > gpurun_out/${TAG}_bench_l3.json 2>&1; note "bench lanczos3 $(python tools/kms.py gpurun_out/${TAG}_bench_l3.json)"
+timeout 200 python bench.py --steps 4 --no-cpu --no-e2e --no-others --alpha 1 > gpurun_out/${TAG}_bench_alpha.json 2>&1; note "bench c2 alpha $(python tools/kms.py gpurun_out/${TAG}_bench_alpha.json)"
+timeout 200 python bench.py --steps 4 --no-cpu --no-e2e --no-others --workload c3_8k_to_1080p_robidoux_sharpen > gpurun_out/${TAG}_bench_c3.json 2>&1; note "bench c3 $(python tools/kms.py gpurun_out/${TAG}_bench_c3.json)"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:hv_ring -s 2 -c 1 -o gpurun_out/prof_hv_$TAG python bench.py --batch 256 --steps 1 --warmup 1 --no-cpu --no-e2e --no-check --no-others > gpurun_out/${TAG}_ncu.log 2>&1; note "ncu rc=$? $(ls -la gpurun_out/prof_hv_$TAG.ncu-rep 2>&1 | head -c 200)"
+note "end"
