@@ -219,9 +219,9 @@ template <class F> void hv_for_av(int av, F&& f) { if (av == 4) f(std::integral_
 
 // host half: strips, per-strip H weights by ring slot in pixel-stream order, completion counts + V-pass marks, V weights by ring slot
 //
-// A strip's pixel stream is walked by the kernel in chunks of four source columns.  Output columns that complete are parked in the
-// warp's exchange buffer (room for cg columns) and the V pass of the parked columns (a "group") runs at the END of a chunk that
-// carries a mark (bit 7 of the completion byte of the chunk's last column): the marks are placed here, as late as the buffer allows,
+// A strip's pixel stream is walked by the kernel in pairs of chunks (eight source columns).  Output columns that complete are parked in
+// the warp's exchange buffer (room for cg columns) and the V pass of the parked columns (a "group") runs at the END of a pair that
+// carries a mark (bit 7 of the completion byte of the pair's last column): the marks are placed here, as late as the buffer allows,
 // and a strip may hold at most ng groups (the kernel keeps one set of vertical accumulators per group in registers).
 std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
     auto ht = std::make_unique<HvTables>();
@@ -234,19 +234,20 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
     // for bitmaps whose window starts on a 16-byte boundary; IFB200_DEBUG_K0_ALIGN=1 lifts that, for experiments)
     static const uint32_t k0_align = [] { const char* e = getenv("IFB200_DEBUG_K0_ALIGN"); const int v = e ? atoi(e) : 4; return (uint32_t)(v >= 1 && v <= 16 ? v : 4); }();
     auto k0_of = [&](uint32_t X0) { return h.left[X0] / k0_align * k0_align; };
-    // V-pass marks of [X0,X1): chunk indices after which a V pass runs; returns false if some chunk completes more than cg columns
+    // V-pass marks of [X0,X1): indices of the chunk PAIRS (eight source columns) after which a V pass runs; returns false if some
+    // pair completes more than cg columns or the strip needs more than ng groups
     auto marks_of = [&](uint32_t X0, uint32_t X1, std::vector<uint32_t>* marks) {
         const uint32_t k0 = k0_of(X0);
         uint32_t parked = 0, X = X0, groups = 0;
-        const uint32_t nchunks = (h.right[X1 - 1] - k0 + 1 + 15) / 16 * 4;
-        for (uint32_t c = 0; c < nchunks; ++c) {
+        const uint32_t npairs = (h.right[X1 - 1] - k0 + 1 + 15) / 16 * 2;
+        for (uint32_t c = 0; c < npairs; ++c) {
             uint32_t m = 0;
-            while (X < X1 && h.right[X] <= k0 + c * 4 + 3) { ++m; ++X; }
+            while (X < X1 && h.right[X] <= k0 + c * 8 + 7) { ++m; ++X; }
             if (m > (uint32_t)cg) return false;
             if (parked + m > (uint32_t)cg) { if (marks) marks->push_back(c - 1); ++groups; parked = 0; }
             parked += m;
         }
-        if (parked) { if (marks) marks->push_back(nchunks - 1); ++groups; }
+        if (parked) { if (marks) marks->push_back(npairs - 1); ++groups; }
         return groups <= (uint32_t)ng;
     };
     auto fits = [&](uint32_t X0, uint32_t X1) {   // [X0,X1): at most col_cap columns in at most ng groups, and a pixel stream (whole stages of 16, plus the chunk the kernel's pipeline reads ahead) within the table
@@ -302,7 +303,7 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
         }
         marks.clear();
         marks_of((uint32_t)sd.X0, (uint32_t)sd.X1, &marks);
-        for (uint32_t c : marks) hdone[(size_t)s * hd_stride + c * 4 + 3] |= 0x80u;
+        for (uint32_t c : marks) hdone[(size_t)s * hd_stride + c * 8 + 7] |= 0x80u;
     }
     for (uint32_t y = 0; y < v.out_size; ++y) {
         const float* w = v.w.data() + v.offset[y];
@@ -435,7 +436,7 @@ struct ifb200_batch {
     std::map<Key, std::unique_ptr<Plan>> plans;
     std::vector<PinnedSlot> pinned;
     // options
-    bool force_generic = false; int strip_cols = 64; int min_items = 0;
+    bool force_generic = false; int strip_cols = IFB_HV_MAXCOLS4; int min_items = 0;
     int sm_count = 148;
     // ring kernel: where dynamic shared memory starts in the shared window (probed once), whether TMA descriptors can be made
     uint32_t smem_base_low16 = 0x400u;
@@ -1217,7 +1218,7 @@ int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_p
                           char* err, size_t err_cap) {
     return guarded(err, err_cap, [&] {
         if (!d || !info) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
-        if (strip_cols < 16 || strip_cols > 64 || strip_cols % 16 || n_pairs < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band-pair count");
+        if (strip_cols < 16 || strip_cols > 128 || strip_cols % 16 || n_pairs < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band-pair count");
         memset(info, 0, sizeof *info);
         auto p = ifb200_batch::build_plan_host(*d, strip_cols);
         if (!p->hv_ok) return;                                            // info->ok stays 0: not a ring-kernel geometry
@@ -1334,7 +1335,7 @@ int ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value) {
     switch (option) {
     case IFB200_OPT_FORCE_GENERIC: b->force_generic = value != 0; return IFB200_OK;
     case IFB200_OPT_STRIP_COLUMNS:
-        if (value < 16 || value > 64 || value % 16) return IFB200_ERR_INVALID_ARGUMENT;
+        if (value < 16 || value > 128 || value % 16) return IFB200_ERR_INVALID_ARGUMENT;
         b->strip_cols = (int)value; return IFB200_OK;
     case IFB200_OPT_MIN_ITEMS:
         if (value < 0 || value > (1 << 24)) return IFB200_ERR_INVALID_ARGUMENT;

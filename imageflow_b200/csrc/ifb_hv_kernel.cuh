@@ -53,12 +53,15 @@ struct HvPlanDev {
 };
 struct alignas(64) HvTmap { unsigned char bytes[128]; };              // CUtensorMap of one job's input bitmap (u32 pixels, box 16 x 32, SWIZZLE_64B)
 
+#ifndef IFB_HV_MAXCOLS4
+#define IFB_HV_MAXCOLS4 64             // widest strip of the ring-depth-4 variants (V accumulators: 12 or 16 registers per 16 columns)
+#endif
 template <int AV, int CH> struct HvCfg {
     static_assert(AV == 4 || AV == 6, "ring depth");
     static constexpr int kAvp = AV == 4 ? 4 : 8;                      // floats per weight record
     static constexpr int kCapPx = 16384 / (kAvp * 4);                 // pixels of H weights that fit in the holes
     static constexpr int kCG = 16;                                    // output columns per group (x 2 streams = 32 lanes in the V pass)
-    static constexpr int kMaxCols = AV == 4 ? 64 : (CH == 3 ? 48 : 32);   // widest strip (output columns)
+    static constexpr int kMaxCols = AV == 4 ? IFB_HV_MAXCOLS4 : (CH == 3 ? 48 : 32);   // widest strip (output columns)
     static constexpr int kNG = kMaxCols / kCG + 1;                    // column groups per strip (V accumulators: NG * AV * CH registers); groups end on
                                                                       // chunk boundaries and are not always full, hence one more than the columns need
     static constexpr int kWarps = CH == 3 ? 8 : 6;
@@ -372,16 +375,15 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             const size_t out_stride = job.out_stride;
 
             for (int rb = 0; rb < nrb; ++rb) {
-                const int nr = min(32, nrmax - rb * 32);                   // rows of the row block (the longer stream's)
                 const int row0 = mJ0 + rb * 32;                            // this lane's stream
-                uint32_t vm1, vm2, vtot;                                   // this lane's stream: rows completing output rows
+                uint32_t vm1, vm2, vtot, vmA, vmB;                         // this lane's stream: rows completing output rows; both streams' (uniform)
                 {
                     const int ra = aJ0 + rb * 32 + lane, rbb = bJ0 + rb * 32 + lane;
                     const uint32_t vda = lane < aNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + ra) : 0u;
                     const uint32_t vdb = lane < bNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + rbb) : 0u;
                     const uint32_t a1 = hv::ballot(vda >= 1u), a2 = hv::ballot(vda >= 2u), b1 = hv::ballot(vdb >= 1u), b2 = hv::ballot(vdb >= 2u);
                     const uint32_t ta = hv::warp_sum(vda), tbb = hv::warp_sum(vdb);
-                    vm1 = laneB ? b1 : a1; vm2 = laneB ? b2 : a2; vtot = laneB ? tbb : ta;
+                    vm1 = laneB ? b1 : a1; vm2 = laneB ? b2 : a2; vtot = laneB ? tbb : ta; vmA = a1; vmB = b1;
                 }
                 float2 accA[CH][NP], accB[CH][NP];
 #pragma unroll
@@ -427,15 +429,19 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 };
                 wload(W0, wcur); conv(P0A, rawA.x); conv(P0B, rawB.x);
 
-                for (uint32_t c = 0; c < nchunks; ++c) {
-                    if ((c & 7u) == 0u) {                                  // completion masks of the next 32 source columns; the bytes after them are on their way
+                // The loop body is a PAIR of chunks (eight source columns): per-chunk bookkeeping is paid once for two, and the V pass
+                // marks sit on pair ends.
+                const uint32_t npairs = nchunks >> 1;
+                for (uint32_t pc = 0; pc < npairs; ++pc) {
+                    if ((pc & 3u) == 0u) {                                 // completion masks of the next 32 source columns; the bytes after them are on their way
                         HM1 = hv::ballot((hd_next & 0x7fu) >= 1u); HM2 = hv::ballot((hd_next & 0x7fu) >= 2u); HMV = hv::ballot((hd_next & 0x80u) != 0u);
-                        hd_next = (uint32_t)hv::ldg(hdone + (c + 8u) * 4u + (uint32_t)lane);
+                        hd_next = (uint32_t)hv::ldg(hdone + (pc + 4u) * 8u + (uint32_t)lane);
                     }
-                    const uint32_t sh = (c & 7u) * 4u;
-                    const uint32_t hm = HM1 >> sh, hm2 = HM2 >> sh, hmv = HMV >> sh;
-                    const uint32_t wnext = wcur + (AV == 4 ? ((c & 1u) ? 192u : 64u) : 256u);
-                    const bool more = c + 1u < nchunks;
+                    const uint32_t hm = HM1, hm2 = HM2, hmv = HMV;
+                    HM1 >>= 8; HM2 >>= 8; HMV >>= 8;
+                    const uint32_t wB = wcur + (AV == 4 ? 64u : 256u);     // second chunk's records
+                    const uint32_t wnext = wcur + (AV == 4 ? 256u : 512u); // next pair's
+                    const bool more = pc + 1u < npairs;
 
                     // a completed output column: both streams park their CH values in the exchange buffer, the ring slot is cleared
 #define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) { \
@@ -444,44 +450,59 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         hv::sts_f32(xwA + (uint32_t)ch_ * 128u, a_); hv::sts_f32(xwB + (uint32_t)ch_ * 128u, b_); a_ = 0.0f; b_ = 0.0f; } } break;
 #define IFB_HV_FLUSH(I_) if ((hm >> (I_)) & 1u) { \
         uint32_t n_ = 1u; \
-        if ((hm2 >> (I_)) & 1u) n_ = uni((uint32_t)hv::ldg(hdone + c * 4u + (I_)) & 0x7fu); \
+        if ((hm2 >> (I_)) & 1u) n_ = uni((uint32_t)hv::ldg(hdone + pc * 8u + (I_)) & 0x7fu); \
         _Pragma("unroll 1") do { \
             switch (hslot) { IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5) default: break; } \
             xwA += kXCol; xwB += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
         } while (--n_); }
 
-                    // ---- source column 0 of the chunk (column 1 on its way)
+                    // ---- first chunk: source column 0 (column 1 on its way), 1, 2, 3
                     wload(W1, wcur + kRec); conv(P1A, rawA.y); conv(P1B, rawB.y);
                     mac(P0A, P0B, W0);
                     IFB_HV_FLUSH(0)
-                    // ---- column 1
                     wload(W0, wcur + 2u * kRec); conv(P0A, rawA.z); conv(P0B, rawB.z);
                     mac(P1A, P1B, W1);
                     IFB_HV_FLUSH(1)
-                    // ---- column 2; the next chunk's sixteen bytes per stream replace this one's (all four columns are converted or in registers)
+                    // the next chunk's sixteen bytes per stream replace this one's (all four columns are converted or in registers)
                     wload(W1, wcur + 3u * kRec); conv(P1A, rawA.w); conv(P1B, rawB.w);
+                    {
+                        const uint32_t o_ = sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz);      // chunk 2 pc + 1 of the same stage
+                        rawA = hv::lds_u32x4(o_); rawB = hv::lds_u32x4(o_ + C::kBoxBytes);
+                    }
+                    mac(P0A, P0B, W0);
+                    IFB_HV_FLUSH(2)
+                    wload(W0, wB); conv(P0A, rawA.x); conv(P0B, rawB.x);
+                    mac(P1A, P1B, W1);
+                    IFB_HV_FLUSH(3)
+                    // ---- second chunk
+                    wload(W1, wB + kRec); conv(P1A, rawA.y); conv(P1B, rawB.y);
+                    mac(P0A, P0B, W0);
+                    IFB_HV_FLUSH(4)
+                    wload(W0, wB + 2u * kRec); conv(P0A, rawA.z); conv(P0B, rawB.z);
+                    mac(P1A, P1B, W1);
+                    IFB_HV_FLUSH(5)
+                    wload(W1, wB + 3u * kRec); conv(P1A, rawA.w); conv(P1B, rawB.w);
                     if (more) {
-                        if ((c & 3u) == 3u) {                              // next stage: refill the slot just emptied, wait for the next one
+                        if (pc & 1u) {                                     // next stage: refill the slot just emptied, wait for the next one
                             cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
                             if (is_n < total_stages) issue();
                             hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                             par ^= 1u << cs_s;
                             sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
                         }
-                        const uint32_t o_ = sbase + ((((c + 1u) & 3u) << 4) ^ swz);
+                        const uint32_t o_ = sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz);      // chunk 2 pc + 2
                         rawA = hv::lds_u32x4(o_); rawB = hv::lds_u32x4(o_ + C::kBoxBytes);
                     }
                     mac(P0A, P0B, W0);
-                    IFB_HV_FLUSH(2)
-                    // ---- column 3 (column 0 of the next chunk on its way)
+                    IFB_HV_FLUSH(6)
                     wload(W0, wnext); conv(P0A, rawA.x); conv(P0B, rawB.x);
                     mac(P1A, P1B, W1);
-                    IFB_HV_FLUSH(3)
+                    IFB_HV_FLUSH(7)
 #undef IFB_HV_FLUSH
 #undef IFB_HV_SLOT
                     wcur = wnext;
 
-                    if ((hmv >> 3) & 1u) {
+                    if ((hmv >> 7) & 1u) {
                         // ---- V pass of the columns parked since the last one (a "group", at most CG of them; the host put the mark where the
                         // group is full or the strip ends): lane = (stream, output column sX0 + gX + cl).  The 32 H-filtered rows of the
                         // block are multiply-added, in row order, into the group's ring of AV vertical accumulators (output row Y owns
@@ -489,26 +510,36 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                         hv::warp_sync();
                         const bool col_live = cl < colbuf;
                         uint8_t* const out_px = out_col + (size_t)gX * 4;
+                        const uint32_t vmU = vmA | vmB;                    // rows at which either stream completes an output row
                         auto vgroup = [&](float2 (&acc)[CH][NP]) {
                             int Yl = Yc, vs = vslot;
                             const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP;
-                            for (int r = 0; r < nr; ++r, vwp += AVP) {
-                                float2 wv[NP];
-                                {
-                                    const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(vwp));
-                                    wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w);
-                                    if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(vwp + 4));
-                                }
+                            uint32_t xrr = xr;
+                            // all 32 rows of the block (rows below a band's last carry no completion bit, and what they add to a slot is never
+                            // read), in runs that end with a row at which a stream completes an output row
+                            for (int r = 0; r < 32;) {
+                                const uint32_t rest = vmU >> r;
+                                const int n = rest ? __ffs((int)rest) : 32 - r;
+#pragma unroll 1
+                                for (int i = 0; i < n; ++i, vwp += AVP, xrr += 4u) {
+                                    float2 wv[NP];
+                                    {
+                                        const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(vwp));
+                                        wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w);
+                                        if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(vwp + 4));
+                                    }
 #pragma unroll
-                                for (int ch_ = 0; ch_ < CH; ++ch_) {
-                                    const float x_ = hv::lds_f32(xr + (uint32_t)ch_ * 128u + (uint32_t)r * 4u);
-                                    const float2 vv = make_float2(x_, x_);
+                                    for (int ch_ = 0; ch_ < CH; ++ch_) {
+                                        const float x_ = hv::lds_f32(xrr + (uint32_t)ch_ * 128u);
+                                        const float2 vv = make_float2(x_, x_);
 #pragma unroll
-                                    for (int q = 0; q < NP; ++q) acc[ch_][q] = hv::ffma2(wv[q], vv, acc[ch_][q]);
+                                        for (int q = 0; q < NP; ++q) acc[ch_][q] = hv::ffma2(wv[q], vv, acc[ch_][q]);
+                                    }
                                 }
-                                if ((vm1 >> r) & 1u) {
+                                r += n;
+                                if (rest != 0u && ((vm1 >> (r - 1)) & 1u)) {
                                     uint32_t nv = 1u;
-                                    if ((vm2 >> r) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r);
+                                    if ((vm2 >> (r - 1)) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r - 1);
                                     for (uint32_t e2 = 0; e2 < nv; ++e2) {
                                         float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                                         switch (vs) {
@@ -529,7 +560,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                         };
                         switch (grp) {
 #define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) vgroup(accV[(G_) % NG]); break;
-                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3) IFB_HV_VGROUP(4) IFB_HV_VGROUP(5) IFB_HV_VGROUP(6) IFB_HV_VGROUP(7)
+                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3) IFB_HV_VGROUP(4) IFB_HV_VGROUP(5) IFB_HV_VGROUP(6) IFB_HV_VGROUP(7) IFB_HV_VGROUP(8)
 #undef IFB_HV_VGROUP
                         default: break;
                         }

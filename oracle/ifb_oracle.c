@@ -9,13 +9,13 @@
  *
  *   load    p[j][x] = (T[b]*af, T[g]*af, T[r]*af, af), af = a*(1/255f)    when alpha is meaningful
  *                     (T[b], T[g], T[r], 0)                                otherwise (scaling.rs:294-302)
- *   V pass  V[y][x][c] = fmaf-chain over j = left_y..right_y ascending, starting from +0
- *   H pass  F[y][X][c] = sum over aligned groups g of 4 input columns (k/4 == g) ascending of
- *                        P_g, P_g = fmaf-chain over the taps of X that fall in group g, from +0
+ *   H pass  H[j][X][c] = fmaf-chain over the taps k = left_x..right_x of output column X, ascending, starting from +0
+ *                        (every source row is filtered horizontally as it streams in, like zenresize's push_row)
+ *   V pass  F[y][X][c] = fmaf-chain over the H-filtered rows j = left_y..right_y, ascending, starting from +0
  *   store   un-premultiply (only if a > 0), encode, compose (scaling.rs:55-88)
  *
- * The grouping of the H sum in blocks of 4 columns is part of the specification (it is what
- * lets the GPU kernel give every input column to exactly one thread); it is documented in DESIGN.md.
+ * Round 2 changed the order from V-then-H (with the H sum grouped by four source columns) to this plain H-then-V statement:
+ * it is the order of a streaming resizer, and both chains are strictly sequential (no grouping); DESIGN.md section 3.
  */
 #include "ifb_oracle.h"
 #include <math.h>
