@@ -225,7 +225,7 @@ template <class F> void hv_for_av(int av, F&& f) { if (av == 4) f(std::integral_
 // and a strip may hold at most ng groups (the kernel keeps one set of vertical accumulators per group in registers).
 std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
     auto ht = std::make_unique<HvTables>();
-    const int max_cols = cols_key & 0xffff, ng = cols_key >> 16, cg = 16;   // hv_cols(): widest strip | groups the kernel variant holds << 16
+    const int max_cols = cols_key & 0xffff, ng = cols_key >> 16, cg = 32 / (p.av / 2);   // hv_cols(): widest strip | groups the kernel variant holds << 16; columns per V-pass group
     ht->max_cols = max_cols;
     const auto& h = p.wh; const auto& v = p.wv;
     const int av = p.av, avp = av == 4 ? 4 : 8, cap = 16384 / (avp * 4);
@@ -336,11 +336,10 @@ HvTables& hv_tables(ifb200_batch* bt, cudaStream_t st, Plan& p, int max_cols) {
     return ht;
 }
 
-// Row bands of one launch: a warp works on a PAIR of bands (two streams), so 2 * pairs bands: output rows split evenly, each
-// band with the source rows its windows need; bands beyond the last output row are empty (a stream that does nothing).
-std::vector<HvBandDev> hv_bands(const Plan& p, int pairs) {
+// Row bands of one launch (a warp's work item is one band of one strip of one job): output rows split evenly, each band with the
+// source rows its windows need.
+std::vector<HvBandDev> hv_bands(const Plan& p, int nb) {
     const auto& v = p.wv;
-    const int nb = 2 * pairs;
     std::vector<HvBandDev> bands;
     for (int i = 0; i < nb; ++i) {
         const uint32_t Y0 = (uint32_t)((uint64_t)p.out_h * i / nb), Y1 = (uint32_t)((uint64_t)p.out_h * (i + 1) / nb);
@@ -355,21 +354,23 @@ std::vector<HvBandDev> hv_bands(const Plan& p, int pairs) {
     }
     return bands;
 }
-// Band pairs of a launch.  min_items > 0 (IFB200_OPT_MIN_ITEMS): the smallest count that gives that many work items.  Otherwise:
-// enough pairs to give every warp of the device one item; and when there is more than one round of items anyway, the count
-// whose last round is fullest, counting what the band halos (the V window is re-read at every band edge) cost.
-int hv_pick_pairs(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
-    const int max_np = (int)std::max<uint32_t>(1u, p.out_h / 16u);
-    auto need = [&](size_t items) { return (int)std::min<size_t>((size_t)max_np, std::max<size_t>(1, (items + jobs_x_strips - 1) / jobs_x_strips)); };
+// Bands of a launch.  min_items > 0 (IFB200_OPT_MIN_ITEMS): the smallest count that gives that many work items.  Otherwise:
+// enough bands to give every warp of the device one item; and when there is more than one round of items anyway, the count
+// whose last round is fullest, counting what the band halos (the V window is re-read at every band edge, and a band's rows are
+// walked in blocks of 32) cost.
+int hv_pick_bands(const Plan& p, size_t jobs_x_strips, int warps, int min_items) {
+    const int max_nb = (int)std::max<uint32_t>(1u, p.out_h / 8u);
+    auto need = [&](size_t items) { return (int)std::min<size_t>((size_t)max_nb, std::max<size_t>(1, (items + jobs_x_strips - 1) / jobs_x_strips)); };
     if (min_items > 0) return need((size_t)min_items);
-    const int np0 = need((size_t)warps);
-    if (jobs_x_strips * (size_t)np0 <= (size_t)warps) return np0;
-    const double halo = (double)p.wv.max_taps / (double)std::max<uint32_t>(p.in_h, 1u);
-    int best = np0; double best_eff = -1.0;
-    for (int np = np0; np <= std::min(max_np, np0 + 7); ++np) {
-        const double items = (double)jobs_x_strips * np;
-        const double eff = items / warps / std::ceil(items / warps) / (1.0 + halo * (2 * np - 1));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best = np; }
+    const int nb0 = need((size_t)warps);
+    if (jobs_x_strips * (size_t)nb0 <= (size_t)warps) return nb0;
+    int best = nb0; double best_eff = -1.0;
+    for (int nb = nb0; nb <= std::min(max_nb, nb0 + 15); ++nb) {
+        const double items = (double)jobs_x_strips * nb;
+        const double rows = (double)p.in_h / nb + (double)p.wv.max_taps;              // source rows of a band
+        const double cost = std::ceil(rows / 32.0) * 32.0 * nb / (double)std::max<uint32_t>(p.in_h, 1u);   // rows walked / rows of the bitmap
+        const double eff = items / warps / std::ceil(items / warps) / cost;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = nb; }
     }
     return best;
 }
@@ -732,10 +733,10 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             const HvTables& ht = *p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols));
             const size_t jxs = g.idx.size() * (size_t)ht.n_strips;
             const int warps_all = b->sm_count * he->warps;
-            const int pairs = hv_pick_pairs(p, jxs, warps_all, b->min_items);
-            lay[gi].bv = hv_bands(p, pairs);
+            const int nb = hv_pick_bands(p, jxs, warps_all, b->min_items);
+            lay[gi].bv = hv_bands(p, nb);
             lay[gi].nb = (int)lay[gi].bv.size();
-            const size_t items = jxs * pairs;
+            const size_t items = jxs * nb;
             lay[gi].grid = (int)std::min<size_t>((size_t)b->sm_count, (items + he->warps - 1) / he->warps);
             lay[gi].tmaps = take(g.idx.size() * sizeof(HvTmap));
             lay[gi].bands = take(lay[gi].bv.size() * sizeof(HvBandDev));
@@ -1218,7 +1219,7 @@ int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_p
                           char* err, size_t err_cap) {
     return guarded(err, err_cap, [&] {
         if (!d || !info) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
-        if (strip_cols < 16 || strip_cols > 128 || strip_cols % 16 || n_pairs < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band-pair count");
+        if (strip_cols < 16 || strip_cols > 128 || strip_cols % 16 || n_pairs < 1) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "bad strip width or band count");
         memset(info, 0, sizeof *info);
         auto p = ifb200_batch::build_plan_host(*d, strip_cols);
         if (!p->hv_ok) return;                                            // info->ok stays 0: not a ring-kernel geometry

@@ -4,23 +4,24 @@
 // horizontally as it arrives, output rows are emitted as soon as their vertical window is complete.  Down-scales (and 1:1)
 // whose contribution windows keep at most AV <= 6 outputs open per source sample on both axes run here.
 //
-// Decomposition: ONE WARP = one work item = (job, strip of <= NG*16 output columns, PAIR of bands of output rows), and inside it
-// LANE = SOURCE ROW of each of the two bands ("streams" A and B): a lane filters row r of band A and row r of band B side by side.
-// A warp walks its bands 32 source rows at a time ("row block"); for every row block it streams the strip's source columns left to right:
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) stages one box of 16 pixels x 32 rows per stream into the warp's own shared-memory
-//     ring (kStages deep, one mbarrier per stage; the same warp issues, waits and consumes: no other synchronisation exists in
-//     this kernel).  The 64-byte swizzle makes the per-lane 16-byte reads of "my row" bank-conflict free.
-//   * H pass: every lane converts its two pixels through the lane-replicated LUT (one PRMT + one conflict-free LDS per channel)
-//     and multiply-adds them into two rings of AV accumulators: output column X owns slot X mod AV while its window is open.
-//     The weights of a source column are the same for all lanes and both streams: one broadcast LDS.128 per source column of a
-//     table the CTA keeps in shared memory.  The whole horizontal reduction (7.5 : 1 for 4K -> 512) happens in registers with no
-//     exchange between threads; what steers it (which column completes where) is warp-uniform and costs once for both streams.
-//   * When a column completes, its CH values of both streams go to the warp's exchange buffer [stream][column][channel][row];
-//     after 16 columns (a "group") the warp turns around: LANE = (stream, OUTPUT COLUMN), and the 32 H-filtered rows of the block
-//     are multiply-added, in row order, into the group's ring of AV vertical accumulators (output row Y owns slot Y mod AV).  A
-//     completed output row goes through the store epilogue and is written as a coalesced 64-byte segment per stream.
-// Two streams per lane instead of twice the warps: the same shared memory per SM, but the weight fetches, the completion
-// bookkeeping and every branch are paid once for two rows, and each warp carries two independent dependency chains.
+// Decomposition: ONE WARP = one work item = (job, strip of output columns, band of output rows), and inside it LANE = SOURCE ROW.
+// A warp walks its band 32 source rows at a time ("row block"); for every row block it streams the strip's source columns left to right:
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_64B) stages one box of 16 pixels x 32 rows into the warp's own shared-memory ring
+//     (kStages deep, one mbarrier per stage; the same warp issues, waits and consumes: no other synchronisation exists in this
+//     kernel).  The 64-byte swizzle makes the per-lane 16-byte reads of "my row" bank-conflict free.
+//   * H pass: every lane converts its pixel through the lane-replicated LUT (one PRMT + one conflict-free LDS per channel) and
+//     multiply-adds it into a ring of AV accumulators: output column X owns slot X mod AV while its window is open.  The weights
+//     of a source column are the same for all lanes: one broadcast LDS.128 per source column of a table the CTA keeps in shared
+//     memory.  The whole horizontal reduction (7.5 : 1 for 4K -> 512) happens in registers with no exchange between threads; what
+//     steers it (which column completes where) is warp-uniform.
+//   * When a column completes, its CH values go to the warp's exchange buffer [column][channel][row]; after kCG columns (a "group")
+//     the warp turns around: LANE = (pair of ring slots, OUTPUT COLUMN), and the 32 H-filtered rows of the block are multiply-added,
+//     in row order, into the group's vertical accumulators (output row Y owns slot Y mod AV; a lane holds two of the AV slots of
+//     its column as one packed pair, so the 32 lanes do AV/2 x kCG columns).  A completed output row goes through the store
+//     epilogue in the lanes that hold its slot and is written as one coalesced segment.
+// One 32-row stream per warp and as many warps as shared memory holds (16, or 12 with four channels): the first form of this
+// kernel gave every lane two streams in half as many warps; at two warps per scheduler every branch, instruction-cache miss and
+// fixed latency was exposed (37 % issue utilisation, profiles/r2_hv_v5_ncu_summary.txt).
 // Every source pixel is read from HBM once (plus strip/band halos), converted once; nothing but source and destination
 // pixels touches HBM.  Arithmetic: the H chain ascends over source columns from +0, the V chain over source rows from +0 --
 // exactly the order of the specification; a slot only ever sees zero weights outside its window, and fmaf(+0, v, acc) == acc.
@@ -30,8 +31,7 @@
 //   driver puts dynamic shared memory): row v (256 B): bytes 0..127 = T[v] for the 32 lanes, so the window address of a lookup
 //   is LUT | v << 8 | lane << 2 -- one PRMT, bank-conflict free for any image content.  Bytes 128..255 of the rows ("holes"):
 //   holes 0..127 = the 16 KB linear->sRGB table of the store epilogue, holes 128..255 = the strip's H weights (16 KB).
-//   Around it, per warp: stage ring, the two halves of the exchange buffer, mbarriers (hv_layout() packs them into the space
-//   before and after the LUT block).
+//   Around it, per warp: stage ring, exchange buffer, mbarriers (hv_layout() packs them into the space before and after the LUT block).
 #pragma once
 
 #ifndef IFB_HV_EMU
@@ -60,50 +60,53 @@ template <int AV, int CH> struct HvCfg {
     static_assert(AV == 4 || AV == 6, "ring depth");
     static constexpr int kAvp = AV == 4 ? 4 : 8;                      // floats per weight record
     static constexpr int kCapPx = 16384 / (kAvp * 4);                 // pixels of H weights that fit in the holes
-    static constexpr int kCG = 16;                                    // output columns per group (x 2 streams = 32 lanes in the V pass)
-    static constexpr int kMaxCols = AV == 4 ? IFB_HV_MAXCOLS4 : (CH == 3 ? 48 : 32);   // widest strip (output columns)
-    static constexpr int kNG = kMaxCols / kCG + 1;                    // column groups per strip (V accumulators: NG * AV * CH registers); groups end on
-                                                                      // chunk boundaries and are not always full, hence one more than the columns need
-    static constexpr int kWarps = CH == 3 ? 8 : 6;
+    static constexpr int kNP = AV / 2;                                // packed slot pairs
+    static constexpr int kCG = 32 / kNP;                              // output columns per group: kNP x kCG lanes in the V pass (16, or 10 at ring depth 6)
+    static constexpr int kMaxCols = AV == 4 ? IFB_HV_MAXCOLS4 : (CH == 3 ? 50 : 40);   // widest strip (output columns)
+    static constexpr int kNG = kMaxCols / kCG + 1;                    // column groups per strip (V accumulators: 2 * CH registers per group); groups end on
+                                                                      // chunk-pair boundaries and are not always full, hence one more than the columns need
+    static constexpr int kWarps = CH == 3 ? 16 : 12;
     static constexpr int kThreads = kWarps * 32;
     static constexpr int kStages = 2;
-    static constexpr int kBoxBytes = 32 * 64;                         // one stream's box: 32 rows x 16 pixels
-    static constexpr int kStageBytes = 2 * kBoxBytes;                 // streams A and B
+    static constexpr int kBoxBytes = 32 * 64;                         // one box: 32 rows x 16 pixels
+    static constexpr int kStageBytes = kBoxBytes;
+    static constexpr int kRingBytes = kStages * kStageBytes;
     static constexpr int kXPitch = CH * 32 + 1;                       // words per column of the exchange buffer (odd: conflict-free both ways)
-    static constexpr int kXHalfBytes = kCG * kXPitch * 4;             // one stream's half; == 64 (mod 128), see hv_layout
-    static_assert(kXHalfBytes % 128 == 64, "the B half must sit 16 banks away from the A half");
+    static constexpr int kXBytes = kCG * kXPitch * 4;
 };
 
 // Shared-memory packing for a given low half of the shared-window base (the LUT block must start on a 64 KB boundary of the
-// window, which splits dynamic shared memory into a region before it and one after it).  Blocks, first fit, in this order: every
-// warp's stage ring (512-byte aligned: the swizzle pattern repeats every 512 bytes), then every warp's exchange-buffer halves
-// (A on a 128-byte boundary, B 64 bytes past one: the V pass reads both halves in one request and they must use different
-// banks), then the mbarriers.  Returns the bytes of dynamic shared memory needed; fills the window OFFSETS (from the dynamic
-// shared-memory base) of warp `warp`'s blocks when the pointers are given.
+// window, which splits dynamic shared memory into a region before it and one after it).  Per warp: a stage ring (512-byte aligned:
+// the swizzle pattern repeats every 512 bytes), an exchange buffer (16-byte aligned), kStages mbarriers.  The region before the
+// LUT block takes as many rings and then exchange buffers as fill it best; the rest follows the block.  Returns the bytes of dynamic
+// shared memory needed; fills the window OFFSETS (from the dynamic shared-memory base) of warp `warp`'s blocks when the pointers are given.
 template <int AV, int CH>
-__host__ __device__ constexpr uint32_t hv_layout(uint32_t sb_low16, int warp, uint32_t* st_off, uint32_t* xa_off, uint32_t* xb_off, uint32_t* mb_off) {
+__host__ __device__ constexpr uint32_t hv_layout(uint32_t sb_low16, int warp, uint32_t* st_off, uint32_t* x_off, uint32_t* mb_off) {
     using C = HvCfg<AV, CH>;
     const uint32_t lut_off = (0x10000u - sb_low16) & 0xffffu;
-    uint32_t cur_a = 0, end_a = lut_off, cur_b = lut_off + 65536u;    // offsets; window address = sb + offset, and sb_low16 fixes alignment
-    auto place = [&](uint32_t bytes, uint32_t align, uint32_t phase) -> uint32_t {
-        // smallest offset >= cursor with (sb_low16 + offset) % align == phase
-        auto fit = [&](uint32_t cur) { const uint32_t w = sb_low16 + cur; const uint32_t r = (w % align + align - phase) % align; return cur + (r ? align - r : 0u); };
-        const uint32_t a = fit(cur_a);
-        if (a + bytes <= end_a) { cur_a = a + bytes; return a; }
-        const uint32_t b = fit(cur_b);
-        cur_b = b + bytes;
-        return b;
-    };
-    for (int w = 0; w < C::kWarps; ++w) { const uint32_t o = place((uint32_t)C::kStages * C::kStageBytes, 512u, 0u); if (w == warp && st_off) *st_off = o; }
-    for (int w = 0; w < C::kWarps; ++w) {
-        const uint32_t oa = place((uint32_t)C::kXHalfBytes, 128u, 0u);
-        const uint32_t ob = place((uint32_t)C::kXHalfBytes, 128u, 64u);
-        if (w == warp) { if (xa_off) *xa_off = oa; if (xb_off) *xb_off = ob; }
+    const uint32_t ring = (uint32_t)C::kRingBytes, xb = (uint32_t)C::kXBytes, W = (uint32_t)C::kWarps;
+    const uint32_t a0 = (512u - (sb_low16 & 511u)) & 511u;             // first 512-byte aligned offset of the region before the block
+    const uint32_t roomA = lut_off > a0 ? lut_off - a0 : 0u;
+    uint32_t ra = 0, xa = 0, best = 0;                                 // rings / exchange buffers placed before the block
+    for (uint32_t r = 0; r <= W; ++r) {
+        if (r * ring > roomA) break;
+        uint32_t x = (roomA - r * ring) / xb;
+        if (x > W) x = W;
+        const uint32_t used = r * ring + x * xb;
+        if (used > best) { best = used; ra = r; xa = x; }
     }
-    for (int w = 0; w < C::kWarps; ++w) { const uint32_t o = place(8u * C::kStages, 8u, 0u); if (w == warp && mb_off) *mb_off = o; }
-    return cur_b;
+    const uint32_t b0 = lut_off + 65536u;                              // window address there is a multiple of 64 KB
+    const uint32_t b_x = b0 + (W - ra) * ring;                         // exchange buffers behind the block's rings
+    const uint32_t b_mb = (b_x + (W - xa) * xb + 7u) & ~7u;
+    if (warp >= 0) {
+        const uint32_t w = (uint32_t)warp;
+        if (st_off) *st_off = w < ra ? a0 + w * ring : b0 + (w - ra) * ring;
+        if (x_off) *x_off = w < xa ? a0 + ra * ring + w * xb : b_x + (w - xa) * xb;
+        if (mb_off) *mb_off = b_mb + w * 8u * (uint32_t)C::kStages;
+    }
+    return b_mb + W * 8u * (uint32_t)C::kStages;
 }
-template <int AV, int CH> constexpr uint32_t hv_total_bytes(uint32_t sb_low16) { return hv_layout<AV, CH>(sb_low16, -1, nullptr, nullptr, nullptr, nullptr); }
+template <int AV, int CH> constexpr uint32_t hv_total_bytes(uint32_t sb_low16) { return hv_layout<AV, CH>(sb_low16, -1, nullptr, nullptr, nullptr); }
 
 // ---------------------------------------------------------------- primitives (tests/cpu_emu provides its own under IFB_HV_EMU)
 #ifndef IFB_HV_EMU
@@ -156,16 +159,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(addr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    // try_wait suspends the thread for a hardware-defined time before it reports failure, so the retry loop is rarely taken;
-    // a transfer that never completes (a bad descriptor) traps after a few seconds instead of hanging the device
-    for (uint32_t tries = 0;; ++tries) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) return;
-        if (tries > (1u << 24)) __trap();
-    }
+    // The retry loop lives inside the asm statement, with uniform branches: written as a C loop it made ptxas give up on the
+    // warp being converged for the rest of the kernel (every vote behind a BRA.DIV, every warp-uniform branch wrapped in
+    // BSSY/BSYNC).  try_wait suspends the thread for a hardware-defined time before it reports failure, so the loop is rarely
+    // taken; a transfer that never completes (a bad descriptor) is given up after a few seconds instead of hanging the device (a
+    // `trap` in this loop brings the convergence barriers back).
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+                 "mov.u32 n, 0;\n\t"
+                 "IFB_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra.uni IFB_DONE;\n\t"
+                 "add.u32 n, n, 1;\n\t"
+                 "setp.lt.u32 p, n, 0x1000000;\n\t"
+                 "@p bra.uni IFB_WAIT;\n\t"
+                 "IFB_DONE:\n\t}" :: "r"(addr), "r"(parity) : "memory");
 }
 // one box of 16 pixels x 32 rows at pixel (x, y) of the job's bitmap -> shared memory, completion counted on the mbarrier
 __device__ __forceinline__ void tma_load_box(uint32_t dst, const HvTmap* tm, int x, int y, uint32_t mbar) {
@@ -256,21 +263,20 @@ __global__ void __launch_bounds__(HvCfg<AV, CH>::kThreads, 1)
 hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps, Tables tb, HvPlanDev pl, uint32_t n_jobs,
                uint32_t* __restrict__ counters) {
     using C = HvCfg<AV, CH>;
-    constexpr int AVP = C::kAvp, NG = C::kNG, NP = AV / 2, S = C::kStages, CG = C::kCG;
+    constexpr int AVP = C::kAvp, NG = C::kNG, NP = C::kNP, S = C::kStages, CG = C::kCG;
     constexpr uint32_t kRec = (uint32_t)AVP * 4u;                          // bytes per H weight record (one source column)
     constexpr uint32_t kXCol = (uint32_t)C::kXPitch * 4u;                  // bytes per column of the exchange buffer
     IFB_HV_DYNAMIC_SMEM(hv_smem);
     const uint32_t sb = hv::smem_u32(hv_smem);
     const uint32_t lut = sb + ((0x10000u - (sb & 0xffffu)) & 0xffffu);     // window address of the LUT block: low 16 bits are zero
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    // A value that is the same in every lane, rebuilt from a warp vote: the compiler then KNOWS it is warp-uniform and keeps it --
-    // and every loop counter, address and branch derived from it -- on the uniform datapath (no divergence bookkeeping).
+    // A value that is the same in every lane, rebuilt from a warp vote: the compiler then KNOWS it is warp-uniform.
     auto uni = [&](uint32_t v) -> uint32_t { return hv::ballot((v >> lane) & 1u); };
-    uint32_t stb, xa, xb, mb;                                              // this warp's stage ring, exchange-buffer halves, mbarriers (window addresses)
+    uint32_t stb, xbuf, mb;                                                // this warp's stage ring, exchange buffer, mbarriers (window addresses)
     {
-        uint32_t o_st = 0, o_xa = 0, o_xb = 0, o_mb = 0;
-        hv_layout<AV, CH>(sb & 0xffffu, warp, &o_st, &o_xa, &o_xb, &o_mb);
-        stb = sb + o_st; xa = sb + o_xa; xb = sb + o_xb; mb = sb + o_mb;
+        uint32_t o_st = 0, o_x = 0, o_mb = 0;
+        hv_layout<AV, CH>(sb & 0xffffu, warp, &o_st, &o_x, &o_mb);
+        stb = sb + o_st; xbuf = sb + o_x; mb = sb + o_mb;
     }
     const uint32_t flags0 = jobs[0].flags;                                 // working space and channel count are the same for all jobs of a launch
 
@@ -292,15 +298,15 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
     // SWIZZLE_64B: 16-byte chunk index ^= (address >> 7) & 3; this lane's row starts at lane * 64: chunk k of "my row" lies at
     // lane * 64 + ((k << 4) ^ swz)
     const uint32_t swz = (((uint32_t)lane >> 1) & 3u) << 4;
-    const uint32_t n_pairs = (uint32_t)pl.n_bands >> 1;
-    const uint32_t n_items = n_jobs * n_pairs;
+    const uint32_t n_bands = (uint32_t)pl.n_bands;
+    const uint32_t n_items = n_jobs * n_bands;
     const uint32_t lutw = lut + 128u * 256u + 128u;                        // hole 128: the strip's H weights
     const bool leader = hv::elect_one();                                   // the lane that talks to the TMA unit
-    // V pass role of this lane: stream (lane >> 4), column (lane & 15) of the group
-    const bool laneB = lane >= CG;
-    const uint32_t cl = (uint32_t)lane & (uint32_t)(CG - 1);
-    const uint32_t xr = (laneB ? xb : xa) + cl * kXCol;
-    const uint32_t xwa = xa + (uint32_t)lane * 4u, xwb = xb + (uint32_t)lane * 4u;   // H pass role: row `lane` of column 0
+    // V pass role of this lane: slot pair vh (ring slots 2 vh, 2 vh + 1) of column cl of the group; lanes beyond NP * CG idle
+    const uint32_t vh = (uint32_t)lane / (uint32_t)CG, cl = (uint32_t)lane % (uint32_t)CG;
+    const bool vlane = vh < (uint32_t)NP;
+    const uint32_t xr = xbuf + cl * kXCol;
+    const uint32_t xw0 = xbuf + (uint32_t)lane * 4u;                       // H pass role: row `lane` of column 0
 
     for (int sv = 0; sv < pl.n_strips; ++sv) {
         const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
@@ -316,24 +322,21 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         }
         hv::cta_sync();
         const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 64);
-        const uint32_t nchunks = (uint32_t)nst * 4u;
+        const uint32_t npairs = (uint32_t)nst * 2u;                        // chunk pairs (eight source columns) per row block
 
         for (;;) {
             uint32_t item = 0;
             if (lane == 0) item = hv::atomic_inc(counters + s);
             item = uni(hv::bcast0(item));
             if (item >= n_items) break;
-            const uint32_t job_i = item / n_pairs, pair_i = item - job_i * n_pairs;
+            const uint32_t job_i = item / n_bands, band_i = item - job_i * n_bands;
             const JobDev& job = jobs[job_i];
             const HvTmap* tm = tmaps + job_i;
-            const HvBandDev ba_ = pl.bands[2u * pair_i], bb_ = pl.bands[2u * pair_i + 1u];
-            const int aJ0 = (int)uni((uint32_t)ba_.j0), aNr = (int)uni((uint32_t)ba_.nrows), bJ0 = (int)uni((uint32_t)bb_.j0), bNr = (int)uni((uint32_t)bb_.nrows);
-            // this lane's stream in the V pass
-            const HvBandDev& bm_ = laneB ? bb_ : ba_;
-            const int mY0 = bm_.Y0, mY1 = bm_.Y1, mJ0 = bm_.j0;
+            const HvBandDev bd_ = pl.bands[band_i];
+            const int bJ0 = (int)uni((uint32_t)bd_.j0), bNr = (int)uni((uint32_t)bd_.nrows);
+            const int bY0 = (int)uni((uint32_t)bd_.Y0), bY1 = (int)uni((uint32_t)bd_.Y1);
             const uint32_t flags = uni(job.flags);
-            const int nrmax = max(aNr, bNr);
-            const int nrb = (nrmax + 31) >> 5;
+            const int nrb = (bNr + 31) >> 5;
             const int x_origin = sK0 + (int)uni(job.in_xoff);
 
             // ---- TMA pipeline state: stages are numbered row block by row block
@@ -343,17 +346,15 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 hv::warp_sync();                                           // every lane has read what the refilled slot held
                 if (leader) {
                     const uint32_t bar = mb + 8u * (uint32_t)is_s;
-                    const uint32_t dst = stb + (uint32_t)is_s * C::kStageBytes;
                     hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
-                    hv::tma_load_box(dst, tm, x_origin + is_x * 16, aJ0 + is_y * 32, bar);
-                    hv::tma_load_box(dst + C::kBoxBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
+                    hv::tma_load_box(stb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
 #if IFB_HV_PREFETCH_AHEAD > 0
-                    // every fourth stage: the boxes IFB_HV_PREFETCH_AHEAD stages further on their way into L2 (the descriptor promotes
+                    // every fourth stage: the box IFB_HV_PREFETCH_AHEAD stages further on its way into L2 (the descriptor promotes
                     // every request to its 256-byte line, i.e. to the width of four stages)
                     if ((is_x & 3) == 0) {
                         int px = is_x + IFB_HV_PREFETCH_AHEAD, py = is_y;
                         if (px >= nst) { px -= nst; ++py; }
-                        if (py < nrb) { hv::tma_prefetch_box(tm, x_origin + px * 16, aJ0 + py * 32); hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32); }
+                        if (py < nrb) hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32);
                     }
 #endif
                 }
@@ -363,49 +364,44 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             for (int i = 0; i < S - 1 && is_n < total_stages; ++i) issue();
             int cs_s = 0;                                                  // ring slot of the stage being consumed
 
-            float2 accV[NG][CH][NP];
+            float2 accV[NG][CH];                                           // this lane's slot pair of column cl of every group
 #pragma unroll
             for (int gq = 0; gq < NG; ++gq)
 #pragma unroll
-                for (int c = 0; c < CH; ++c)
-#pragma unroll
-                    for (int q = 0; q < NP; ++q) accV[gq][c][q] = make_float2(0.0f, 0.0f);
-            int Yc = bm_.Yf, vslot = bm_.vslot0;                           // this lane's stream: next output row to complete at the start of the row block, its slot
+                for (int c = 0; c < CH; ++c) accV[gq][c] = make_float2(0.0f, 0.0f);
+            int Yc = (int)uni((uint32_t)bd_.Yf);                           // next output row to complete at the start of the row block, and its slot
+            uint32_t vslot = uni((uint32_t)bd_.vslot0);
             uint8_t* const out_col = job.out + (size_t)(sX0 + (int)cl) * 4;
             const size_t out_stride = job.out_stride;
 
             for (int rb = 0; rb < nrb; ++rb) {
-                const int row0 = mJ0 + rb * 32;                            // this lane's stream
-                uint32_t vm1, vm2, vtot, vmA, vmB;                         // this lane's stream: rows completing output rows; both streams' (uniform)
+                const int row0 = bJ0 + rb * 32;
+                uint32_t vm1, vm2, vtot;                                   // rows of the block completing output rows
                 {
-                    const int ra = aJ0 + rb * 32 + lane, rbb = bJ0 + rb * 32 + lane;
-                    const uint32_t vda = lane < aNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + ra) : 0u;
-                    const uint32_t vdb = lane < bNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + rbb) : 0u;
-                    const uint32_t a1 = hv::ballot(vda >= 1u), a2 = hv::ballot(vda >= 2u), b1 = hv::ballot(vdb >= 1u), b2 = hv::ballot(vdb >= 2u);
-                    const uint32_t ta = hv::warp_sum(vda), tbb = hv::warp_sum(vdb);
-                    vm1 = laneB ? b1 : a1; vm2 = laneB ? b2 : a2; vtot = laneB ? tbb : ta; vmA = a1; vmB = b1;
+                    const uint32_t vd = lane < bNr - rb * 32 ? (uint32_t)hv::ldg(pl.vdone + row0 + lane) : 0u;
+                    vm1 = hv::ballot(vd >= 1u); vm2 = hv::ballot(vd >= 2u); vtot = hv::warp_sum(vd);
                 }
-                float2 accA[CH][NP], accB[CH][NP];
+                float2 accH[CH][NP];
 #pragma unroll
                 for (int c = 0; c < CH; ++c)
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) { accA[c][q] = make_float2(0.0f, 0.0f); accB[c][q] = make_float2(0.0f, 0.0f); }
+                    for (int q = 0; q < NP; ++q) accH[c][q] = make_float2(0.0f, 0.0f);
                 uint32_t hslot = sH0, colbuf = 0, grp = 0, gX = 0;         // ring slot of the next column to complete; columns parked since the last V pass; group; its first column
-                uint32_t xwA = xwa, xwB = xwb;                             // where this lane parks its value of the next completed column
-                uint32_t wcur = lutw;                                      // H weight records of the current chunk
+                uint32_t xw = xw0;                                         // where this lane parks its value of the next completed column
+                uint32_t wcur = lutw;                                      // H weight records of the current chunk pair
 
                 // ---- first stage of the row block
                 if (is_n < total_stages) issue();
                 hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                 par ^= 1u << cs_s;
                 uint32_t sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
-                uint4 rawA = hv::lds_u32x4(sbase + swz), rawB = hv::lds_u32x4(sbase + C::kBoxBytes + swz);
+                uint4 raw = hv::lds_u32x4(sbase + swz);
                 uint32_t hd_next = (uint32_t)hv::ldg(hdone + lane);
                 uint32_t HM1 = 0, HM2 = 0, HMV = 0;
 
                 // The pixel loop is software-pipelined by one source column: while column i is multiply-added, column i+1 is being
-                // converted (its six table look-ups are in flight) and its weight record fetched.
-                float P0A[CH], P0B[CH], P1A[CH], P1B[CH];
+                // converted (its table look-ups are in flight) and its weight record fetched.
+                float P0[CH], P1[CH];
                 float2 W0[NP], W1[NP];
                 auto conv = [&](float (&P)[CH], const uint32_t v) {
                     P[0] = hv::lut_gather<0x6504>(v, lane4); P[1] = hv::lut_gather<0x6514>(v, lane4); P[2] = hv::lut_gather<0x6524>(v, lane4);
@@ -419,69 +415,66 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     W[0] = make_float2(q4.x, q4.y); W[1] = make_float2(q4.z, q4.w);
                     if (AV == 6) W[NP - 1] = hv::lds_w2(a + 16u);
                 };
-                auto mac = [&](const float (&PA)[CH], const float (&PB)[CH], const float2 (&W)[NP]) {
+                auto mac = [&](const float (&P)[CH], const float2 (&W)[NP]) {
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
-                        const float2 va_ = make_float2(PA[c], PA[c]), vb_ = make_float2(PB[c], PB[c]);
+                        const float2 v_ = make_float2(P[c], P[c]);
 #pragma unroll
-                        for (int q = 0; q < NP; ++q) { accA[c][q] = hv::ffma2(W[q], va_, accA[c][q]); accB[c][q] = hv::ffma2(W[q], vb_, accB[c][q]); }
+                        for (int q = 0; q < NP; ++q) accH[c][q] = hv::ffma2(W[q], v_, accH[c][q]);
                     }
                 };
-                wload(W0, wcur); conv(P0A, rawA.x); conv(P0B, rawB.x);
+                wload(W0, wcur); conv(P0, raw.x);
 
                 // The loop body is a PAIR of chunks (eight source columns): per-chunk bookkeeping is paid once for two, and the V pass
                 // marks sit on pair ends.
-                const uint32_t npairs = nchunks >> 1;
-                for (uint32_t pc = 0; pc < npairs; ++pc) {
-                    if ((pc & 3u) == 0u) {                                 // completion masks of the next 32 source columns; the bytes after them are on their way
-                        HM1 = hv::ballot((hd_next & 0x7fu) >= 1u); HM2 = hv::ballot((hd_next & 0x7fu) >= 2u); HMV = hv::ballot((hd_next & 0x80u) != 0u);
-                        hd_next = (uint32_t)hv::ldg(hdone + (pc + 4u) * 8u + (uint32_t)lane);
-                    }
+                for (uint32_t pq = 0; pq < npairs; pq += 4u) {
+                    // completion masks of the next 32 source columns (four pairs); the bytes after them are on their way
+                    HM1 = hv::ballot((hd_next & 0x7fu) >= 1u); HM2 = hv::ballot((hd_next & 0x7fu) >= 2u); HMV = hv::ballot((hd_next & 0x80u) != 0u);
+                    hd_next = (uint32_t)hv::ldg(hdone + (pq + 4u) * 8u + (uint32_t)lane);
+                    const uint32_t pe = min(pq + 4u, npairs);
+#pragma unroll 1
+                  for (uint32_t pc = pq; pc < pe; ++pc) {
                     const uint32_t hm = HM1, hm2 = HM2, hmv = HMV;
                     HM1 >>= 8; HM2 >>= 8; HMV >>= 8;
                     const uint32_t wB = wcur + (AV == 4 ? 64u : 256u);     // second chunk's records
                     const uint32_t wnext = wcur + (AV == 4 ? 256u : 512u); // next pair's
                     const bool more = pc + 1u < npairs;
 
-                    // a completed output column: both streams park their CH values in the exchange buffer, the ring slot is cleared
+                    // a completed output column: its CH values are parked in the exchange buffer, the ring slot is cleared
 #define IFB_HV_SLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) { \
-        float& a_ = (S_ & 1) ? accA[ch_][(S_ % AV) / 2].y : accA[ch_][(S_ % AV) / 2].x; \
-        float& b_ = (S_ & 1) ? accB[ch_][(S_ % AV) / 2].y : accB[ch_][(S_ % AV) / 2].x; \
-        hv::sts_f32(xwA + (uint32_t)ch_ * 128u, a_); hv::sts_f32(xwB + (uint32_t)ch_ * 128u, b_); a_ = 0.0f; b_ = 0.0f; } } break;
+        float& a_ = (S_ & 1) ? accH[ch_][(S_ % AV) / 2].y : accH[ch_][(S_ % AV) / 2].x; \
+        hv::sts_f32(xw + (uint32_t)ch_ * 128u, a_); a_ = 0.0f; } } break;
 #define IFB_HV_FLUSH(I_) if ((hm >> (I_)) & 1u) { \
         uint32_t n_ = 1u; \
         if ((hm2 >> (I_)) & 1u) n_ = uni((uint32_t)hv::ldg(hdone + pc * 8u + (I_)) & 0x7fu); \
         _Pragma("unroll 1") do { \
             switch (hslot) { IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5) default: break; } \
-            xwA += kXCol; xwB += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
+            xw += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
         } while (--n_); }
 
                     // ---- first chunk: source column 0 (column 1 on its way), 1, 2, 3
-                    wload(W1, wcur + kRec); conv(P1A, rawA.y); conv(P1B, rawB.y);
-                    mac(P0A, P0B, W0);
+                    wload(W1, wcur + kRec); conv(P1, raw.y);
+                    mac(P0, W0);
                     IFB_HV_FLUSH(0)
-                    wload(W0, wcur + 2u * kRec); conv(P0A, rawA.z); conv(P0B, rawB.z);
-                    mac(P1A, P1B, W1);
+                    wload(W0, wcur + 2u * kRec); conv(P0, raw.z);
+                    mac(P1, W1);
                     IFB_HV_FLUSH(1)
-                    // the next chunk's sixteen bytes per stream replace this one's (all four columns are converted or in registers)
-                    wload(W1, wcur + 3u * kRec); conv(P1A, rawA.w); conv(P1B, rawB.w);
-                    {
-                        const uint32_t o_ = sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz);      // chunk 2 pc + 1 of the same stage
-                        rawA = hv::lds_u32x4(o_); rawB = hv::lds_u32x4(o_ + C::kBoxBytes);
-                    }
-                    mac(P0A, P0B, W0);
+                    // the next chunk's sixteen bytes replace this one's (all four columns are converted or in registers)
+                    wload(W1, wcur + 3u * kRec); conv(P1, raw.w);
+                    raw = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));      // chunk 2 pc + 1 of the same stage
+                    mac(P0, W0);
                     IFB_HV_FLUSH(2)
-                    wload(W0, wB); conv(P0A, rawA.x); conv(P0B, rawB.x);
-                    mac(P1A, P1B, W1);
+                    wload(W0, wB); conv(P0, raw.x);
+                    mac(P1, W1);
                     IFB_HV_FLUSH(3)
                     // ---- second chunk
-                    wload(W1, wB + kRec); conv(P1A, rawA.y); conv(P1B, rawB.y);
-                    mac(P0A, P0B, W0);
+                    wload(W1, wB + kRec); conv(P1, raw.y);
+                    mac(P0, W0);
                     IFB_HV_FLUSH(4)
-                    wload(W0, wB + 2u * kRec); conv(P0A, rawA.z); conv(P0B, rawB.z);
-                    mac(P1A, P1B, W1);
+                    wload(W0, wB + 2u * kRec); conv(P0, raw.z);
+                    mac(P1, W1);
                     IFB_HV_FLUSH(5)
-                    wload(W1, wB + 3u * kRec); conv(P1A, rawA.w); conv(P1B, rawB.w);
+                    wload(W1, wB + 3u * kRec); conv(P1, raw.w);
                     if (more) {
                         if (pc & 1u) {                                     // next stage: refill the slot just emptied, wait for the next one
                             cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
@@ -490,13 +483,12 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                             par ^= 1u << cs_s;
                             sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
                         }
-                        const uint32_t o_ = sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz);      // chunk 2 pc + 2
-                        rawA = hv::lds_u32x4(o_); rawB = hv::lds_u32x4(o_ + C::kBoxBytes);
+                        raw = hv::lds_u32x4(sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz));  // chunk 2 pc + 2
                     }
-                    mac(P0A, P0B, W0);
+                    mac(P0, W0);
                     IFB_HV_FLUSH(6)
-                    wload(W0, wnext); conv(P0A, rawA.x); conv(P0B, rawB.x);
-                    mac(P1A, P1B, W1);
+                    wload(W0, wnext); conv(P0, raw.x);
+                    mac(P1, W1);
                     IFB_HV_FLUSH(7)
 #undef IFB_HV_FLUSH
 #undef IFB_HV_SLOT
@@ -504,56 +496,48 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
 
                     if ((hmv >> 7) & 1u) {
                         // ---- V pass of the columns parked since the last one (a "group", at most CG of them; the host put the mark where the
-                        // group is full or the strip ends): lane = (stream, output column sX0 + gX + cl).  The 32 H-filtered rows of the
-                        // block are multiply-added, in row order, into the group's ring of AV vertical accumulators (output row Y owns
-                        // slot Y mod AV); a completed output row goes through the store epilogue.
+                        // group is full or the strip ends): lane = (slot pair vh, output column sX0 + gX + cl).  The 32 H-filtered rows of the
+                        // block are multiply-added, in row order, into the lane's pair of vertical accumulators (output row Y owns slot Y mod AV);
+                        // a completed output row goes through the store epilogue in the lanes whose pair holds its slot.
                         hv::warp_sync();
-                        const bool col_live = cl < colbuf;
+                        const bool col_live = vlane && cl < colbuf;
                         uint8_t* const out_px = out_col + (size_t)gX * 4;
-                        const uint32_t vmU = vmA | vmB;                    // rows at which either stream completes an output row
-                        auto vgroup = [&](float2 (&acc)[CH][NP]) {
-                            int Yl = Yc, vs = vslot;
-                            const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP;
+                        auto vgroup = [&](float2 (&acc)[CH]) {
+                            int Yl = Yc;
+                            uint32_t vs = vslot;
+                            const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP + 2u * (vlane ? vh : 0u);
                             uint32_t xrr = xr;
-                            // all 32 rows of the block (rows below a band's last carry no completion bit, and what they add to a slot is never
-                            // read), in runs that end with a row at which a stream completes an output row
+                            // all 32 rows of the block (rows below the band's last carry no completion bit, and what they add to a slot is never
+                            // read), in runs that end with a row that completes an output row
                             for (int r = 0; r < 32;) {
-                                const uint32_t rest = vmU >> r;
+                                const uint32_t rest = vm1 >> r;
                                 const int n = rest ? __ffs((int)rest) : 32 - r;
 #pragma unroll 1
                                 for (int i = 0; i < n; ++i, vwp += AVP, xrr += 4u) {
-                                    float2 wv[NP];
-                                    {
-                                        const float4 q4 = hv::ldg(reinterpret_cast<const float4*>(vwp));
-                                        wv[0] = make_float2(q4.x, q4.y); wv[1] = make_float2(q4.z, q4.w);
-                                        if (AV == 6) wv[NP - 1] = hv::ldg(reinterpret_cast<const float2*>(vwp + 4));
-                                    }
+                                    const float2 wv = hv::ldg(reinterpret_cast<const float2*>(vwp));
 #pragma unroll
                                     for (int ch_ = 0; ch_ < CH; ++ch_) {
                                         const float x_ = hv::lds_f32(xrr + (uint32_t)ch_ * 128u);
-                                        const float2 vv = make_float2(x_, x_);
-#pragma unroll
-                                        for (int q = 0; q < NP; ++q) acc[ch_][q] = hv::ffma2(wv[q], vv, acc[ch_][q]);
+                                        acc[ch_] = hv::ffma2(wv, make_float2(x_, x_), acc[ch_]);
                                     }
                                 }
                                 r += n;
-                                if (rest != 0u && ((vm1 >> (r - 1)) & 1u)) {
+                                if (rest != 0u) {
                                     uint32_t nv = 1u;
-                                    if ((vm2 >> (r - 1)) & 1u) nv = (uint32_t)hv::ldg(pl.vdone + row0 + r - 1);
+                                    if ((vm2 >> (r - 1)) & 1u) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
                                     for (uint32_t e2 = 0; e2 < nv; ++e2) {
+                                        const bool holder = (vs >> 1) == vh, odd = vs & 1u;
                                         float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                                        switch (vs) {
-#define IFB_HV_VSLOT(S_) case S_: if (S_ < AV) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) { \
-        float& a_ = (S_ & 1) ? acc[ch_][(S_ % AV) / 2].y : acc[ch_][(S_ % AV) / 2].x; f_[ch_] = a_; a_ = 0.0f; } } break;
-                                        IFB_HV_VSLOT(0) IFB_HV_VSLOT(1) IFB_HV_VSLOT(2) IFB_HV_VSLOT(3) IFB_HV_VSLOT(4) IFB_HV_VSLOT(5)
-#undef IFB_HV_VSLOT
-                                        default: break;
+#pragma unroll
+                                        for (int ch_ = 0; ch_ < CH; ++ch_) {
+                                            f_[ch_] = odd ? acc[ch_].y : acc[ch_].x;
+                                            if (holder) { if (odd) acc[ch_].y = 0.0f; else acc[ch_].x = 0.0f; }
                                         }
-                                        if (Yl >= mY0 && Yl < mY1 && col_live) {
+                                        if (holder && Yl >= bY0 && Yl < bY1 && col_live) {
                                             uint8_t* dst = out_px + (size_t)Yl * out_stride;
                                             *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
                                         }
-                                        ++Yl; vs = vs + 1 == AV ? 0 : vs + 1;
+                                        ++Yl; vs = vs + 1u == (uint32_t)AV ? 0u : vs + 1u;
                                     }
                                 }
                             }
@@ -565,13 +549,14 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                         default: break;
                         }
                         hv::warp_sync();
-                        ++grp; gX += colbuf; colbuf = 0; xwA = xwa; xwB = xwb;
+                        ++grp; gX += colbuf; colbuf = 0; xw = xw0;
                     }
+                  }
                 }
                 cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
-                // every group of the row block has seen the same rows: commit the vertical position of this lane's stream
+                // every group of the row block has seen the same rows: commit the vertical position
                 Yc += (int)vtot;
-                vslot = (int)(((uint32_t)vslot + vtot) % (uint32_t)AV);
+                vslot = (vslot + vtot) % (uint32_t)AV;
             }
         }
     }
