@@ -502,36 +502,52 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                         hv::warp_sync();
                         const bool col_live = vlane && cl < colbuf;
                         uint8_t* const out_px = out_col + (size_t)gX * 4;
-                        auto vgroup = [&](float2 (&acc)[CH]) {
+                        // the group's accumulators: fetched from / returned to the register set of group `grp` by two small switches, so that
+                        // the V pass code exists once
+                        float2 acc[CH];
+                        switch (grp) {
+#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) acc[ch_] = accV[(G_) % NG][ch_]; } break;
+                        IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3) IFB_HV_VGROUP(4) IFB_HV_VGROUP(5) IFB_HV_VGROUP(6) IFB_HV_VGROUP(7) IFB_HV_VGROUP(8)
+#undef IFB_HV_VGROUP
+                        default:
+#pragma unroll
+                            for (int ch_ = 0; ch_ < CH; ++ch_) acc[ch_] = make_float2(0.0f, 0.0f);
+                            break;
+                        }
+                        {
                             int Yl = Yc;
                             uint32_t vs = vslot;
-                            const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP + 2u * (vlane ? vh : 0u);
+                            const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP + 2u * (vlane ? vh : 0u);   // this lane's pair of V weights, row by row
                             uint32_t xrr = xr;
+                            auto vrow = [&](const float* __restrict__ wp, const uint32_t xa_) {
+                                const float2 wv = hv::ldg(reinterpret_cast<const float2*>(wp));
+#pragma unroll
+                                for (int ch_ = 0; ch_ < CH; ++ch_) {
+                                    const float x_ = hv::lds_f32(xa_ + (uint32_t)ch_ * 128u);
+                                    acc[ch_] = hv::ffma2(wv, make_float2(x_, x_), acc[ch_]);
+                                }
+                            };
                             // all 32 rows of the block (rows below the band's last carry no completion bit, and what they add to a slot is never
-                            // read), in runs that end with a row that completes an output row
+                            // read), in runs that end with a row that completes an output row; a run is walked two rows at a time
                             for (int r = 0; r < 32;) {
                                 const uint32_t rest = vm1 >> r;
                                 const int n = rest ? __ffs((int)rest) : 32 - r;
 #pragma unroll 1
-                                for (int i = 0; i < n; ++i, vwp += AVP, xrr += 4u) {
-                                    const float2 wv = hv::ldg(reinterpret_cast<const float2*>(vwp));
-#pragma unroll
-                                    for (int ch_ = 0; ch_ < CH; ++ch_) {
-                                        const float x_ = hv::lds_f32(xrr + (uint32_t)ch_ * 128u);
-                                        acc[ch_] = hv::ffma2(wv, make_float2(x_, x_), acc[ch_]);
-                                    }
-                                }
+                                for (int i = n >> 1; i > 0; --i, vwp += 2 * AVP, xrr += 8u) { vrow(vwp, xrr); vrow(vwp + AVP, xrr + 4u); }
+                                if (n & 1) { vrow(vwp, xrr); vwp += AVP; xrr += 4u; }
                                 r += n;
                                 if (rest != 0u) {
                                     uint32_t nv = 1u;
-                                    if ((vm2 >> (r - 1)) & 1u) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
+                                    if (vm2 != 0u && ((vm2 >> (r - 1)) & 1u)) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
                                     for (uint32_t e2 = 0; e2 < nv; ++e2) {
-                                        const bool holder = (vs >> 1) == vh, odd = vs & 1u;
+                                        const bool holder = (vs >> 1) == vh;
                                         float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                                        if (vs & 1u) {
 #pragma unroll
-                                        for (int ch_ = 0; ch_ < CH; ++ch_) {
-                                            f_[ch_] = odd ? acc[ch_].y : acc[ch_].x;
-                                            if (holder) { if (odd) acc[ch_].y = 0.0f; else acc[ch_].x = 0.0f; }
+                                            for (int ch_ = 0; ch_ < CH; ++ch_) { f_[ch_] = acc[ch_].y; if (holder) acc[ch_].y = 0.0f; }
+                                        } else {
+#pragma unroll
+                                            for (int ch_ = 0; ch_ < CH; ++ch_) { f_[ch_] = acc[ch_].x; if (holder) acc[ch_].x = 0.0f; }
                                         }
                                         if (holder && Yl >= bY0 && Yl < bY1 && col_live) {
                                             uint8_t* dst = out_px + (size_t)Yl * out_stride;
@@ -541,9 +557,9 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                                     }
                                 }
                             }
-                        };
+                        }
                         switch (grp) {
-#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) vgroup(accV[(G_) % NG]); break;
+#define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) accV[(G_) % NG][ch_] = acc[ch_]; } break;
                         IFB_HV_VGROUP(0) IFB_HV_VGROUP(1) IFB_HV_VGROUP(2) IFB_HV_VGROUP(3) IFB_HV_VGROUP(4) IFB_HV_VGROUP(5) IFB_HV_VGROUP(6) IFB_HV_VGROUP(7) IFB_HV_VGROUP(8)
 #undef IFB_HV_VGROUP
                         default: break;

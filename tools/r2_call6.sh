@@ -8,9 +8,9 @@ note() { echo "[$((SECONDS-T0))s] $*" | tee -a gpurun_out/$TAG.log; }
 B="python bench.py --no-cpu --no-e2e --no-others"
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/${TAG}_parity.log 2>&1; note "parity rc=$? $(tail -3 gpurun_out/${TAG}_parity.log | tr '\n' ' ' | head -c 900)"
 timeout 300 $B --steps 6 > gpurun_out/${TAG}_bench_c2.json 2>gpurun_out/${TAG}_bench_c2.err; note "bench c2 $(python tools/kms.py gpurun_out/${TAG}_bench_c2.json)"
-IFB200_LIB=$PWD/imageflow_b200/libifb200_w128.so timeout 300 $B --steps 6 > gpurun_out/${TAG}_bench_c2_w128.json 2>&1; note "bench c2 w128 $(python tools/kms.py gpurun_out/${TAG}_bench_c2_w128.json)"
+
 for mi in 4096 8192 16384 32768; do timeout 200 $B --steps 4 --min-items $mi > gpurun_out/${TAG}_mi$mi.json 2>&1; note "bench c2 items$mi $(python tools/kms.py gpurun_out/${TAG}_mi$mi.json)"; done
-for mi in 4096 8192 16384; do IFB200_LIB=$PWD/imageflow_b200/libifb200_w128.so timeout 200 $B --steps 4 --min-items $mi > gpurun_out/${TAG}_w128_mi$mi.json 2>&1; note "bench c2 w128 items$mi $(python tools/kms.py gpurun_out/${TAG}_w128_mi$mi.json)"; done
+
 timeout 200 $B --steps 4 --workload c2_4k_to_512_lanczos3 > gpurun_out/${TAG}_bench_l3.json 2>&1; note "bench lanczos3 $(python tools/kms.py gpurun_out/${TAG}_bench_l3.json)"
 timeout 200 $B --steps 4 --alpha 1 > gpurun_out/${TAG}_bench_alpha.json 2>&1; note "bench c2 alpha $(python tools/kms.py gpurun_out/${TAG}_bench_alpha.json)"
 timeout 200 $B --steps 4 --workload c3_8k_to_1080p_robidoux_sharpen > gpurun_out/${TAG}_bench_c3.json 2>&1; note "bench c3 $(python tools/kms.py gpurun_out/${TAG}_bench_c3.json)"
