@@ -381,9 +381,9 @@ int hv_cols(int av, int ch, int option);
 // ------------------------------------------------------------------------------------------------
 // ring kernel dispatch table
 using HvFn = void (*)(const JobDev*, const HvTmap*, Tables, HvPlanDev, uint32_t, uint32_t*);
-struct HvEntry { int av, ch; HvFn fn, fn_simple; int threads, warps, max_cols, ng; uint32_t (*smem)(uint32_t); };
+struct HvEntry { int av, ch; HvFn fn[3]; int threads, warps, max_cols, ng; uint32_t (*smem)(uint32_t); };   // fn[EPI]: general, simple + linear, simple + sRGB
 template <int AV, int CH> uint32_t hv_smem_bytes(uint32_t sb_low16) { return hv_total_bytes<AV, CH>(sb_low16); }
-#define IFB_HV(AV_, CH_) {AV_, CH_, hv_ring_kernel<AV_, CH_, false>, hv_ring_kernel<AV_, CH_, true>, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, HvCfg<AV_, CH_>::kMaxCols, HvCfg<AV_, CH_>::kNG, hv_smem_bytes<AV_, CH_>}
+#define IFB_HV(AV_, CH_) {AV_, CH_, {hv_ring_kernel<AV_, CH_, 0>, hv_ring_kernel<AV_, CH_, 1>, hv_ring_kernel<AV_, CH_, 2>}, HvCfg<AV_, CH_>::kThreads, HvCfg<AV_, CH_>::kWarps, HvCfg<AV_, CH_>::kMaxCols, HvCfg<AV_, CH_>::kNG, hv_smem_bytes<AV_, CH_>}
 const HvEntry kHv[] = {IFB_HV(4, 3), IFB_HV(4, 4), IFB_HV(6, 3), IFB_HV(6, 4)};
 const HvEntry* find_hv(int av, int ch) {
     for (const auto& e : kHv) if (e.av == av && e.ch == ch) return &e;
@@ -820,7 +820,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             pl.bands = reinterpret_cast<const HvBandDev*>(dbuf + lay[gi].bands);
             pl.hw = ht.blob.at<float>(ht.o_hw); pl.hdone = ht.blob.at<uint8_t>(ht.o_hdone);
             pl.vw = ht.blob.at<float>(ht.o_vw); pl.vdone = ht.blob.at<uint8_t>(ht.o_vdone);
-            HvFn fn = g.simple ? he->fn_simple : he->fn;
+            HvFn fn = he->fn[g.simple ? ((g.variant & 1) ? 1 : 2) : 0];        // the ring kernel's launches are per working space (variant bit 0 = linear)
             const size_t smem = he->smem(b->smem_base_low16);
             if (!b->hv_attr_set.count((const void*)fn)) {
                 CUDA_OK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -187,6 +187,9 @@ template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p
 #define IFB_HV_DYNAMIC_SMEM(name_) extern __shared__ __align__(1024) unsigned char name_[]
 #endif
 
+#ifndef IFB_HV_DISPATCH
+#define IFB_HV_DISPATCH 0              // how a chunk picks its compiled form: 0 = jump table, 1 = chain of tests
+#endif
 #ifndef IFB_HV_PREFETCH_AHEAD
 #define IFB_HV_PREFETCH_AHEAD 8        // L2 prefetch distance in stages (0 = off)
 #endif
@@ -200,10 +203,13 @@ __global__ void smem_base_probe_kernel(uint32_t* out) {
 // Store epilogue with the tables in shared memory: same operations, same order as finish_pixel().
 //   enc(v)  floatspace_to_srgb (color.rs:59-69): linear -> 16 K table in the LUT holes; sRGB space -> uchar_clamp_ff(255 v)
 //   tl(b)   byte_to_float of the working space = the lane's own copy in the replicated LUT
-template <bool SIMPLE>
+// EPI: 0 = every compositing mode / working space / colour matrix (read from the job); 1 = ReplaceSelf, linear light, no matrix;
+// 2 = ReplaceSelf, sRGB space, no matrix (the thumbnail cases: nothing but the encode is compiled).  CH == 4 <=> alpha is meaningful.
+template <int EPI, int CH>
 __device__ __forceinline__ uint32_t hv_finish_pixel(float b, float g, float r, float a, const uint32_t flags, const JobDev& job,
                                                     const uint32_t lut, const uint32_t lut_lane, const uint8_t* dst) {
-    const bool linear = flags & JF_LINEAR;
+    constexpr bool SIMPLE = EPI != 0;
+    const bool linear = EPI == 1 ? true : EPI == 2 ? false : (flags & JF_LINEAR) != 0u;
     auto enc = [&](float v) -> uint32_t {
         if (linear) {                                          // lut.rs:4-8
             float s = __fmul_rn(v, 16383.0f);
@@ -213,7 +219,7 @@ __device__ __forceinline__ uint32_t hv_finish_pixel(float b, float g, float r, f
         }
         return uchar_clamp_ff(__fmul_rn(255.0f, v));
     };
-    const bool am = flags & JF_ALPHA;
+    constexpr bool am = CH == 4;
     const uint32_t compose = SIMPLE ? 0u : (flags >> JF_COMPOSE_SHIFT) & 3u;
     uint32_t ob, og, orr, oa;
     if (compose == 1u) {                                   // BlendWithSelf: scaling.rs:254-287
@@ -258,7 +264,7 @@ __device__ __forceinline__ uint32_t hv_finish_pixel(float b, float g, float r, f
     return ob | (og << 8) | (orr << 16) | (oa << 24);
 }
 
-template <int AV, int CH, bool SIMPLE>
+template <int AV, int CH, int EPI>
 __global__ void __launch_bounds__(HvCfg<AV, CH>::kThreads, 1)
 hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps, Tables tb, HvPlanDev pl, uint32_t n_jobs,
                uint32_t* __restrict__ counters) {
@@ -452,44 +458,64 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             xw += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
         } while (--n_); }
 
-                    // ---- first chunk: source column 0 (column 1 on its way), 1, 2, 3
-                    wload(W1, wcur + kRec); conv(P1, raw.y);
-                    mac(P0, W0);
-                    IFB_HV_FLUSH(0)
-                    wload(W0, wcur + 2u * kRec); conv(P0, raw.z);
-                    mac(P1, W1);
-                    IFB_HV_FLUSH(1)
-                    // the next chunk's sixteen bytes replace this one's (all four columns are converted or in registers)
-                    wload(W1, wcur + 3u * kRec); conv(P1, raw.w);
-                    raw = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));      // chunk 2 pc + 1 of the same stage
-                    mac(P0, W0);
-                    IFB_HV_FLUSH(2)
-                    wload(W0, wB); conv(P0, raw.x);
-                    mac(P1, W1);
-                    IFB_HV_FLUSH(3)
-                    // ---- second chunk
-                    wload(W1, wB + kRec); conv(P1, raw.y);
-                    mac(P0, W0);
-                    IFB_HV_FLUSH(4)
-                    wload(W0, wB + 2u * kRec); conv(P0, raw.z);
-                    mac(P1, W1);
-                    IFB_HV_FLUSH(5)
-                    wload(W1, wB + 3u * kRec); conv(P1, raw.w);
-                    if (more) {
-                        if (pc & 1u) {                                     // next stage: refill the slot just emptied, wait for the next one
-                            cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
-                            if (is_n < total_stages) issue();
-                            hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
-                            par ^= 1u << cs_s;
-                            sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
-                        }
-                        raw = hv::lds_u32x4(sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz));  // chunk 2 pc + 2
+                    // A chunk (four source columns) is compiled six times: no completion, one completion behind column 0 / 1 / 2 / 3, and
+                    // the general form with a test behind every column; the mask of the chunk picks one.  The usual case therefore
+                    // has ONE branch per chunk instead of four: a branch, taken or not, holds the warp until it is resolved, and in
+                    // the first form of this loop the instruction behind every test carried half of the loop's stall samples.
+#define IFB_HV_FLUSH1 { switch (hslot) { IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5) default: break; } \
+        xw += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; }
+#define IFB_HV_NONE
+#define IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, F0_, F1_, F2_, F3_) { \
+        wload(W1, (WB_) + kRec); conv(P1, raw.y); mac(P0, W0); F0_ \
+        wload(W0, (WB_) + 2u * kRec); conv(P0, raw.z); mac(P1, W1); F1_ \
+        wload(W1, (WB_) + 3u * kRec); conv(P1, raw.w); RELOAD_ mac(P0, W0); F2_ \
+        wload(W0, (WN_)); conv(P0, raw.x); mac(P1, W1); F3_ }
+#if IFB_HV_DISPATCH == 1     /* a chain of tests, the commonest case first */
+#define IFB_HV_CHUNK(WB_, WN_, RELOAD_, SH_) { \
+        const uint32_t m4_ = (hm >> (SH_)) & 15u, d4_ = (hm2 >> (SH_)) & 15u; \
+        if ((d4_ | (m4_ & (m4_ - 1u))) != 0u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) \
+        else if (m4_ == 0u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
+        else if (m4_ & 3u) { \
+            if (m4_ & 1u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
+            else IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE) \
+        } else { \
+            if (m4_ & 4u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE) \
+            else IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1) \
+        } }
+#else                        /* a jump table */
+#define IFB_HV_CHUNK(WB_, WN_, RELOAD_, SH_) { \
+        const uint32_t m4_ = (hm >> (SH_)) & 15u; \
+        switch (((hm2 >> (SH_)) & 15u) ? 16u : m4_) { \
+        case 0u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) break; \
+        case 1u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) break; \
+        case 2u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE) break; \
+        case 4u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE) break; \
+        case 8u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1) break; \
+        default: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) break; \
+        } }
+#endif
+                    // ---- first chunk; behind its third column the next chunk's sixteen bytes replace this one's (all four columns are
+                    // converted or in registers)
+#define IFB_HV_RELOAD_A raw = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));      /* chunk 2 pc + 1 of the same stage */
+                    IFB_HV_CHUNK(wcur, wB, IFB_HV_RELOAD_A, 0)
+                    // ---- second chunk; the chunk after it may be the first of the next stage.  This stage's last sixteen bytes are in
+                    // registers by now, so its slot can be refilled and the next stage waited for before the chunk starts.
+                    if ((pc & 1u) && more) {
+                        cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
+                        if (is_n < total_stages) issue();
+                        hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
+                        par ^= 1u << cs_s;
+                        sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
                     }
-                    mac(P0, W0);
-                    IFB_HV_FLUSH(6)
-                    wload(W0, wnext); conv(P0, raw.x);
-                    mac(P1, W1);
-                    IFB_HV_FLUSH(7)
+                    // chunk 2 pc + 2 (behind the last pair of the row block: bytes nobody uses)
+#define IFB_HV_RELOAD_B raw = hv::lds_u32x4(sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz));
+                    IFB_HV_CHUNK(wB, wnext, IFB_HV_RELOAD_B, 4)
+#undef IFB_HV_RELOAD_A
+#undef IFB_HV_RELOAD_B
+#undef IFB_HV_CHUNK
+#undef IFB_HV_CHUNK4
+#undef IFB_HV_NONE
+#undef IFB_HV_FLUSH1
 #undef IFB_HV_FLUSH
 #undef IFB_HV_SLOT
                     wcur = wnext;
@@ -539,6 +565,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                                 if (rest != 0u) {
                                     uint32_t nv = 1u;
                                     if (vm2 != 0u && ((vm2 >> (r - 1)) & 1u)) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
+#pragma unroll 1
                                     for (uint32_t e2 = 0; e2 < nv; ++e2) {
                                         const bool holder = (vs >> 1) == vh;
                                         float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -549,9 +576,13 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
 #pragma unroll
                                             for (int ch_ = 0; ch_ < CH; ++ch_) { f_[ch_] = acc[ch_].x; if (holder) acc[ch_].x = 0.0f; }
                                         }
-                                        if (holder && Yl >= bY0 && Yl < bY1 && col_live) {
-                                            uint8_t* dst = out_px + (size_t)Yl * out_stride;
-                                            *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<SIMPLE>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
+                                        const bool mine = holder && Yl >= bY0 && Yl < bY1 && col_live;
+                                        uint8_t* dst = out_px + (size_t)Yl * out_stride;
+                                        if (EPI != 0) {                    // the encode never reads the canvas: every lane runs it, the owners store (no branch)
+                                            const uint32_t px_ = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
+                                            if (mine) *reinterpret_cast<uint32_t*>(dst) = px_;
+                                        } else if (mine) {
+                                            *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
                                         }
                                         ++Yl; vs = vs + 1u == (uint32_t)AV ? 0u : vs + 1u;
                                     }

@@ -165,8 +165,8 @@ static_assert(sizeof(EmuTmap) == 128 && sizeof(HvTmapDecl) == 128, "descriptor s
 using KernelFn = void (*)(const JobDev*, const HvTmapDecl*, Tables, HvPlanDev, uint32_t, uint32_t*);
 struct Pick { KernelFn fn; int threads; uint32_t (*smem)(uint32_t); };
 template <int AV, int CH> static uint32_t smem_of(uint32_t low16) { return hv_total_bytes<AV, CH>(low16); }
-static Pick pick(int av, int ch, int simple) {
-#define IFB_PICK(AV_, CH_) if (av == AV_ && ch == CH_) return Pick{simple ? hv_ring_kernel<AV_, CH_, true> : hv_ring_kernel<AV_, CH_, false>, HvCfg<AV_, CH_>::kThreads, smem_of<AV_, CH_>};
+static Pick pick(int av, int ch, int epi) {      // epi: 0 general, 1 simple + linear, 2 simple + sRGB (as the engine picks them)
+#define IFB_PICK(AV_, CH_) if (av == AV_ && ch == CH_) return Pick{epi == 1 ? hv_ring_kernel<AV_, CH_, 1> : epi == 2 ? hv_ring_kernel<AV_, CH_, 2> : hv_ring_kernel<AV_, CH_, 0>, HvCfg<AV_, CH_>::kThreads, smem_of<AV_, CH_>};
     IFB_PICK(4, 3) IFB_PICK(4, 4) IFB_PICK(6, 3) IFB_PICK(6, 4)
     return Pick{nullptr, 0, nullptr};
 }
@@ -179,7 +179,7 @@ extern "C" uint32_t emu_hv_sizeof_jobdev(void) { return (uint32_t)sizeof(JobDev)
 extern "C" int emu_hv_launch(int av, int ch, int simple, unsigned grid, const void* jobs, uint32_t n_jobs, const uint8_t* const* in_ptrs,
                              const uint32_t* in_whs, const float* t_lin, const float* t_srgb, const uint8_t* lut16k, const uint8_t* blob,
                              const uint64_t* o, const uint32_t* dims4, int n_strips, int n_bands, uint32_t sb_low16) {
-    const Pick pk = pick(av, ch, simple);
+    const Pick pk = pick(av, ch, simple ? ((static_cast<const JobDev*>(jobs)[0].flags & JF_LINEAR) ? 1 : 2) : 0);
     if (!pk.fn) return -1;
     std::vector<EmuTmap> tms(n_jobs);
     for (uint32_t i = 0; i < n_jobs; ++i) { tms[i] = EmuTmap{}; tms[i].base = in_ptrs[i]; tms[i].w = in_whs[i * 3]; tms[i].h = in_whs[i * 3 + 1]; tms[i].stride = in_whs[i * 3 + 2]; }
