@@ -137,6 +137,28 @@ __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("
 __device__ __forceinline__ void sts_f32x4(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// A completed output column, without a branch: if (mask & BIT) { park a0.. at [xw], [xw + 128], ..; clear them; xw += STEP; } as
+// predicated instructions behind one predicate (a branch, taken or not, holds the warp until it is resolved).
+template <uint32_t BIT, uint32_t STEP>
+__device__ __forceinline__ void flush3_if(uint32_t& xw, float& a0, float& a1, float& a2, const uint32_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %4, %5;\n\tsetp.ne.u32 q, t, 0;\n\t"
+                 "@q st.shared.f32 [%0], %1;\n\t@q st.shared.f32 [%0+128], %2;\n\t@q st.shared.f32 [%0+256], %3;\n\t"
+                 "@q mov.f32 %1, 0f00000000;\n\t@q mov.f32 %2, 0f00000000;\n\t@q mov.f32 %3, 0f00000000;\n\t"
+                 "@q add.u32 %0, %0, %6;\n\t}"
+                 : "+r"(xw), "+f"(a0), "+f"(a1), "+f"(a2) : "r"(mask), "n"(BIT), "n"(STEP) : "memory");
+}
+template <uint32_t BIT, uint32_t STEP>
+__device__ __forceinline__ void flush4_if(uint32_t& xw, float& a0, float& a1, float& a2, float& a3, const uint32_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
+                 "and.b32 t, %5, %6;\n\tsetp.ne.u32 q, t, 0;\n\t"
+                 "@q st.shared.f32 [%0], %1;\n\t@q st.shared.f32 [%0+128], %2;\n\t@q st.shared.f32 [%0+256], %3;\n\t@q st.shared.f32 [%0+384], %4;\n\t"
+                 "@q mov.f32 %1, 0f00000000;\n\t@q mov.f32 %2, 0f00000000;\n\t@q mov.f32 %3, 0f00000000;\n\t@q mov.f32 %4, 0f00000000;\n\t"
+                 "@q add.u32 %0, %0, %7;\n\t}"
+                 : "+r"(xw), "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3) : "r"(mask), "n"(BIT), "n"(STEP) : "memory");
+}
+// 0, but only once v has arrived (a register dependency the compiler cannot remove)
+__device__ __forceinline__ uint32_t zero_after(uint32_t v) { uint32_t z; asm volatile("xor.b32 %0, %1, %1;" : "=r"(z) : "r"(v)); return z; }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -187,11 +209,11 @@ template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p
 #define IFB_HV_DYNAMIC_SMEM(name_) extern __shared__ __align__(1024) unsigned char name_[]
 #endif
 
-#ifndef IFB_HV_DISPATCH
-#define IFB_HV_DISPATCH 0              // how a chunk picks its compiled form: 0 = jump table, 1 = chain of tests
+#ifndef IFB_HV_NOFAST
+#define IFB_HV_NOFAST 0                // 1: only the general form of a chunk (A/B builds)
 #endif
 #ifndef IFB_HV_PREFETCH_AHEAD
-#define IFB_HV_PREFETCH_AHEAD 8        // L2 prefetch distance in stages (0 = off)
+#define IFB_HV_PREFETCH_AHEAD 0        // L2 prefetch distance in boxes (0 = off: measured 4 % faster than 8 on the 4K -> 512 batch)
 #endif
 
 // Where a CTA's dynamic shared memory starts in the shared window (the engine sizes the ring kernel's layout with it).
@@ -345,29 +367,31 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             const int nrb = (bNr + 31) >> 5;
             const int x_origin = sK0 + (int)uni(job.in_xoff);
 
-            // ---- TMA pipeline state: stages are numbered row block by row block
-            const int total_stages = nrb * nst;
-            int is_n = 0, is_x = 0, is_y = 0, is_s = 0;                    // next stage to issue: index, stage within row block, row block, ring slot
-            auto issue = [&]() {
+            // ---- TMA pipeline state: boxes are fetched row block by row block, left to right
+            const int x_end = x_origin + nst * 16;
+            int tma_x = x_origin, tma_y = bJ0, tma_left = nrb * nst, is_s = 0;   // next box to fetch, boxes not fetched yet, the ring slot it goes to
+            auto issue = [&](const uint32_t zero_dep) {                    // zero_dep: 0, computed from what the slot's last load returned
                 hv::warp_sync();                                           // every lane has read what the refilled slot held
                 if (leader) {
                     const uint32_t bar = mb + 8u * (uint32_t)is_s;
                     hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
-                    hv::tma_load_box(stb + (uint32_t)is_s * C::kStageBytes, tm, x_origin + is_x * 16, bJ0 + is_y * 32, bar);
+                    hv::tma_load_box(stb + (uint32_t)is_s * C::kStageBytes, tm, tma_x + (int)zero_dep, tma_y, bar);
 #if IFB_HV_PREFETCH_AHEAD > 0
-                    // every fourth stage: the box IFB_HV_PREFETCH_AHEAD stages further on its way into L2 (the descriptor promotes
-                    // every request to its 256-byte line, i.e. to the width of four stages)
-                    if ((is_x & 3) == 0) {
-                        int px = is_x + IFB_HV_PREFETCH_AHEAD, py = is_y;
-                        if (px >= nst) { px -= nst; ++py; }
-                        if (py < nrb) hv::tma_prefetch_box(tm, x_origin + px * 16, bJ0 + py * 32);
+                    // every fourth box: the box IFB_HV_PREFETCH_AHEAD further on its way into L2 (the descriptor promotes every request to
+                    // its 256-byte line, i.e. to the width of four boxes)
+                    if (((tma_x - x_origin) & 63) == 0) {
+                        int px = tma_x + 16 * IFB_HV_PREFETCH_AHEAD, py = tma_y;
+                        if (px >= x_end) { px -= nst * 16; py += 32; }
+                        if (py < bJ0 + nrb * 32) hv::tma_prefetch_box(tm, px, py);
                     }
 #endif
                 }
-                ++is_n; is_s = is_s + 1 == S ? 0 : is_s + 1;
-                if (++is_x == nst) { is_x = 0; ++is_y; }
+                --tma_left; is_s ^= 1;
+                tma_x += 16;
+                if (tma_x == x_end) { tma_x = x_origin; tma_y += 32; }
             };
-            for (int i = 0; i < S - 1 && is_n < total_stages; ++i) issue();
+            static_assert(S == 2, "the slot bookkeeping below toggles between two slots");
+            if (tma_left > 0) issue(0u);
             int cs_s = 0;                                                  // ring slot of the stage being consumed
 
             float2 accV[NG][CH];                                           // this lane's slot pair of column cl of every group
@@ -397,11 +421,11 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                 uint32_t wcur = lutw;                                      // H weight records of the current chunk pair
 
                 // ---- first stage of the row block
-                if (is_n < total_stages) issue();
+                if (tma_left > 0) issue(0u);
                 hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                 par ^= 1u << cs_s;
                 uint32_t sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
-                uint4 raw = hv::lds_u32x4(sbase + swz);
+                uint4 rawA = hv::lds_u32x4(sbase + swz), rawB;             // the sixteen bytes of this lane's row in the pair's first / second chunk
                 uint32_t hd_next = (uint32_t)hv::ldg(hdone + lane);
                 uint32_t HM1 = 0, HM2 = 0, HMV = 0;
 
@@ -429,7 +453,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                         for (int q = 0; q < NP; ++q) accH[c][q] = hv::ffma2(W[q], v_, accH[c][q]);
                     }
                 };
-                wload(W0, wcur); conv(P0, raw.x);
+                wload(W0, wcur); conv(P0, rawA.x);
 
                 // The loop body is a PAIR of chunks (eight source columns): per-chunk bookkeeping is paid once for two, and the V pass
                 // marks sit on pair ends.
@@ -458,64 +482,64 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
             xw += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
         } while (--n_); }
 
-                    // A chunk (four source columns) is compiled six times: no completion, one completion behind column 0 / 1 / 2 / 3, and
-                    // the general form with a test behind every column; the mask of the chunk picks one.  The usual case therefore
-                    // has ONE branch per chunk instead of four: a branch, taken or not, holds the warp until it is resolved, and in
-                    // the first form of this loop the instruction behind every test carried half of the loop's stall samples.
-#define IFB_HV_FLUSH1 { switch (hslot) { IFB_HV_SLOT(0) IFB_HV_SLOT(1) IFB_HV_SLOT(2) IFB_HV_SLOT(3) IFB_HV_SLOT(4) IFB_HV_SLOT(5) default: break; } \
-        xw += kXCol; ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; }
-#define IFB_HV_NONE
-#define IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, F0_, F1_, F2_, F3_) { \
-        wload(W1, (WB_) + kRec); conv(P1, raw.y); mac(P0, W0); F0_ \
-        wload(W0, (WB_) + 2u * kRec); conv(P0, raw.z); mac(P1, W1); F1_ \
-        wload(W1, (WB_) + 3u * kRec); conv(P1, raw.w); RELOAD_ mac(P0, W0); F2_ \
-        wload(W0, (WN_)); conv(P0, raw.x); mac(P1, W1); F3_ }
-#if IFB_HV_DISPATCH == 1     /* a chain of tests, the commonest case first */
-#define IFB_HV_CHUNK(WB_, WN_, RELOAD_, SH_) { \
-        const uint32_t m4_ = (hm >> (SH_)) & 15u, d4_ = (hm2 >> (SH_)) & 15u; \
-        if ((d4_ | (m4_ & (m4_ - 1u))) != 0u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) \
-        else if (m4_ == 0u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
-        else if (m4_ & 3u) { \
-            if (m4_ & 1u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
-            else IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE) \
-        } else { \
-            if (m4_ & 4u) IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE) \
-            else IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1) \
-        } }
-#else                        /* a jump table */
-#define IFB_HV_CHUNK(WB_, WN_, RELOAD_, SH_) { \
-        const uint32_t m4_ = (hm >> (SH_)) & 15u; \
-        switch (((hm2 >> (SH_)) & 15u) ? 16u : m4_) { \
-        case 0u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) break; \
-        case 1u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) break; \
-        case 2u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE, IFB_HV_NONE) break; \
-        case 4u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1, IFB_HV_NONE) break; \
-        case 8u: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_FLUSH1) break; \
-        default: IFB_HV_CHUNK4(WB_, WN_, RELOAD_, SH_, IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) break; \
-        } }
-#endif
-                    // ---- first chunk; behind its third column the next chunk's sixteen bytes replace this one's (all four columns are
-                    // converted or in registers)
-#define IFB_HV_RELOAD_A raw = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));      /* chunk 2 pc + 1 of the same stage */
-                    IFB_HV_CHUNK(wcur, wB, IFB_HV_RELOAD_A, 0)
-                    // ---- second chunk; the chunk after it may be the first of the next stage.  This stage's last sixteen bytes are in
-                    // registers by now, so its slot can be refilled and the next stage waited for before the chunk starts.
+                    // Second chunk's bytes (chunk 2 pc + 1, same stage as the first).  With them in registers the second pair of a stage has
+                    // read its stage completely: the slot is refilled and the next stage waited for before the pair starts (the refill is
+                    // made to depend on the loaded bytes, so that it cannot overtake the load).
+                    rawB = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));
                     if ((pc & 1u) && more) {
-                        cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
-                        if (is_n < total_stages) issue();
+                        cs_s ^= 1;
+                        if (tma_left > 0) issue(hv::zero_after(rawB.x));
                         hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                         par ^= 1u << cs_s;
                         sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;
                     }
-                    // chunk 2 pc + 2 (behind the last pair of the row block: bytes nobody uses)
-#define IFB_HV_RELOAD_B raw = hv::lds_u32x4(sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz));
-                    IFB_HV_CHUNK(wB, wnext, IFB_HV_RELOAD_B, 4)
-#undef IFB_HV_RELOAD_A
-#undef IFB_HV_RELOAD_B
+                    // behind the pair's seventh column: the next pair's first chunk (chunk 2 pc + 2; behind the last pair of the row block: bytes nobody uses)
+#define IFB_HV_RELOAD rawA = hv::lds_u32x4(sbase + (((((pc + 1u) & 1u) << 1) << 4) ^ swz));
+                    // A chunk (four source columns) exists in six compiled forms, picked by tests whose operands are known long before
+                    // they are needed: no completion (plain straight-line code: about half of the chunks of a 7.5 : 1 down-scale); exactly
+                    // one completion and no column that completes twice -- one form per ring slot of the completing column, with a
+                    // predicated "park and clear" of that slot behind every column (no branch inside, no look-up of the slot); and
+                    // the general form with a test behind every column.
+#define IFB_HV_ACC(S_, C_) (((S_) & 1) ? accH[C_][((S_) % AV) / 2].y : accH[C_][((S_) % AV) / 2].x)
+#define IFB_HV_PF(S_, BIT_, M_) { \
+        if (CH == 3) hv::flush3_if<BIT_, kXCol>(xw, IFB_HV_ACC(S_, 0), IFB_HV_ACC(S_, 1), IFB_HV_ACC(S_, 2), M_); \
+        else hv::flush4_if<BIT_, kXCol>(xw, IFB_HV_ACC(S_, 0), IFB_HV_ACC(S_, 1), IFB_HV_ACC(S_, 2), IFB_HV_ACC(S_, CH - 1), M_); }
+#define IFB_HV_NONE
+#define IFB_HV_STEPS_A(F0_, F1_, F2_, F3_) { \
+        wload(W1, wcur + kRec); conv(P1, rawA.y); mac(P0, W0); F0_ \
+        wload(W0, wcur + 2u * kRec); conv(P0, rawA.z); mac(P1, W1); F1_ \
+        wload(W1, wcur + 3u * kRec); conv(P1, rawA.w); mac(P0, W0); F2_ \
+        wload(W0, wB); conv(P0, rawB.x); mac(P1, W1); F3_ }
+#define IFB_HV_STEPS_B(F0_, F1_, F2_, F3_) { \
+        wload(W1, wB + kRec); conv(P1, rawB.y); mac(P0, W0); F0_ \
+        wload(W0, wB + 2u * kRec); conv(P0, rawB.z); mac(P1, W1); F1_ \
+        wload(W1, wB + 3u * kRec); conv(P1, rawB.w); IFB_HV_RELOAD mac(P0, W0); F2_ \
+        wload(W0, wnext); conv(P0, rawA.x); mac(P1, W1); F3_ }
+#define IFB_HV_CHUNK(STEPS_, SH_) { \
+        const uint32_t m4_ = (hm >> (SH_)) & 15u; \
+        if (IFB_HV_NOFAST || AV != 4 || ((((hm2 >> (SH_)) & 15u) | (m4_ & (m4_ - 1u))) != 0u)) { \
+            STEPS_(IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) \
+        } else if (m4_ == 0u) { \
+            STEPS_(IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
+        } else { \
+            if (hslot < 2u) { \
+                if (hslot == 0u) STEPS_(IFB_HV_PF(0, 1u, m4_), IFB_HV_PF(0, 2u, m4_), IFB_HV_PF(0, 4u, m4_), IFB_HV_PF(0, 8u, m4_)) \
+                else STEPS_(IFB_HV_PF(1, 1u, m4_), IFB_HV_PF(1, 2u, m4_), IFB_HV_PF(1, 4u, m4_), IFB_HV_PF(1, 8u, m4_)) \
+            } else { \
+                if (hslot == 2u) STEPS_(IFB_HV_PF(2, 1u, m4_), IFB_HV_PF(2, 2u, m4_), IFB_HV_PF(2, 4u, m4_), IFB_HV_PF(2, 8u, m4_)) \
+                else STEPS_(IFB_HV_PF(3, 1u, m4_), IFB_HV_PF(3, 2u, m4_), IFB_HV_PF(3, 4u, m4_), IFB_HV_PF(3, 8u, m4_)) \
+            } \
+            ++colbuf; hslot = (hslot + 1u) & 3u; \
+        } }
+                    IFB_HV_CHUNK(IFB_HV_STEPS_A, 0)
+                    IFB_HV_CHUNK(IFB_HV_STEPS_B, 4)
 #undef IFB_HV_CHUNK
-#undef IFB_HV_CHUNK4
+#undef IFB_HV_STEPS_A
+#undef IFB_HV_STEPS_B
 #undef IFB_HV_NONE
-#undef IFB_HV_FLUSH1
+#undef IFB_HV_PF
+#undef IFB_HV_ACC
+#undef IFB_HV_RELOAD
 #undef IFB_HV_FLUSH
 #undef IFB_HV_SLOT
                     wcur = wnext;
@@ -541,8 +565,34 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                             break;
                         }
                         {
-                            int Yl = Yc;
+                            // Completed output rows are not encoded where they complete: the lanes that hold the row's slot park its values in
+                            // the exchange buffer -- row k of their column for the k-th completion of the block; rows 0..k of the buffer have
+                            // been consumed by then -- and the store epilogue runs afterwards over the parked rows with ALL lanes at work
+                            // (lane = (row k mod NP, column)) and no branch in its body.
+                            int Yb = Yc;                                   // output row of parked row 0
+                            uint32_t nc = 0;                               // rows parked
                             uint32_t vs = vslot;
+                            auto drain = [&]() {
+                                hv::warp_sync();
+#pragma unroll 1
+                                for (uint32_t k0 = 0; k0 < nc; k0 += (uint32_t)NP) {
+                                    const uint32_t k = k0 + (vlane ? vh : 0u);
+                                    float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                                    for (int ch_ = 0; ch_ < CH; ++ch_) f_[ch_] = hv::lds_f32(xr + (uint32_t)ch_ * 128u + (k & 31u) * 4u);
+                                    const int Yl = Yb + (int)k;
+                                    const bool mine = k < nc && Yl >= bY0 && Yl < bY1 && col_live;
+                                    uint8_t* dst = out_px + (size_t)Yl * out_stride;
+                                    if (EPI != 0) {                        // the encode never reads the canvas: every lane runs it, the owners store
+                                        const uint32_t px_ = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
+                                        if (mine) *reinterpret_cast<uint32_t*>(dst) = px_;
+                                    } else if (mine) {
+                                        *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
+                                    }
+                                }
+                                hv::warp_sync();
+                                Yb += (int)nc; nc = 0;
+                            };
                             const float* __restrict__ vwp = pl.vw + (size_t)row0 * AVP + 2u * (vlane ? vh : 0u);   // this lane's pair of V weights, row by row
                             uint32_t xrr = xr;
                             auto vrow = [&](const float* __restrict__ wp, const uint32_t xa_) {
@@ -567,27 +617,22 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                                     if (vm2 != 0u && ((vm2 >> (r - 1)) & 1u)) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
 #pragma unroll 1
                                     for (uint32_t e2 = 0; e2 < nv; ++e2) {
+                                        if (nc >= (uint32_t)r) drain();    // (only when several rows complete at once near the top of a block)
+                                        hv::warp_sync();                   // the column's other lanes have read the row that is about to be overwritten
                                         const bool holder = (vs >> 1) == vh;
-                                        float f_[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                                        const uint32_t pa = xr + nc * 4u;
                                         if (vs & 1u) {
 #pragma unroll
-                                            for (int ch_ = 0; ch_ < CH; ++ch_) { f_[ch_] = acc[ch_].y; if (holder) acc[ch_].y = 0.0f; }
+                                            for (int ch_ = 0; ch_ < CH; ++ch_) if (holder) { hv::sts_f32(pa + (uint32_t)ch_ * 128u, acc[ch_].y); acc[ch_].y = 0.0f; }
                                         } else {
 #pragma unroll
-                                            for (int ch_ = 0; ch_ < CH; ++ch_) { f_[ch_] = acc[ch_].x; if (holder) acc[ch_].x = 0.0f; }
+                                            for (int ch_ = 0; ch_ < CH; ++ch_) if (holder) { hv::sts_f32(pa + (uint32_t)ch_ * 128u, acc[ch_].x); acc[ch_].x = 0.0f; }
                                         }
-                                        const bool mine = holder && Yl >= bY0 && Yl < bY1 && col_live;
-                                        uint8_t* dst = out_px + (size_t)Yl * out_stride;
-                                        if (EPI != 0) {                    // the encode never reads the canvas: every lane runs it, the owners store (no branch)
-                                            const uint32_t px_ = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
-                                            if (mine) *reinterpret_cast<uint32_t*>(dst) = px_;
-                                        } else if (mine) {
-                                            *reinterpret_cast<uint32_t*>(dst) = hv_finish_pixel<EPI, CH>(f_[0], f_[1], f_[2], CH == 4 ? f_[3] : 0.0f, flags, job, lut, lut_lane, dst);
-                                        }
-                                        ++Yl; vs = vs + 1u == (uint32_t)AV ? 0u : vs + 1u;
+                                        ++nc; vs = vs + 1u == (uint32_t)AV ? 0u : vs + 1u;
                                     }
                                 }
                             }
+                            drain();
                         }
                         switch (grp) {
 #define IFB_HV_VGROUP(G_) case G_: if (G_ < NG) { _Pragma("unroll") for (int ch_ = 0; ch_ < CH; ++ch_) accV[(G_) % NG][ch_] = acc[ch_]; } break;
@@ -600,7 +645,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     }
                   }
                 }
-                cs_s = cs_s + 1 == S ? 0 : cs_s + 1;
+                cs_s ^= 1;
                 // every group of the row block has seen the same rows: commit the vertical position
                 Yc += (int)vtot;
                 vslot = (vslot + vtot) % (uint32_t)AV;
