@@ -71,7 +71,9 @@ template <int AV, int CH> struct HvCfg {
     static constexpr int kBoxBytes = 32 * 64;                         // one box: 32 rows x 16 pixels
     static constexpr int kStageBytes = kBoxBytes;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kXPitch = CH * 32 + 1;                       // words per column of the exchange buffer (odd: conflict-free both ways)
+    static constexpr int kXPitch = CH * 32 + 2;                       // words per column of the exchange buffer: rows are written one word per lane (any
+                                                                      // pitch is conflict-free), the V pass reads two rows per access: 8-byte aligned columns
+                                                                      // whose 16 (or 10) 8-byte accesses fall into different bank pairs (pitch = 2 mod 32)
     static constexpr int kXBytes = kCG * kXPitch * 4;
 };
 
@@ -159,6 +161,7 @@ __device__ __forceinline__ void flush4_if(uint32_t& xw, float& a0, float& a1, fl
 }
 // 0, but only once v has arrived (a register dependency the compiler cannot remove)
 __device__ __forceinline__ uint32_t zero_after(uint32_t v) { uint32_t z; asm volatile("xor.b32 %0, %1, %1;" : "=r"(z) : "r"(v)); return z; }
+__device__ __forceinline__ float saturate(float v) { return __saturatef(v); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
@@ -234,8 +237,8 @@ __device__ __forceinline__ uint32_t hv_finish_pixel(float b, float g, float r, f
     const bool linear = EPI == 1 ? true : EPI == 2 ? false : (flags & JF_LINEAR) != 0u;
     auto enc = [&](float v) -> uint32_t {
         if (linear) {                                          // lut.rs:4-8
-            float s = __fmul_rn(v, 16383.0f);
-            s = fminf(fmaxf(s, 0.0f), 16383.0f);
+            const float s = __fmul_rn(hv::saturate(v), 16383.0f);   // == min(max(v * 16383, 0), 16383) for every v (lut.rs:4-8): same product inside
+                                                                     // [0, 1], the bounds outside, 0 for NaN
             const uint32_t i = (uint32_t)(int)s;
             return hv::lds_lut_u8(lut + 128u + i + (i & 0x3f80u));
         }
@@ -517,23 +520,25 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         wload(W0, wnext); conv(P0, rawA.x); mac(P1, W1); F3_ }
 #define IFB_HV_CHUNK(STEPS_, SH_) { \
         const uint32_t m4_ = (hm >> (SH_)) & 15u; \
-        if (IFB_HV_NOFAST || AV != 4 || ((((hm2 >> (SH_)) & 15u) | (m4_ & (m4_ - 1u))) != 0u)) { \
+        if (IFB_HV_NOFAST || ((((hm2 >> (SH_)) & 15u) | (m4_ & (m4_ - 1u))) != 0u)) { \
             STEPS_(IFB_HV_FLUSH((SH_) + 0), IFB_HV_FLUSH((SH_) + 1), IFB_HV_FLUSH((SH_) + 2), IFB_HV_FLUSH((SH_) + 3)) \
         } else if (m4_ == 0u) { \
             STEPS_(IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE, IFB_HV_NONE) \
         } else { \
             if (hslot < 2u) { \
-                if (hslot == 0u) STEPS_(IFB_HV_PF(0, 1u, m4_), IFB_HV_PF(0, 2u, m4_), IFB_HV_PF(0, 4u, m4_), IFB_HV_PF(0, 8u, m4_)) \
-                else STEPS_(IFB_HV_PF(1, 1u, m4_), IFB_HV_PF(1, 2u, m4_), IFB_HV_PF(1, 4u, m4_), IFB_HV_PF(1, 8u, m4_)) \
+                if (hslot == 0u) IFB_HV_FORM(STEPS_, 0) else IFB_HV_FORM(STEPS_, 1) \
+            } else if (AV == 4 || hslot < 4u) { \
+                if (hslot == 2u) IFB_HV_FORM(STEPS_, 2) else IFB_HV_FORM(STEPS_, 3) \
             } else { \
-                if (hslot == 2u) STEPS_(IFB_HV_PF(2, 1u, m4_), IFB_HV_PF(2, 2u, m4_), IFB_HV_PF(2, 4u, m4_), IFB_HV_PF(2, 8u, m4_)) \
-                else STEPS_(IFB_HV_PF(3, 1u, m4_), IFB_HV_PF(3, 2u, m4_), IFB_HV_PF(3, 4u, m4_), IFB_HV_PF(3, 8u, m4_)) \
+                if (hslot == 4u) IFB_HV_FORM(STEPS_, 4) else IFB_HV_FORM(STEPS_, 5) \
             } \
-            ++colbuf; hslot = (hslot + 1u) & 3u; \
+            ++colbuf; hslot = hslot + 1u == (uint32_t)AV ? 0u : hslot + 1u; \
         } }
+#define IFB_HV_FORM(STEPS_, K_) STEPS_(IFB_HV_PF((K_) % AV, 1u, m4_), IFB_HV_PF((K_) % AV, 2u, m4_), IFB_HV_PF((K_) % AV, 4u, m4_), IFB_HV_PF((K_) % AV, 8u, m4_))
                     IFB_HV_CHUNK(IFB_HV_STEPS_A, 0)
                     IFB_HV_CHUNK(IFB_HV_STEPS_B, 4)
 #undef IFB_HV_CHUNK
+#undef IFB_HV_FORM
 #undef IFB_HV_STEPS_A
 #undef IFB_HV_STEPS_B
 #undef IFB_HV_NONE
@@ -603,15 +608,26 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                                     acc[ch_] = hv::ffma2(wv, make_float2(x_, x_), acc[ch_]);
                                 }
                             };
+                            auto vrow2 = [&](const float* __restrict__ wp, const uint32_t xa_) {      // rows r, r + 1 (r even): one 8-byte access per channel
+                                const float2 wa = hv::ldg(reinterpret_cast<const float2*>(wp)), wb = hv::ldg(reinterpret_cast<const float2*>(wp + AVP));
+#pragma unroll
+                                for (int ch_ = 0; ch_ < CH; ++ch_) {
+                                    const float2 x_ = hv::lds_w2(xa_ + (uint32_t)ch_ * 128u);
+                                    acc[ch_] = hv::ffma2(wa, make_float2(x_.x, x_.x), acc[ch_]);
+                                    acc[ch_] = hv::ffma2(wb, make_float2(x_.y, x_.y), acc[ch_]);
+                                }
+                            };
                             // all 32 rows of the block (rows below the band's last carry no completion bit, and what they add to a slot is never
-                            // read), in runs that end with a row that completes an output row; a run is walked two rows at a time
+                            // read), in runs that end with a row that completes an output row; a run is walked two rows at a time from its
+                            // first even row
                             for (int r = 0; r < 32;) {
                                 const uint32_t rest = vm1 >> r;
-                                const int n = rest ? __ffs((int)rest) : 32 - r;
-#pragma unroll 1
-                                for (int i = n >> 1; i > 0; --i, vwp += 2 * AVP, xrr += 8u) { vrow(vwp, xrr); vrow(vwp + AVP, xrr + 4u); }
-                                if (n & 1) { vrow(vwp, xrr); vwp += AVP; xrr += 4u; }
+                                int n = rest ? __ffs((int)rest) : 32 - r;
                                 r += n;
+                                if (((xrr - xr) & 4u) != 0u) { vrow(vwp, xrr); vwp += AVP; xrr += 4u; --n; }
+#pragma unroll 1
+                                for (int i = n >> 1; i > 0; --i, vwp += 2 * AVP, xrr += 8u) vrow2(vwp, xrr);
+                                if (n & 1) { vrow(vwp, xrr); vwp += AVP; xrr += 4u; }
                                 if (rest != 0u) {
                                     uint32_t nv = 1u;
                                     if (vm2 != 0u && ((vm2 >> (r - 1)) & 1u)) nv = uni((uint32_t)hv::ldg(pl.vdone + row0 + r - 1));
