@@ -50,6 +50,7 @@ struct HvPlanDev {
     const uint8_t* hdone;     // [n_strips][cap px + 32]: output columns completing after this pixel
     const float* vw;          // [in_h][AVP]
     const uint8_t* vdone;     // [in_h + 32]
+    uint32_t zero;            // 0 (a zero the compiler cannot see: hv::zero_after)
 };
 struct alignas(64) HvTmap { unsigned char bytes[128]; };              // CUtensorMap of one job's input bitmap (u32 pixels, box 16 x 32, SWIZZLE_64B)
 
@@ -159,8 +160,11 @@ __device__ __forceinline__ void flush4_if(uint32_t& xw, float& a0, float& a1, fl
                  "@q add.u32 %0, %0, %7;\n\t}"
                  : "+r"(xw), "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3) : "r"(mask), "n"(BIT), "n"(STEP) : "memory");
 }
-// 0, but only once v has arrived (a register dependency the compiler cannot remove)
-__device__ __forceinline__ uint32_t zero_after(uint32_t v) { uint32_t z; asm volatile("xor.b32 %0, %1, %1;" : "=r"(z) : "r"(v)); return z; }
+// 0, but only once v has arrived: v & zero with a zero that comes from the kernel's arguments, so that the instruction (and the
+// scoreboard wait on v) survives.  (v ^ v is folded away by ptxas; and it also drops __syncwarp() where it knows the warp to be
+// converged, so nothing else would keep a TMA refill of a ring slot behind the slot's last LDS.  Found with compute-sanitizer:
+// its instrumented loads are slow enough to lose that race.)
+__device__ __forceinline__ uint32_t zero_after(uint32_t v, uint32_t zero) { uint32_t z; asm volatile("and.b32 %0, %1, %2;" : "=r"(z) : "r"(v), "r"(zero)); return z; }
 __device__ __forceinline__ float saturate(float v) { return __saturatef(v); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
@@ -491,7 +495,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     rawB = hv::lds_u32x4(sbase + (((((pc & 1u) << 1) | 1u) << 4) ^ swz));
                     if ((pc & 1u) && more) {
                         cs_s ^= 1;
-                        if (tma_left > 0) issue(hv::zero_after(rawB.x));
+                        if (tma_left > 0) issue(hv::zero_after(rawB.x, pl.zero));
                         hv::mbar_wait(mb + 8u * (uint32_t)cs_s, (par >> cs_s) & 1u);
                         par ^= 1u << cs_s;
                         sbase = stb + (uint32_t)cs_s * C::kStageBytes + (uint32_t)lane * 64u;

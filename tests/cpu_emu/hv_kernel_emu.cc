@@ -84,7 +84,7 @@ template <uint32_t BIT, uint32_t STEP> static inline void flush3_if(uint32_t& xw
 template <uint32_t BIT, uint32_t STEP> static inline void flush4_if(uint32_t& xw, float& a0, float& a1, float& a2, float& a3, uint32_t mask) {
     if (mask & BIT) { sts_f32(xw, a0); sts_f32(xw + 128u, a1); sts_f32(xw + 256u, a2); sts_f32(xw + 384u, a3); a0 = a1 = a2 = a3 = 0.0f; xw += STEP; }
 }
-static inline uint32_t zero_after(uint32_t) { return 0u; }
+static inline uint32_t zero_after(uint32_t v, uint32_t zero) { return v & zero; }
 static inline float saturate(float v) { return v != v ? 0.0f : (v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v)); }
 static inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     const uint64_t src = ((uint64_t)b << 32) | a;
