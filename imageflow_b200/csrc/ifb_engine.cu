@@ -153,6 +153,7 @@ struct AxisOnDev {
 // Streaming H-then-V ring kernel (ifb_hv_kernel.cuh): host tables of one plan.
 struct HvTables {
     int max_cols = 0, n_strips = 0;
+    uint32_t hw_stride = 0;             // weight records per strip (the longest pixel stream + the chunk the kernel reads ahead), <= cap
     std::vector<HvStripDev> strips;     // host copy (band choice, tests)
     DevBlob blob;                       // strips, hw, hdone, vw, vdone: one allocation, one asynchronous copy
     size_t o_strips = 0, o_hw = 0, o_hdone = 0, o_vw = 0, o_vdone = 0;
@@ -278,10 +279,13 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
         if (ns > h.out_size) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: strip partition failed");
     }
     ht->n_strips = (int)ns;
-    const size_t hd_stride = (size_t)cap + 64;
-    ht->blob.reserve(ns * (sizeof(HvStripDev) + (size_t)cap * avp * 4 + hd_stride) + ((size_t)p.in_h + 32) * (avp * 4 + 1) + 4096);
+    uint32_t rec = 0;                                        // table rows per strip: what the longest stream needs, not the capacity (a mixed
+    for (const auto& sd : strips) rec = std::max<uint32_t>(rec, (uint32_t)sd.nst * 16u + 16u);   // workload uploads thousands of these tables)
+    ht->hw_stride = rec;
+    const size_t hd_stride = (size_t)rec + 64;
+    ht->blob.reserve(ns * (sizeof(HvStripDev) + (size_t)rec * avp * 4 + hd_stride) + ((size_t)p.in_h + 32) * (avp * 4 + 1) + 4096);
     ht->o_strips = ht->blob.add(strips);
-    ht->o_hw = ht->blob.add_zeroed((size_t)ns * cap * avp * sizeof(float));
+    ht->o_hw = ht->blob.add_zeroed((size_t)ns * rec * avp * sizeof(float));
     ht->o_hdone = ht->blob.add_zeroed((size_t)ns * hd_stride);
     ht->o_vw = ht->blob.add_zeroed(((size_t)p.in_h + 32) * avp * sizeof(float));   // 32 rows of zeros behind the last: a row block may end below the bitmap
     ht->o_vdone = ht->blob.add_zeroed((size_t)p.in_h + 32);
@@ -296,7 +300,7 @@ std::unique_ptr<HvTables> hv_tables_host(const Plan& p, int cols_key) {
         for (uint32_t X = (uint32_t)sd.X0; X < (uint32_t)sd.X1; ++X) {
             const float* w = h.w.data() + h.offset[X];
             const uint32_t slot = X % (uint32_t)av;
-            for (uint32_t k = h.left[X]; k <= h.right[X]; ++k) hw[((size_t)s * cap + (k - k0)) * avp + slot] = w[k - h.left[X]];
+            for (uint32_t k = h.left[X]; k <= h.right[X]; ++k) hw[((size_t)s * rec + (k - k0)) * avp + slot] = w[k - h.left[X]];
             uint8_t& d = hdone[(size_t)s * hd_stride + (h.right[X] - k0)];
             if (d == 127) IFB_THROW(IFB200_ERR_INVALID_STATE, "ring kernel: too many columns complete at once");
             ++d;
@@ -826,6 +830,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             pl.bands = reinterpret_cast<const HvBandDev*>(dbuf + lay[gi].bands);
             pl.hw = ht.blob.at<float>(ht.o_hw); pl.hdone = ht.blob.at<uint8_t>(ht.o_hdone);
             pl.vw = ht.blob.at<float>(ht.o_vw); pl.vdone = ht.blob.at<uint8_t>(ht.o_vdone);
+            pl.hw_stride = ht.hw_stride;
             HvFn fn = he->fn[g.simple ? ((g.variant & 1) ? 1 : 2) : 0];        // the ring kernel's launches are per working space (variant bit 0 = linear)
             const size_t smem = he->smem(b->smem_base_low16);
             if (!b->hv_attr_set.count((const void*)fn)) {
@@ -1235,7 +1240,7 @@ int ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_p
         const std::vector<HvBandDev> bands = hv_bands(*p, n_pairs);
         const size_t o_bands = (ht.blob.host.size() + 255) / 256 * 256;
         info->ok = 1; info->av = p->av; info->n_strips = ht.n_strips; info->n_bands = (int32_t)bands.size();
-        info->avp = p->av == 4 ? 4 : 8; info->cap_px = 16384 / (info->avp * 4);
+        info->avp = p->av == 4 ? 4 : 8; info->cap_px = (int32_t)ht.hw_stride;       // weight records per strip in hw (hdone: + 64 bytes)
         info->o_strips = ht.o_strips; info->o_hw = ht.o_hw; info->o_hdone = ht.o_hdone; info->o_vw = ht.o_vw; info->o_vdone = ht.o_vdone;
         info->o_bands = o_bands; info->total = o_bands + bands.size() * sizeof(HvBandDev);
         if (!buf) return;

@@ -46,11 +46,12 @@ struct HvPlanDev {
     int n_strips, n_bands;
     const HvStripDev* strips;
     const HvBandDev* bands;
-    const float* hw;          // [n_strips][cap px][AVP]: weight of the open output column in each ring slot, pixel-stream order
-    const uint8_t* hdone;     // [n_strips][cap px + 32]: output columns completing after this pixel
+    const float* hw;          // [n_strips][hw_stride][AVP]: weight of the open output column in each ring slot, pixel-stream order
+    const uint8_t* hdone;     // [n_strips][hw_stride + 64]: output columns completing after this pixel (bits 0..6), V-pass mark (bit 7)
     const float* vw;          // [in_h][AVP]
     const uint8_t* vdone;     // [in_h + 32]
     uint32_t zero;            // 0 (a zero the compiler cannot see: hv::zero_after)
+    uint32_t hw_stride;       // source columns (weight records) per strip in hw; hdone has hw_stride + 64 bytes per strip
 };
 struct alignas(64) HvTmap { unsigned char bytes[128]; };              // CUtensorMap of one job's input bitmap (u32 pixels, box 16 x 32, SWIZZLE_64B)
 
@@ -351,12 +352,12 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         const uint32_t sH0 = uni((uint32_t)sd_.hslot0);
         const int sK0 = (int)uni((uint32_t)sd_.k0), nst = (int)uni((uint32_t)sd_.nst);
         {   // H weights of the strip: 16-byte units u -> hole 128 + u/8, offset (u%8)*16
-            const float4* __restrict__ src = reinterpret_cast<const float4*>(pl.hw + (size_t)s * C::kCapPx * AVP);
+            const float4* __restrict__ src = reinterpret_cast<const float4*>(pl.hw + (size_t)s * pl.hw_stride * AVP);
             const int n16 = (nst * 16 + 4) * AVP / 4;                      // + one chunk: the pipeline fetches one record ahead
             for (int u = t; u < n16; u += C::kThreads) hv::sts_f32x4(lutw + ((uint32_t)(u >> 3) << 8) + ((uint32_t)(u & 7) << 4), hv::ldg(src + u));
         }
         hv::cta_sync();
-        const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (C::kCapPx + 64);
+        const uint8_t* __restrict__ hdone = pl.hdone + (size_t)s * (pl.hw_stride + 64u);
         const uint32_t npairs = (uint32_t)nst * 2u;                        // chunk pairs (eight source columns) per row block
 
         for (;;) {

@@ -112,7 +112,7 @@ int  ifb200_plan_probe(const ifb200_resample_desc* descs, size_t n, int threads,
    would be uploaded (alpha_meaningful selects the 3- or 4-channel kernel variant's strip width): call with buf = NULL for the size.  info->ok == 0: the geometry does not run on the ring kernel.
    Layout: imageflow_b200/csrc/ifb_hv_kernel.cuh (HvStripDev, HvBandDev, HvPlanDev).  No CUDA call. */
 typedef struct ifb200_hv_plan_info {
-    int32_t ok, av, n_strips, n_bands, cap_px, avp;
+    int32_t ok, av, n_strips, n_bands, cap_px /* weight records per strip in hw; hdone has cap_px + 64 bytes per strip */, avp;
     uint64_t o_strips, o_hw, o_hdone, o_vw, o_vdone, o_bands, total;
 } ifb200_hv_plan_info;
 int  ifb200_hv_plan_tables(const ifb200_resample_desc* d, int strip_cols, int n_band_pairs, ifb200_hv_plan_info* info, uint8_t* buf, size_t cap,

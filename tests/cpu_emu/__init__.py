@@ -179,7 +179,7 @@ def run_hv(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=2, sharpen
     in_ptrs = (C.c_void_p * jobs_repeat)(*[wide.ctypes.data] * jobs_repeat)
     in_whs = np.array([iw + in_xoff, ih, pitch] * jobs_repeat, np.uint32)
     offs = np.array([info.o_strips, info.o_hw, info.o_hdone, info.o_vw, info.o_vdone, info.o_bands, info.total], np.uint64)
-    dims = np.array([iw, ih, w, h], np.uint32)
+    dims = np.array([iw, ih, w, h, info.cap_px], np.uint32)
     bad = lib.emu_hv_launch(info.av, ch, int(simple), grid, C.cast(jobs, C.c_void_p), jobs_repeat, C.cast(in_ptrs, C.c_void_p), in_whs.ctypes.data,
                             t_lin.ctypes.data, t_srgb.ctypes.data, lut.ctypes.data, blob.ctypes.data, offs.ctypes.data, dims.ctypes.data,
                             info.n_strips, info.n_bands, sb_low16)

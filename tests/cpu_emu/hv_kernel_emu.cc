@@ -182,7 +182,7 @@ static Pick pick(int av, int ch, int epi) {      // epi: 0 general, 1 simple + l
 extern "C" uint32_t emu_hv_sizeof_jobdev(void) { return (uint32_t)sizeof(JobDev); }
 
 // One launch of hv_ring_kernel<av, ch, simple> with `grid` CTAs.  `blob` = the tables of ifb200_hv_plan_tables (offsets in o[7]:
-// strips, hw, hdone, vw, vdone, bands, total); in_ptrs[i] / in_whs[i*3..] describe job i's input bitmap (the TMA descriptor).
+// strips, hw, hdone, vw, vdone, bands, total; dims4[4] = weight records per strip = info.cap_px); in_ptrs[i] / in_whs[i*3..] describe job i's input bitmap (the TMA descriptor).
 // sb_low16: where dynamic shared memory starts in the emulated shared window.  Returns the number of bad accesses (0 = clean).
 extern "C" int emu_hv_launch(int av, int ch, int simple, unsigned grid, const void* jobs, uint32_t n_jobs, const uint8_t* const* in_ptrs,
                              const uint32_t* in_whs, const float* t_lin, const float* t_srgb, const uint8_t* lut16k, const uint8_t* blob,
@@ -192,7 +192,7 @@ extern "C" int emu_hv_launch(int av, int ch, int simple, unsigned grid, const vo
     std::vector<EmuTmap> tms(n_jobs);
     for (uint32_t i = 0; i < n_jobs; ++i) { tms[i] = EmuTmap{}; tms[i].base = in_ptrs[i]; tms[i].w = in_whs[i * 3]; tms[i].h = in_whs[i * 3 + 1]; tms[i].stride = in_whs[i * 3 + 2]; }
     HvPlanDev pl{};
-    pl.in_w = dims4[0]; pl.in_h = dims4[1]; pl.out_w = dims4[2]; pl.out_h = dims4[3];
+    pl.in_w = dims4[0]; pl.in_h = dims4[1]; pl.out_w = dims4[2]; pl.out_h = dims4[3]; pl.hw_stride = dims4[4];
     pl.n_strips = n_strips; pl.n_bands = n_bands;
     pl.strips = reinterpret_cast<const HvStripDev*>(blob + o[0]);
     pl.hw = reinterpret_cast<const float*>(blob + o[1]); pl.hdone = blob + o[2];
