@@ -361,11 +361,16 @@ def git_sha():
 
 
 def lib_digest():
-    """identifies the binary a traffic measurement belongs to"""
+    """identifies the build a traffic measurement belongs to: a digest of the library's SOURCES (the in-tree .so is rebuilt from
+    them by __graft_entry__.build(); its bytes may differ between builds, what it is built from does not)"""
+    import glob
     import hashlib
-    import imageflow_b200
+    h = hashlib.sha256()
     try:
-        return hashlib.sha256(open(imageflow_b200.LIB_PATH, "rb").read()).hexdigest()[:16]
+        for f in sorted(glob.glob(os.path.join(ROOT, "imageflow_b200", "csrc", "*"))):
+            if f.endswith((".cu", ".cuh", ".cc", ".h", ".inc", "Makefile")):
+                h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+        return h.hexdigest()[:16]
     except Exception:
         return None
 
@@ -392,7 +397,7 @@ def measure_traffic(args):
         mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         vals[row[metric_i]] = v * mult
     out = {"workload": args.workload, "kernel": kname, "images_per_launch": n, "dram_bytes_per_launch": vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"],
-           "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"], "git": git_sha(), "lib_sha256_16": lib_digest(),
+           "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"], "git": git_sha(), "src_sha256_16": lib_digest(),
            "source": "bench.py --ncu-traffic: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch after 3 warm-up launches"}
     json.dump(out, open(os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json"), "w"), indent=1)
     print(json.dumps(out))
@@ -455,7 +460,7 @@ def main():
     if os.path.exists(tfile):
         try:
             tj = json.load(open(tfile))
-            if tj.get("lib_sha256_16") == lib_digest():      # only a measurement of THIS binary describes this run
+            if tj.get("src_sha256_16") == lib_digest():      # only a measurement of a build of THESE sources describes this run
                 roofline["traffic"] = tj["dram_bytes_per_launch"] * (B / tj["images_per_launch"])
                 roofline["traffic_source"] = tj.get("source")
                 roofline["traffic_kernel"] = tj.get("kernel")

@@ -118,7 +118,7 @@ struct DevVec {
 struct DevBlob {
     uint8_t* p = nullptr;
     std::vector<uint8_t> host;
-    cudaEvent_t ready = nullptr; bool done = false; cudaStream_t up_stream = nullptr;
+    cudaEvent_t ready = nullptr; bool owns_ready = true; bool done = false; cudaStream_t up_stream = nullptr;
     size_t add(const void* src, size_t bytes) {
         const size_t off = (host.size() + 255) / 256 * 256;
         host.resize(off + bytes);
@@ -137,7 +137,7 @@ struct DevBlob {
         CUDA_OK(cudaStreamWaitEvent(st, ready, 0));
     }
     template <class T> const T* at(size_t off) const { return reinterpret_cast<const T*>(p + off); }
-    ~DevBlob() { if (ready) cudaEventDestroy(ready); }     // the memory belongs to the batch's table arena
+    ~DevBlob() { if (ready && owns_ready) cudaEventDestroy(ready); }     // the memory belongs to the batch's table arena (and a shared event to the batch)
     DevBlob() = default;
     DevBlob(const DevBlob&) = delete;
     DevBlob& operator=(const DevBlob&) = delete;
@@ -458,6 +458,7 @@ struct ifb200_batch {
     ~ifb200_batch() {
         cudaSetDevice(device);
         for (auto& s : pinned) { if (s.ev) cudaEventDestroy(s.ev); if (s.p) cudaFreeHost(s.p); }
+        for (auto& e : shared_events) cudaEventDestroy(e);
         drop_plans();
         if (own_stream) cudaStreamDestroy(own_stream);
         for (auto& sd : side) if (sd) cudaStreamDestroy(sd);
@@ -468,6 +469,8 @@ struct ifb200_batch {
     // Bump allocator for plan tables: thousands of small tables cost one cudaMalloc per 32 MiB, not one each.
     // Freed as a whole together with the plan cache.
     std::vector<uint8_t*> arena_chunks; size_t arena_used = 0, arena_cap = 0;
+    std::vector<cudaEvent_t> shared_events;                   // `ready` events of table uploads that were committed together (commit_many)
+    void commit_many(cudaStream_t st, const std::vector<DevBlob*>& blobs);
     uint8_t* table_alloc(size_t bytes) {
         bytes = (bytes + 255) / 256 * 256;
         if (arena_chunks.empty() || arena_used + bytes > arena_cap) {
@@ -602,6 +605,46 @@ void DevBlob::commit(ifb200_batch* b, cudaStream_t st) {
     host.clear(); host.shrink_to_fit();
 }
 
+// The tables of many cold plans of one enqueue call: packed into few pinned chunks (<= 32 MiB), ONE asynchronous copy and ONE pair of
+// events per chunk instead of one of each per plan (a mixed thumbnail workload brings thousands of new geometries per call, and the
+// per-upload cost -- a staging slot, a cudaMemcpyAsync, two event records -- was most of its host time).
+void ifb200_batch::commit_many(cudaStream_t st, const std::vector<DevBlob*>& blobs) {
+    Tick tk(prof.upload);
+    const size_t kChunk = (size_t)32 << 20;
+    size_t i = 0;
+    while (i < blobs.size()) {
+        size_t j = i, bytes = 0;
+        while (j < blobs.size() && (j == i || bytes + (blobs[j]->host.size() + 255) / 256 * 256 <= kChunk)) { bytes += (blobs[j]->host.size() + 255) / 256 * 256; ++j; }
+        uint8_t* dst = table_alloc(bytes);
+        cudaEvent_t slot_ev;
+        uint8_t* pin = static_cast<uint8_t*>(stage(bytes, &slot_ev));
+        cudaEvent_t ready;
+        CUDA_OK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        shared_events.push_back(ready);
+        size_t off = 0;
+        {
+            Tick tm(prof.memcpy_);
+            for (size_t k = i; k < j; ++k) {
+                DevBlob& bl = *blobs[k];
+                memcpy(pin + off, bl.host.data(), bl.host.size());
+                off += (bl.host.size() + 255) / 256 * 256;
+            }
+        }
+        CUDA_OK(cudaMemcpyAsync(dst, pin, bytes, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaEventRecord(slot_ev, st));            // releases the pinned slot
+        CUDA_OK(cudaEventRecord(ready, st));
+        off = 0;
+        for (size_t k = i; k < j; ++k) {
+            DevBlob& bl = *blobs[k];
+            ++prof.commits; prof.staged_bytes += bl.host.size();
+            bl.p = dst + off; bl.ready = ready; bl.owns_ready = false; bl.up_stream = st;
+            off += (bl.host.size() + 255) / 256 * 256;
+            bl.host.clear(); bl.host.shrink_to_fit();
+        }
+        i = j;
+    }
+}
+
 namespace {
 
 // CSR windows on the device (tile kernel and generic pair only)
@@ -729,6 +772,28 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         if (!g) { groups.push_back(Group{&p, ch, kind, simple, variant, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
+    // tables of the plans this call sees for the first time, in launch order: uploaded in packed slices (commit_many) just ahead
+    // of the launches that need them, so that the GPU starts on the first geometries while the host is still preparing the later ones
+    std::vector<DevBlob*> cold;
+    {
+        std::set<DevBlob*> seen;
+        for (auto& g : groups) {
+            Plan& p = *g.plan;
+            DevBlob* bl = nullptr;
+            if (g.kind == 1) {
+                bl = &p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols))->blob;
+            } else {
+                if (!p.axes) { p.axes = std::make_unique<DevBlob>(); p.dv.add_to(*p.axes, p.wv); p.dh.add_to(*p.axes, p.wh); }
+                bl = p.axes.get();
+            }
+            if (!bl->p && !bl->host.empty() && seen.insert(bl).second) cold.push_back(bl);
+        }
+    }
+    size_t cold_next = 0;
+    auto upload_ahead = [&](cudaStream_t up) {                // the next slice of cold tables (<= 128 plans)
+        const size_t end = std::min(cold.size(), cold_next + 128);
+        if (cold_next < end) { b->commit_many(up, std::vector<DevBlob*>(cold.begin() + cold_next, cold.begin() + end)); cold_next = end; }
+    };
     // job array (+ the ring kernel's TMA descriptors, band tables and work counters) -> device (pinned staging, stream ordered)
     struct GroupLayout { size_t jobs = 0, tmaps = 0, bands = 0, counters = 0; int nb = 0, grid = 0; std::vector<HvBandDev> bv; };
     std::vector<GroupLayout> lay(groups.size());
@@ -794,6 +859,10 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     for (size_t gi = 0; gi < groups.size(); ++gi) {
         Group& g = groups[gi];
         Plan& p = *g.plan;
+        {
+            const DevBlob* need = g.kind == 1 ? &p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols))->blob : p.axes.get();
+            while (need && !need->p && cold_next < cold.size()) upload_ahead(user_stream);
+        }
         const JobDev* jobs = reinterpret_cast<const JobDev*>(dbuf + lay[gi].jobs);
         const size_t nj = g.idx.size();
         st = fork ? b->side[gi % ifb200_batch::kSideStreams] : user_stream;
