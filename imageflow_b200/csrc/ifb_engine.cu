@@ -536,7 +536,19 @@ struct ifb200_batch {
         if (rc) IFB_THROW(rc, "horizontal weights failed: %s", ifb200_status_name(rc));
         build_hv(*p);
         build_tile(*p);
-        if (p->hv_ok) { hv_host_ready(*p, hv_cols(p->av, 3, strip_cols)); hv_host_ready(*p, hv_cols(p->av, 4, strip_cols)); }
+        if (p->hv_ok)
+            for (int ch : {3, 4}) {
+                // the strip width enqueue_locked() picks for a call with ONE job of this geometry (narrower strips for small images:
+                // see there), so that these tables too are built here, on the builder threads, and not inside the launch loop
+                int k = hv_cols(p->av, ch, strip_cols);
+                if (!hv_host_ready(*p, k)) continue;
+                const size_t max_nb = std::max<uint32_t>(1u, p->out_h / 8u), warps_all = 148u * 16u;
+                for (int c : {32, 16}) {
+                    if ((size_t)p->by_cols.at(k)->n_strips * max_nb >= warps_all || c >= strip_cols) break;
+                    k = hv_cols(p->av, ch, c);
+                    if (!hv_host_ready(*p, k)) break;
+                }
+            }
         return p;
     }
     Plan& plan_for(const ifb200_resample_desc& d) {
@@ -748,7 +760,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
     { Tick tk(b->prof.plans); b->prebuild_plans(descs, n); }
     // group jobs by (plan, kernel class)
     // kind: 0 generic pair, 1 ring kernel, 3 tile kernel (`variant` = its compile-time case)
-    struct Group { Plan* plan; int ch; int kind; bool simple; int variant; std::vector<size_t> idx; };
+    struct Group { Plan* plan; int ch; int kind; bool simple; int variant; std::vector<size_t> idx; int cols_key = 0; };
     std::vector<Group> groups;
     for (size_t i = 0; i < n; ++i) {
         Plan* pp; { Tick tk(b->prof.plans); pp = &b->plan_for(descs[i]); }
@@ -772,6 +784,23 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         if (!g) { groups.push_back(Group{&p, ch, kind, simple, variant, {}}); g = &groups.back(); }
         g->idx.push_back(i);
     }
+    // Strip width of every ring group: the widest (least halo) that still gives every warp of the device an item; a launch for one
+    // small image is bound by the latency of a warp's walk along its strip, so it gets narrower strips = more, shorter items.
+    for (auto& g : groups) {
+        if (g.kind != 1) continue;
+        Plan& p = *g.plan;
+        const HvEntry* he = find_hv(p.av, g.ch);
+        const size_t warps_all = (size_t)b->sm_count * he->warps;
+        const size_t max_nb = std::max<uint32_t>(1u, p.out_h / 8u);
+        g.cols_key = hv_cols(p.av, g.ch, b->strip_cols);
+        if (b->min_items == 0)
+            for (int c : {32, 16}) {
+                if (g.idx.size() * (size_t)p.by_cols.at(g.cols_key)->n_strips * max_nb >= warps_all || c >= b->strip_cols) break;
+                const int k = hv_cols(p.av, g.ch, c);
+                if (!hv_host_ready(p, k)) break;
+                g.cols_key = k;
+            }
+    }
     // tables of the plans this call sees for the first time, in launch order: uploaded in packed slices (commit_many) just ahead
     // of the launches that need them, so that the GPU starts on the first geometries while the host is still preparing the later ones
     std::vector<DevBlob*> cold;
@@ -781,7 +810,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             Plan& p = *g.plan;
             DevBlob* bl = nullptr;
             if (g.kind == 1) {
-                bl = &p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols))->blob;
+                bl = &p.by_cols.at(g.cols_key)->blob;
             } else {
                 if (!p.axes) { p.axes = std::make_unique<DevBlob>(); p.dv.add_to(*p.axes, p.wv); p.dh.add_to(*p.axes, p.wh); }
                 bl = p.axes.get();
@@ -805,7 +834,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         if (g.kind == 1) {
             Plan& p = *g.plan;
             const HvEntry* he = find_hv(p.av, g.ch);
-            const HvTables& ht = *p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols));
+            const HvTables& ht = *p.by_cols.at(g.cols_key);
             const size_t jxs = g.idx.size() * (size_t)ht.n_strips;
             const int warps_all = b->sm_count * he->warps;
             const int nb = hv_pick_bands(p, jxs, warps_all, b->min_items);
@@ -832,7 +861,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         }
         if (g.kind == 1) {
             memcpy(hbuf + lay[gi].bands, lay[gi].bv.data(), lay[gi].bv.size() * sizeof(HvBandDev));
-            memset(hbuf + lay[gi].counters, 0, (size_t)g.plan->by_cols.at(hv_cols(g.plan->av, g.ch, b->strip_cols))->n_strips * sizeof(uint32_t));
+            memset(hbuf + lay[gi].counters, 0, (size_t)g.plan->by_cols.at(g.cols_key)->n_strips * sizeof(uint32_t));
         }
     }
     uint8_t* dbuf = nullptr;
@@ -860,7 +889,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
         Group& g = groups[gi];
         Plan& p = *g.plan;
         {
-            const DevBlob* need = g.kind == 1 ? &p.by_cols.at(hv_cols(p.av, g.ch, b->strip_cols))->blob : p.axes.get();
+            const DevBlob* need = g.kind == 1 ? &p.by_cols.at(g.cols_key)->blob : p.axes.get();
             while (need && !need->p && cold_next < cold.size()) upload_ahead(user_stream);
         }
         const JobDev* jobs = reinterpret_cast<const JobDev*>(dbuf + lay[gi].jobs);
@@ -890,7 +919,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             }
             b->tile_jobs += nj;
         } else if (g.kind == 1) {
-            HvTables& ht = hv_tables(b, st, p, hv_cols(p.av, g.ch, b->strip_cols));
+            HvTables& ht = hv_tables(b, st, p, g.cols_key);
             const HvEntry* he = find_hv(p.av, g.ch);
             HvPlanDev pl{};
             pl.in_w = p.in_w; pl.in_h = p.in_h; pl.out_w = p.out_w; pl.out_h = p.out_h;

@@ -108,8 +108,10 @@ __host__ __device__ constexpr uint32_t hv_layout(uint32_t sb_low16, int warp, ui
         if (x_off) *x_off = w < xa ? a0 + ra * ring + w * xb : b_x + (w - xa) * xb;
         if (mb_off) *mb_off = b_mb + w * 8u * (uint32_t)C::kStages;
     }
-    return b_mb + W * 8u * (uint32_t)C::kStages;
+    return b_mb + W * 8u * (uint32_t)C::kStages + 16u;                // + one CTA-wide flag word (hv_flag_offset)
 }
+// window offset of the CTA-wide flag word: the last 16 bytes of the layout
+template <int AV, int CH> __host__ __device__ constexpr uint32_t hv_flag_offset(uint32_t sb_low16) { return hv_layout<AV, CH>(sb_low16, -1, nullptr, nullptr, nullptr) - 16u; }
 template <int AV, int CH> constexpr uint32_t hv_total_bytes(uint32_t sb_low16) { return hv_layout<AV, CH>(sb_low16, -1, nullptr, nullptr, nullptr); }
 
 // ---------------------------------------------------------------- primitives (tests/cpu_emu provides its own under IFB_HV_EMU)
@@ -213,15 +215,14 @@ __device__ __forceinline__ void tma_prefetch_box(const HvTmap* tm, int x, int y)
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(x), "r"(y) : "memory");
 }
 template <class T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ uint32_t ldg_volatile(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 }  // namespace hv
 #define IFB_HV_DYNAMIC_SMEM(name_) extern __shared__ __align__(1024) unsigned char name_[]
 #endif
 
 #ifndef IFB_HV_NOFAST
 #define IFB_HV_NOFAST 0                // 1: only the general form of a chunk (A/B builds)
-#endif
-#ifndef IFB_HV_PREFETCH_AHEAD
-#define IFB_HV_PREFETCH_AHEAD 0        // L2 prefetch distance in boxes (0 = off: measured 4 % faster than 8 on the 4K -> 512 batch)
 #endif
 
 // Where a CTA's dynamic shared memory starts in the shared window (the engine sizes the ring kernel's layout with it).
@@ -314,6 +315,7 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
         hv_layout<AV, CH>(sb & 0xffffu, warp, &o_st, &o_x, &o_mb);
         stb = sb + o_st; xbuf = sb + o_x; mb = sb + o_mb;
     }
+    const uint32_t flagw = sb + hv_flag_offset<AV, CH>(sb & 0xffffu);
     const uint32_t flags0 = jobs[0].flags;                                 // working space and channel count are the same for all jobs of a launch
 
     // ---- tables: forward LUT replicated for the 32 lanes; linear->sRGB table into holes 0..127
@@ -345,8 +347,22 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
     const uint32_t xw0 = xbuf + (uint32_t)lane * 4u;                       // H pass role: row `lane` of column 0
 
     for (int sv = 0; sv < pl.n_strips; ++sv) {
-        const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
+        // The next strip (from this CTA's starting strip on) whose work counter has not run out: warp 0 looks at up to 32 counters
+        // at once.  A launch for one small image has more strips than items per CTA, and every CTA used to copy every strip's
+        // weight table whether or not anything was left to do there (most of the 70 us such a launch took).
+        if (warp == 0) {
+            const int k = sv + lane;
+            const bool work = k < pl.n_strips && hv::ldg_volatile(counters + (blockIdx.x + (uint32_t)k) % (uint32_t)pl.n_strips) < n_items;
+            const uint32_t m = hv::ballot(work);
+            if (lane == 0) hv::sts_u32(flagw, m ? (uint32_t)__ffs((int)m) : (sv + 32 < pl.n_strips ? 33u : 0u));
+        }
         hv::cta_sync();                                                    // every warp is done with the previous strip's weights (first time: tables filled)
+        const uint32_t skip1 = hv::lds_u32(flagw);                         // 0: nothing left anywhere; 1..32: strips to skip + 1; 33: none of these 32
+        hv::cta_sync();                                                    // (the flag word is rewritten by the next look)
+        if (skip1 == 0u) break;
+        if (skip1 == 33u) { sv += 31; continue; }
+        sv += (int)skip1 - 1;
+        const int s = (int)((blockIdx.x + (uint32_t)sv) % (uint32_t)pl.n_strips);
         const HvStripDev sd_ = pl.strips[s];
         const int sX0 = (int)uni((uint32_t)sd_.X0);
         const uint32_t sH0 = uni((uint32_t)sd_.hslot0);
@@ -384,15 +400,6 @@ hv_ring_kernel(const JobDev* __restrict__ jobs, const HvTmap* __restrict__ tmaps
                     const uint32_t bar = mb + 8u * (uint32_t)is_s;
                     hv::mbar_expect_tx(bar, (uint32_t)C::kStageBytes);
                     hv::tma_load_box(stb + (uint32_t)is_s * C::kStageBytes, tm, tma_x + (int)zero_dep, tma_y, bar);
-#if IFB_HV_PREFETCH_AHEAD > 0
-                    // every fourth box: the box IFB_HV_PREFETCH_AHEAD further on its way into L2 (the descriptor promotes every request to
-                    // its 256-byte line, i.e. to the width of four boxes)
-                    if (((tma_x - x_origin) & 63) == 0) {
-                        int px = tma_x + 16 * IFB_HV_PREFETCH_AHEAD, py = tma_y;
-                        if (px >= x_end) { px -= nst * 16; py += 32; }
-                        if (py < bJ0 + nrb * 32) hv::tma_prefetch_box(tm, px, py);
-                    }
-#endif
                 }
                 --tma_left; is_s ^= 1;
                 tma_x += 16;

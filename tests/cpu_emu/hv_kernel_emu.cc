@@ -156,6 +156,8 @@ static inline void tma_load_box(uint32_t dst, const void* tmv, int x, int y, uin
 }
 static inline void tma_prefetch_box(const void*, int, int) {}
 template <class T> static inline T ldg(const T* p) { return *p; }
+static inline uint32_t ldg_volatile(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
+static inline uint32_t lds_u32(uint32_t a) { return ld<uint32_t>(a); }
 }  // namespace hv
 #define IFB_HV_DYNAMIC_SMEM(name_) unsigned char* const name_ = emu::smem
 

@@ -147,10 +147,10 @@ def test_plan_tables_build_on_the_host_for_any_geometry():
     # regression pins (cubic filters only: polynomial f64 arithmetic, no libm): the kernel tables of the benchmark geometries
     # as the build whose kernel source passes tests/test_hv_emulation.py lays them out (round 2: streaming H-then-V ring kernel).
     # A deliberate change of the table layout updates these constants.
-    pins = {((3840, 2160, 512, 512, 2),): (0xf4d8a615951a7014, 109968),
+    pins = {((3840, 2160, 512, 512, 2),): (0xf4276ae5577da3e2, 354480),
             ((7680, 4320, 1920, 1080, 2, 50.0),): (0x4d5a0cc2c88695c1, 224000),
             ((1920, 1080, 3840, 2160, 14),): (0xe0ce1caa7adbc55b, 0),            # up-scale: tile kernel, no ring tables
-            ((640, 480, 200, 150, 2), (33, 17, 7, 5, 2)): (0x3b22a853cc3abc85, 24881)}
+            ((640, 480, 200, 150, 2), (33, 17, 7, 5, 2)): (0x5175ec0383b3940b, 82835)}
     for geo, (h, nbytes) in pins.items():
         r = ifb.plan_probe(list(geo), threads=1, want_hash=True)
         assert (r["table_hash"], r["table_bytes"]) == (h, nbytes), geo
