@@ -442,8 +442,10 @@ def main():
     if rank == 0:
         sampler.mark()
     barrier()
+    torch.cuda.cudart().cudaProfilerStart()      # `ncu --profile-from-start off` then lists the launches of the timed region only
     e0, e1, k_ev, host_ms = w.timed(args.steps)
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = e0.elapsed_time(e1)
     step_ms = [a.elapsed_time(b) for a, b in k_ev]

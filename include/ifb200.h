@@ -194,9 +194,11 @@ void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */
 enum ifb200_option {
     IFB200_OPT_FORCE_GENERIC = 1,      /* 1: always use the two-kernel generic path (parity cross-check)  */
-    IFB200_OPT_STRIP_COLUMNS = 2,      /* ring kernel: widest strip of output columns one warp works on: 16, 32, 48 or 64 (default) */
-    IFB200_OPT_MIN_ITEMS = 3           /* ring kernel: split images into pairs of row bands until a launch has at least this many warp
-                                          work items (0 = as many as the device has warps, the default)    */
+    IFB200_OPT_STRIP_COLUMNS = 2,      /* ring kernel: widest strip of output columns one warp works on: a multiple of 16 up to 128
+                                          (default 64; clipped to what the kernel variant holds: 64, or 50 / 40 at ring depth 6) */
+    IFB200_OPT_MIN_ITEMS = 3           /* ring kernel: split images into row bands until a launch has at least this many warp work
+                                          items.  0 (default): as many as the device has warps, and launches that still cannot
+                                          fill the device get narrower strips; > 0: exactly the strip width asked for */
 };
 int      ifb200_batch_set_option(ifb200_batch* b, int option, int64_t value);
 uint64_t ifb200_batch_kernel_launches(const ifb200_batch* b);   /* total kernels launched so far   */

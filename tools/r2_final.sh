@@ -12,7 +12,7 @@ timeout 900 python bench.py > gpurun_out/${TAG}_bench_line.json 2>gpurun_out/${T
 timeout 900 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2>gpurun_out/${TAG}_bench_ref.err; note "bench reference rc=$? $(tail -c 400 gpurun_out/${TAG}_bench_ref.json)"
 timeout 600 python bench.py --ncu-traffic --no-cpu --no-e2e --no-others --steps 2 > gpurun_out/${TAG}_traffic.log 2>&1; note "traffic rc=$? $(cat profiles/traffic_c2_4k_to_512_robidoux.json | tr '\n' ' ' | head -c 400)"
 cp profiles/traffic_*.json gpurun_out/ 2>/dev/null
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-others --no-check > gpurun_out/${TAG}_launches.log 2>&1; note "launch list rc=$? $(wc -l < gpurun_out/${TAG}_launches.csv) lines"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-others --no-check > gpurun_out/${TAG}_launches.log 2>&1; note "launch list rc=$? $(wc -l < gpurun_out/${TAG}_launches.csv) lines"
 for tool in racecheck memcheck; do
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py -q -x -k "ring_kernel_forms or tile_kernel_bit_exact or fused_decompositions" > gpurun_out/${TAG}_sanitizer_$tool.log 2>&1; note "compute-sanitizer $tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|passed|failed' gpurun_out/${TAG}_sanitizer_$tool.log | tail -3 | tr '\n' ' ' | head -c 400)"
 done
