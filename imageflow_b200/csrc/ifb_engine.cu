@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <thread>
 #include <cmath>
 #include <cstdarg>
@@ -1125,13 +1126,66 @@ void detect_content_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint3
     if (!ifb::detect_content_from_codes(codes, w, h, rect, nullptr)) IFB_THROW(IFB200_ERR_INVALID_STATE, "whitespace walk failed");
 }
 
+// Pageable host bitmaps (imageflow's Bitmap buffers are plain Vecs, aligned_buffer.rs:40-43): cudaMemcpy2DAsync from pageable memory
+// is staged by the driver on the calling thread (about 10 GB/s, and it does not overlap).  The drop-in path therefore stages such
+// bitmaps itself: the rows are copied into a pinned buffer of the pipeline slot by a few host threads in parallel, the pinned buffer
+// goes to the GPU with one asynchronous copy; results come back into a pinned buffer and are copied out when the slot is reused.
+struct CopyPool {
+    struct Task { const uint8_t* src; uint8_t* dst; size_t sp, dp, row_bytes, r0, r1; };
+    std::vector<std::thread> th;
+    std::mutex m; std::condition_variable cv, cv_done;
+    std::vector<Task> q; size_t pending = 0; bool stop = false;
+    static void run(const Task& t) {
+        if (t.sp == t.row_bytes && t.dp == t.row_bytes) { memcpy(t.dst + t.r0 * t.dp, t.src + t.r0 * t.sp, (t.r1 - t.r0) * t.row_bytes); return; }
+        for (size_t r = t.r0; r < t.r1; ++r) memcpy(t.dst + r * t.dp, t.src + r * t.sp, t.row_bytes);
+    }
+    void start(int n) {
+        for (int i = 0; i < n; ++i)
+            th.emplace_back([this] {
+                for (;;) {
+                    Task t;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (stop && q.empty()) return;
+                        t = q.back(); q.pop_back();
+                    }
+                    run(t);
+                    { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_all(); }
+                }
+            });
+    }
+    // dst[r][0..row_bytes) = src[r][0..row_bytes) for r < rows, split over the pool's threads and the caller
+    void copy2d(uint8_t* dst, size_t dp, const uint8_t* src, size_t sp, size_t row_bytes, size_t rows) {
+        const size_t parts = std::min<size_t>(th.size() + 1, std::max<size_t>(1, rows * row_bytes >> 20));   // at least 1 MiB per part
+        if (parts <= 1) { run(Task{src, dst, sp, dp, row_bytes, 0, rows}); return; }
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t k = 1; k < parts; ++k) { q.push_back(Task{src, dst, sp, dp, row_bytes, rows * k / parts, rows * (k + 1) / parts}); ++pending; }
+        }
+        cv.notify_all();
+        run(Task{src, dst, sp, dp, row_bytes, 0, rows / parts});
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [this] { return pending == 0; });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
 struct HostSlot {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_cv = nullptr; size_t cap_in = 0, cap_cv = 0;
+    uint8_t *h_in = nullptr, *h_cv = nullptr; size_t hcap_in = 0, hcap_cv = 0;     // pinned staging (pageable bitmaps only)
+    cudaEvent_t up_done = nullptr;                                                   // the upload from h_in has completed
+    // a result waiting in h_cv for its copy to the caller's (pageable) canvas
+    uint8_t* out_dst = nullptr; size_t out_stride = 0, out_row_bytes = 0, out_rows = 0, out_pitch = 0;
 };
 struct HostCtx {
     ifb200_batch* batch = nullptr;
     HostSlot slot[kHostSlots];
+    std::unique_ptr<CopyPool> pool;
     ~HostCtx() {
         if (!batch) return;
         cudaSetDevice(batch->device);
@@ -1139,7 +1193,11 @@ struct HostCtx {
             if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_cv) cudaFree(s.d_cv);
+            if (s.h_in) cudaFreeHost(s.h_in);
+            if (s.h_cv) cudaFreeHost(s.h_cv);
+            if (s.up_done) cudaEventDestroy(s.up_done);
         }
+        pool.reset();
         delete batch;
     }
 };
@@ -1472,7 +1530,25 @@ int ifb200_batch_ring_status(const ifb200_batch* b, char* why, size_t cap) {
 
 // ---- drop-in calls with HOST buffers -----------------------------------------------------------
 namespace {
-// one host-buffer job on pipeline slot `sl` (asynchronous; caller synchronises the slot's stream)
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+void ensure_pinned(uint8_t*& p, size_t& cap, size_t need) {
+    if (cap >= need) return;
+    if (p) CUDA_OK(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    CUDA_OK(cudaMallocHost(&p, need));
+    cap = need;
+}
+// the result parked in the slot's pinned buffer (if any) goes to the caller's canvas; the slot's stream must have been synchronised
+void flush_result(HostCtx& c, HostSlot& sl) {
+    if (!sl.out_dst) return;
+    c.pool->copy2d(sl.out_dst, sl.out_stride, sl.h_cv, sl.out_pitch, sl.out_row_bytes, sl.out_rows);
+    sl.out_dst = nullptr;
+}
+// one host-buffer job on pipeline slot `sl` (asynchronous; caller synchronises the slot's stream and calls flush_result)
 void host_job_async(HostCtx& c, HostSlot& sl, const ifb200_resample_desc& d) {
     ifb200_batch* b = c.batch;
     cudaStream_t st = sl.stream;
@@ -1481,15 +1557,41 @@ void host_job_async(HostCtx& c, HostSlot& sl, const ifb200_resample_desc& d) {
     const size_t cv_pitch = ((size_t)d.w * 4 + 63) / 64 * 64;
     ensure(sl.d_in, sl.cap_in, in_pitch * d.in_h, st);
     ensure(sl.d_cv, sl.cap_cv, cv_pitch * d.h, st);
-    CUDA_OK(cudaMemcpy2DAsync(sl.d_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h, cudaMemcpyHostToDevice, st));
     uint8_t* host_rect = d.canvas + (size_t)d.y * d.cv_stride + (size_t)d.x * 4;
-    if (d.compose == IFB200_BLEND_WITH_SELF)        // the composite reads the canvas (scaling.rs:271-283)
-        CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h, cudaMemcpyHostToDevice, st));
+    const bool stage_in = is_pageable(d.in), stage_cv = is_pageable(host_rect);
+    if (stage_in || stage_cv) {
+        if (!c.pool) { c.pool.reset(new CopyPool()); c.pool->start((int)std::min(7u, std::max(1u, std::thread::hardware_concurrency() / 2u))); }
+        if (!sl.up_done) CUDA_OK(cudaEventCreateWithFlags(&sl.up_done, cudaEventDisableTiming));
+    }
+    if (sl.out_dst) { CUDA_OK(cudaStreamSynchronize(st)); flush_result(c, sl); }     // the slot's previous result leaves its pinned buffer
+    if (stage_in) {
+        if (sl.hcap_in < in_pitch * d.in_h) { CUDA_OK(cudaStreamSynchronize(st)); ensure_pinned(sl.h_in, sl.hcap_in, in_pitch * d.in_h); }
+        else CUDA_OK(cudaEventSynchronize(sl.up_done));                              // the previous upload from h_in is through
+        c.pool->copy2d(sl.h_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h);
+        CUDA_OK(cudaMemcpyAsync(sl.d_in, sl.h_in, in_pitch * d.in_h, cudaMemcpyHostToDevice, st));
+        CUDA_OK(cudaEventRecord(sl.up_done, st));
+    } else {
+        CUDA_OK(cudaMemcpy2DAsync(sl.d_in, in_pitch, d.in, d.in_stride, (size_t)d.in_w * 4, d.in_h, cudaMemcpyHostToDevice, st));
+    }
+    if (stage_cv && sl.hcap_cv < cv_pitch * d.h) { CUDA_OK(cudaStreamSynchronize(st)); ensure_pinned(sl.h_cv, sl.hcap_cv, cv_pitch * d.h); }
+    if (d.compose == IFB200_BLEND_WITH_SELF) {      // the composite reads the canvas (scaling.rs:271-283)
+        if (stage_cv) {
+            c.pool->copy2d(sl.h_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h);
+            CUDA_OK(cudaMemcpyAsync(sl.d_cv, sl.h_cv, cv_pitch * d.h, cudaMemcpyHostToDevice, st));
+        } else {
+            CUDA_OK(cudaMemcpy2DAsync(sl.d_cv, cv_pitch, host_rect, d.cv_stride, (size_t)d.w * 4, d.h, cudaMemcpyHostToDevice, st));
+        }
+    }
     ifb200_resample_desc dd = d;
     dd.in = sl.d_in; dd.in_stride = (uint32_t)in_pitch;
     dd.canvas = sl.d_cv; dd.cv_w = d.w; dd.cv_h = d.h; dd.cv_stride = (uint32_t)cv_pitch; dd.x = 0; dd.y = 0;
     enqueue_locked(b, &dd, 1, st);
-    CUDA_OK(cudaMemcpy2DAsync(host_rect, d.cv_stride, sl.d_cv, cv_pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, st));
+    if (stage_cv) {
+        CUDA_OK(cudaMemcpyAsync(sl.h_cv, sl.d_cv, cv_pitch * d.h, cudaMemcpyDeviceToHost, st));
+        sl.out_dst = host_rect; sl.out_stride = d.cv_stride; sl.out_row_bytes = (size_t)d.w * 4; sl.out_rows = d.h; sl.out_pitch = cv_pitch;
+    } else {
+        CUDA_OK(cudaMemcpy2DAsync(host_rect, d.cv_stride, sl.d_cv, cv_pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, st));
+    }
 }
 }  // namespace
 
@@ -1502,6 +1604,7 @@ int ifb200_scale_and_render(const ifb200_resample_desc* desc, char* err, size_t 
         DeviceScope dev_scope_(c.batch->device);
         host_job_async(c, c.slot[0], *desc);
         CUDA_OK(cudaStreamSynchronize(c.slot[0].stream));
+        flush_result(c, c.slot[0]);
     });
 }
 
@@ -1515,10 +1618,10 @@ int ifb200_scale_and_render_many(const ifb200_resample_desc* descs, size_t n, ch
         try {
             for (size_t i = 0; i < n; ++i) host_job_async(c, c.slot[i % kHostSlots], descs[i]);
         } catch (...) {
-            for (auto& sl : c.slot) cudaStreamSynchronize(sl.stream);
+            for (auto& sl : c.slot) { cudaStreamSynchronize(sl.stream); sl.out_dst = nullptr; }
             throw;
         }
-        for (auto& sl : c.slot) CUDA_OK(cudaStreamSynchronize(sl.stream));
+        for (auto& sl : c.slot) { CUDA_OK(cudaStreamSynchronize(sl.stream)); flush_result(c, sl); }
     });
 }
 
