@@ -198,7 +198,7 @@ void build_hv(Plan& p) {
     p.hv_ok = true;
 }
 
-// tile kernel: 64 x 16 output pixels per CTA; usable when the source extent of every tile fits in shared memory
+// tile kernel: 64 x 32 output pixels per CTA at a time (kTile2W x kTile2H); usable when the source extent of every tile fits in shared memory
 void build_tile(Plan& p) {
     if (!monotone(p.wv) || !monotone(p.wh)) return;
     TilePlanDev t{};
@@ -1093,6 +1093,25 @@ void white_balance_locked(ifb200_batch* b, uint8_t* px, uint32_t w, uint32_t h, 
     b->launches += 3;
 }
 
+// The per-pixel code map of detect_content (layout: ifb_whitespace.h) of a DEVICE bitmap into a DEVICE buffer of w*h bytes; asynchronous.
+void whitespace_codes_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                             uint32_t threshold, uint8_t* dcodes, cudaStream_t st) {
+    if (!px || !dcodes) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null pointer");
+    if (w == 0 || h == 0 || w > 0x7fffffffu || h > 0x7fffffffu) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "empty or oversized bitmap");
+    if (stride < w * 4ull || (stride & 3)) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "stride smaller than a BGRA row or not a multiple of 4");
+    if (threshold > 0x7fffffffu) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "threshold out of range");
+    // grid.y is bounded: tall bitmaps go in chunks of rows (a chunk's first and last rows look one row up / down: the kernel
+    // takes the whole bitmap and the chunk's first row)
+    const uint32_t rows_per_launch = 65535u * 8u;
+    for (uint32_t y0 = 0; y0 < h; y0 += rows_per_launch) {
+        const uint32_t rows = std::min(rows_per_launch, h - y0);
+        dim3 grid((w + 31) / 32, (rows + 7) / 8);
+        whitespace_codes_kernel<<<grid, dim3(32, 8), 0, st>>>(px, w, h, stride, alpha_meaningful ? 1u : 0u, (int)threshold, dcodes, y0);
+        CUDA_OK(cudaGetLastError());
+        b->launches++;
+    }
+}
+
 // detect_content (graphics/whitespace.rs:284-331) on a DEVICE bitmap: the per-pixel code map on the GPU, one byte per pixel
 // back to the host, the reference's window walk over it there.  Returns a rectangle, so it synchronises `st`.
 void detect_content_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
@@ -1110,16 +1129,7 @@ void detect_content_locked(ifb200_batch* b, const uint8_t* px, uint32_t w, uint3
     uint8_t* dcodes = nullptr;
     CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&dcodes), n, st));
     AsyncFree dcodes_guard{dcodes, st};
-    // grid.y is bounded: tall bitmaps go in chunks of rows (a chunk's first and last rows look one row up / down: the kernel
-    // takes the whole bitmap and the chunk's first row)
-    const uint32_t rows_per_launch = 65535u * 8u;
-    for (uint32_t y0 = 0; y0 < h; y0 += rows_per_launch) {
-        const uint32_t rows = std::min(rows_per_launch, h - y0);
-        dim3 grid((w + 31) / 32, (rows + 7) / 8);
-        whitespace_codes_kernel<<<grid, dim3(32, 8), 0, st>>>(px, w, h, stride, alpha_meaningful ? 1u : 0u, (int)threshold, dcodes, y0);
-        CUDA_OK(cudaGetLastError());
-        b->launches++;
-    }
+    whitespace_codes_locked(b, px, w, h, stride, alpha_meaningful, threshold, dcodes, st);
     CUDA_OK(cudaMemcpyAsync(codes, dcodes, n, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaEventRecord(ev, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -1681,6 +1691,17 @@ int ifb200_batch_detect_content(ifb200_batch* b, const uint8_t* dev_px, uint32_t
         std::lock_guard<std::mutex> lk(b->mu);
         detect_content_locked(b, dev_px, w, h, stride, alpha_meaningful, threshold,
                               stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream), rect);
+    });
+}
+
+int ifb200_batch_whitespace_codes(ifb200_batch* b, const uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                                  uint32_t threshold, uint8_t* dev_codes, void* stream, char* err, size_t cap) {
+    return guarded(err, cap, [&] {
+        if (!b) IFB_THROW(IFB200_ERR_INVALID_ARGUMENT, "null batch");
+        std::lock_guard<std::mutex> lk(b->mu);
+        DeviceScope dev_scope_(b->device);
+        whitespace_codes_locked(b, dev_px, w, h, stride, alpha_meaningful, threshold, dev_codes,
+                                stream == IFB200_STREAM_OWN ? b->own_stream : static_cast<cudaStream_t>(stream));
     });
 }
 

@@ -363,6 +363,13 @@ class Batch:
                                                  int(threshold), rect, self._stream(stream), buf, 512), buf)
         return tuple(rect)
 
+    def whitespace_codes(self, bitmap: BitmapWindow, dev_codes_ptr: int, threshold: int = 1, stream=None) -> None:
+        """the GPU half of detect_content alone (graphics/whitespace.rs:426-613 per pixel): code map of a DEVICE bitmap into a
+        DEVICE buffer of w*h bytes; asynchronous on `stream`."""
+        buf = C.create_string_buffer(512)
+        _check(lib().ifb200_batch_whitespace_codes(self._h, bitmap.ptr, bitmap.w, bitmap.h, bitmap.stride, int(bool(bitmap.alpha_meaningful)),
+                                                   int(threshold), dev_codes_ptr, self._stream(stream), buf, 512), buf)
+
     def flip_vertical(self, bitmap: BitmapWindow, stream=None) -> None:
         """graphics/flip.rs:10-22 on a DEVICE bitmap, in place."""
         buf = C.create_string_buffer(512)

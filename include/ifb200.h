@@ -189,6 +189,11 @@ int  ifb200_batch_white_balance(ifb200_batch* b, uint8_t* dev_px, uint32_t w, ui
  * alpha_meaningful selects the Bgra32 (1) or Bgr32 (0) grayscale.  Synchronous (a rectangle comes back). */
 int  ifb200_batch_detect_content(ifb200_batch* b, const uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
                                  uint32_t threshold, uint32_t rect[4], void* cuda_stream, char* err, size_t err_cap);
+/* The GPU half of detect_content alone: the one-byte-per-pixel code map (layout: imageflow_b200/csrc/ifb_whitespace.h; what
+ * sobel_scharr_detect :525-613 derives per 3x3 neighbourhood) of a DEVICE bitmap into a DEVICE buffer of w*h bytes, row pitch w.
+ * Asynchronous on `cuda_stream`; ifb200_detect_content_from_codes() walks a host copy of it. */
+int  ifb200_batch_whitespace_codes(ifb200_batch* b, const uint8_t* dev_px, uint32_t w, uint32_t h, uint32_t stride, int alpha_meaningful,
+                                   uint32_t threshold, uint8_t* dev_codes, void* cuda_stream, char* err, size_t err_cap);
 int  ifb200_batch_sync(ifb200_batch* b, char* err, size_t err_cap);
 void ifb200_batch_destroy(ifb200_batch* b);
 /* knobs / introspection (benchmarks, tests) */

@@ -41,10 +41,11 @@ def run_tile2(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=14, lin
     h = canvas.shape[0] - y if h is None else h
     wv, wh = ifb.populate_weights(filter, h, ih), ifb.populate_weights(filter, w, iw)
     vl, vr, vo, vw = csr(wv); hl, hr, ho, hw = csr(wh)
-    tiles_x, tiles_y = (w + 63) // 64, (h + 15) // 16
+    th = L.emu_tile2_tile_h()
+    tiles_x, tiles_y = (w + 63) // 64, (h + th - 1) // th
     max_ic = max(int(hr[min(tx * 64 + 64, w) - 1]) - int(hl[tx * 64]) + 1 for tx in range(tiles_x))
-    max_ir = max(int(vr[min(ty * 16 + 16, h) - 1]) - int(vl[ty * 16]) + 1 for ty in range(tiles_y))
-    plan = np.array([iw, ih, w, h, 64, 16, tiles_x, tiles_y, max_ic, max_ir], np.int32)
+    max_ir = max(int(vr[min(ty * th + th, h) - 1]) - int(vl[ty * th]) + 1 for ty in range(tiles_y))
+    plan = np.array([iw, ih, w, h, 64, th, tiles_x, tiles_y, max_ic, max_ir], np.int32)
     t_lin, t_srgb, lut = (np.zeros(256, np.float32), np.zeros(256, np.float32), np.zeros(16384, np.uint8))
     f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
     ifb.lib().ifb200_byte_to_float_table(1, t_lin.ctypes.data_as(f32p)); ifb.lib().ifb200_byte_to_float_table(0, t_srgb.ctypes.data_as(f32p))
@@ -86,6 +87,7 @@ def run_tile2(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=14, lin
 def load_tile2(so):
     L = C.CDLL(so)
     L.emu_tile2_sizeof_jobdev.restype = u32
+    L.emu_tile2_tile_h.restype = C.c_int
     L.emu_tile2_launch.restype = C.c_int
     L.emu_tile2_launch.argtypes = [C.c_int] * 4 + [C.c_uint, C.c_void_p, u32] + [C.c_void_p] * 11 + [C.c_void_p]
     return L

@@ -40,6 +40,17 @@ using std::min;
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct alignas(8) float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)}; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = ((uint64_t)y << 32) | x; uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
@@ -71,7 +82,7 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
 namespace ifbk {
 #include "../../imageflow_b200/csrc/ifb_types.cuh"
 #ifndef IFB_TILE2_MINB
-#define IFB_TILE2_MINB 5
+#define IFB_TILE2_MINB 4
 #endif
 #include "../../imageflow_b200/csrc/ifb_tile2_kernel.cuh"
 }  // namespace ifbk
@@ -88,6 +99,7 @@ static KernelFn pick(int ch, int linear, int compose, int cm) {
 }
 
 extern "C" uint32_t emu_tile2_smem_bytes(int max_ir, int max_ic, int linear) { return Tile2Smem::make(max_ir, max_ic, linear != 0).total; }
+extern "C" int emu_tile2_tile_h(void) { return kTile2H; }
 extern "C" uint32_t emu_tile2_sizeof_jobdev(void) { return (uint32_t)sizeof(JobDev); }
 
 // one launch of fused_tile2_kernel<ch, linear, compose, cm> with `grid` blocks of 256 threads

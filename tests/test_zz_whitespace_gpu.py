@@ -30,4 +30,9 @@ def test_detect_content_matches_oracle():
         v.copy_(torch.from_numpy(a))
         got = b.detect_content(ifb.BitmapWindow.from_torch(v, alpha_meaningful=am), thr, stream=torch.cuda.current_stream().cuda_stream)
         assert got == want, ("device", a.shape, thr, am)
+        if h >= 3 and w >= 3:       # the code map itself, byte for byte (the reference returns early below 3x3: no map)
+            dc = torch.empty((h, w), dtype=torch.uint8, device="cuda")
+            b.whitespace_codes(ifb.BitmapWindow.from_torch(v, alpha_meaningful=am), dc.data_ptr(), thr, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert np.array_equal(dc.cpu().numpy(), oracle.whitespace_codes(a, thr, am)), ("codes", a.shape, thr, am)
     b.close()

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Measurement of the SURVEY.md section 8(f) neighbours of the resample path that are built: transpose, flips and white balance
+"""Measurement of the SURVEY.md section 8(f) neighbours of the resample path that are built: transpose, flips, white balance and detect_content
 (the reference benchmarks transposes at 4K / 8K in benches/bench_graphics.rs:9-62).  Inputs resident in HBM, CUDA events on
 the launching stream, >= 3 warm-up calls; a set of 64 different images per size (>= 2 GB, far larger than L2) is cycled so that
 no call finds its data in cache.  One JSON line per (operation, size) with the HBM roofline of the kernel: algorithmic
@@ -73,7 +73,47 @@ def main():
                               "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s", "frac": alg / ms / 1e6 / pk,
                                            "peak_source": src, "algorithmic_bytes_per_launch": alg},
                               "cpu_oracle_ms_1_thread": cpu_ms, "bit_exact_vs_oracle": ok, "images_cycled": n}))
-        del imgs, outs
+        # detect_content (graphics/whitespace.rs:284-331): the code kernel (4 B read + 1 B written per pixel) timed alone with CUDA
+        # events, the whole call (kernel + 1 B/px device->host + the reference's window walk on the host) by wall clock, the host
+        # walk alone over the same map, and the oracle's scalar loop.  Content: a noisy rectangle on a white page (the trim case).
+        page = np.full((h, w, 4), 255, np.uint8)
+        page[h // 8: h - h // 6, w // 10: w - w // 7] = host[h // 8: h - h // 6, w // 10: w - w // 7]
+        for i in range(n):
+            imgs[i].copy_(torch.from_numpy(page))
+            imgs[i, :, :, 0].add_(i & 1)                      # cycled images are not identical (white wraps to 0 on odd ones)
+        codes = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        wfn = lambda i: batch.whitespace_codes(ifb.BitmapWindow.from_torch(imgs[i]), codes[i].data_ptr(), 1, stream)
+        for i in range(n):
+            wfn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            for i in range(n):
+                wfn(i)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (3 * n)
+        batch.detect_content(ifb.BitmapWindow.from_torch(imgs[0]), 1, stream)
+        t0 = time.perf_counter()
+        for i in range(8):
+            rect = batch.detect_content(ifb.BitmapWindow.from_torch(imgs[2 * i]), 1, stream)
+        call_ms = (time.perf_counter() - t0) * 1e3 / 8
+        hc = codes[0].cpu().numpy()
+        t0 = time.perf_counter()
+        for _ in range(8):
+            rect_w, visited = ifb.detect_content_from_codes(hc)
+        walk_ms = (time.perf_counter() - t0) * 1e3 / 8
+        t0 = time.perf_counter()
+        want, _ = oracle.detect_content(imgs[0].cpu().numpy(), 1, True)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        alg = w * h * 5
+        print(json.dumps({"op": "detect_content", "size": f"{w}x{h}", "code_kernel_ms_per_image": ms, "mpx_per_s_kernel": w * h / ms / 1e3,
+                          "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk, "unit": "GB/s", "frac": alg / ms / 1e6 / pk,
+                                       "peak_source": src, "algorithmic_bytes_per_launch": alg},
+                          "whole_call_ms": call_ms, "host_walk_ms": walk_ms, "host_walk_pixels_visited": visited,
+                          "cpu_oracle_ms_1_thread": cpu_ms, "rect": list(rect), "bit_exact_vs_oracle": bool(tuple(rect) == tuple(want) == tuple(rect_w)),
+                          "images_cycled": n}))
+        del imgs, outs, codes
         torch.cuda.empty_cache()
 
 
