@@ -166,6 +166,9 @@ struct Plan {
     AxisOnDev dv, dh; std::unique_ptr<DevBlob> axes;   // CSR windows on the device: only the tile kernel and the generic pair read them
     // tile kernel (small windows: up-scales, 1:1, mild down-scales)
     bool tile_ok = false; TilePlanDev tile{};
+    // per output row: its V window padded with zeros to the six source rows of its quad; per quad: first of those rows + 1 (0 = the
+    // quad does not fit); per output column: the H window padded to four taps (ifb_tile2_kernel.cuh)
+    std::vector<float> tile_vw, tile_hw; std::vector<uint32_t> tile_vq; size_t o_tile_vw = 0, o_tile_vq = 0, o_tile_hw = 0;
     // ring kernel
     bool hv_ok = false; std::string hv_reason;
     int av = 0;                          // ring depth of the kernel variant: 4 or 6 (both axes)
@@ -214,6 +217,28 @@ void build_tile(Plan& p) {
         t.max_ir = std::max<int>(t.max_ir, (int)(p.wv.right[Y1 - 1] - p.wv.left[Y0] + 1));
     }
     if (Tile2Smem::make(t.max_ir, t.max_ic, true).total > 96u * 1024u) return;   // large windows: the ring kernel or the generic pair
+    // tables of the register forms (kernel header): everything that depends only on the plan is prepared here
+    const int rows_pad = t.tiles_y * kTile2H;
+    p.tile_vw.assign((size_t)rows_pad * 8, 0.0f);
+    p.tile_vq.assign((size_t)rows_pad / 4, 0u);
+    for (int ty = 0; ty < t.tiles_y; ++ty) {
+        const uint32_t Y0 = ty * t.toh, Y1 = std::min<uint32_t>(Y0 + t.toh, p.out_h);
+        const uint32_t r0 = p.wv.left[Y0], r1 = p.wv.right[Y1 - 1];
+        for (uint32_t yq = Y0; yq < Y1; yq += 4) {
+            const uint32_t b0 = std::min(p.wv.left[yq], std::max(r1 - std::min<uint32_t>(r1, kTile2Span - 1), r0));
+            bool fit = r1 - r0 + 1 >= (uint32_t)kTile2Span;
+            for (uint32_t y = yq; y < std::min(yq + 4, Y1); ++y) fit = fit && p.wv.left[y] >= b0 && p.wv.right[y] < b0 + kTile2Span;
+            p.tile_vq[yq / 4] = fit ? b0 + 1 : 0u;
+            if (!fit) continue;
+            for (uint32_t y = yq; y < std::min(yq + 4, Y1); ++y)
+                for (uint32_t j = p.wv.left[y]; j <= p.wv.right[y]; ++j) p.tile_vw[(size_t)y * 8 + (j - b0)] = p.wv.w[p.wv.offset[y] + (j - p.wv.left[y])];
+        }
+    }
+    t.h4 = p.wh.max_taps <= 4 ? 1 : 0;
+    p.tile_hw.assign(t.h4 ? (size_t)t.tiles_x * kTile2W * 4 : 4, 0.0f);
+    if (t.h4)
+        for (uint32_t x = 0; x < p.out_w; ++x)
+            for (uint32_t j = p.wh.left[x]; j <= p.wh.right[x]; ++j) p.tile_hw[(size_t)x * 4 + (j - p.wh.left[x])] = p.wh.w[p.wh.offset[x] + (j - p.wh.left[x])];
     p.tile = t; p.tile_ok = true;
 }
 
@@ -661,11 +686,15 @@ void ifb200_batch::commit_many(cudaStream_t st, const std::vector<DevBlob*>& blo
 namespace {
 
 // CSR windows on the device (tile kernel and generic pair only)
-void ensure_axes(ifb200_batch* b, cudaStream_t st, Plan& p) {
-    if (p.axes) { p.axes->use_on(st); return; }
+void make_axes_blob(Plan& p) {
     p.axes = std::make_unique<DevBlob>();
     p.dv.add_to(*p.axes, p.wv);
     p.dh.add_to(*p.axes, p.wh);
+    if (p.tile_ok) { p.o_tile_vw = p.axes->add(p.tile_vw); p.o_tile_vq = p.axes->add(p.tile_vq); p.o_tile_hw = p.axes->add(p.tile_hw); }
+}
+void ensure_axes(ifb200_batch* b, cudaStream_t st, Plan& p) {
+    if (p.axes) { p.axes->use_on(st); return; }
+    make_axes_blob(p);
     p.axes->commit(b, st);
 }
 
@@ -813,7 +842,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             if (g.kind == 1) {
                 bl = &p.by_cols.at(g.cols_key)->blob;
             } else {
-                if (!p.axes) { p.axes = std::make_unique<DevBlob>(); p.dv.add_to(*p.axes, p.wv); p.dh.add_to(*p.axes, p.wh); }
+                if (!p.axes) make_axes_blob(p);
                 bl = p.axes.get();
             }
             if (!bl->p && !bl->host.empty() && seen.insert(bl).second) cold.push_back(bl);
@@ -901,6 +930,8 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             // tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the (job, tile) list
             const TilePlanDev& t = p.tile;
             ensure_axes(b, st, p);
+            TilePlanDev tv = t;
+            tv.vw = p.axes->at<float>(p.o_tile_vw); tv.vq = p.axes->at<uint32_t>(p.o_tile_vq); tv.hw = p.axes->at<float>(p.o_tile_hw);
             const bool linear = g.variant & 1;
             Tile2Fn fn = find_tile2(g.ch, linear, (g.variant >> 1) & 3, (g.variant & 8) != 0);
             const size_t smem = Tile2Smem::make(t.max_ir, t.max_ic, linear).total;
@@ -914,7 +945,7 @@ void enqueue_locked(ifb200_batch* b, const ifb200_resample_desc* descs, size_t n
             for (size_t off = 0; off < nj; off += 65535) {
                 const size_t cnt = std::min<size_t>(65535, nj - off);
                 const uint64_t total = (uint64_t)cnt * t.tiles_x * t.tiles_y;
-                fn<<<(unsigned)std::min<uint64_t>(total, resident), 256, smem, st>>>(jobs + off, (uint32_t)cnt, b->tables, p.dv.view(*p.axes), p.dh.view(*p.axes), t);
+                fn<<<(unsigned)std::min<uint64_t>(total, resident), 256, smem, st>>>(jobs + off, (uint32_t)cnt, b->tables, p.dv.view(*p.axes), p.dh.view(*p.axes), tv);
                 CUDA_OK(cudaGetLastError());
                 b->launches++;
             }

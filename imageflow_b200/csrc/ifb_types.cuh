@@ -38,4 +38,8 @@ struct TilePlanDev {
     int tow, toh;               // tile size in output pixels
     int tiles_x, tiles_y;
     int max_ic, max_ir;         // largest source extent of any tile (shared-memory tile dimensions)
+    int h4;                     // every H window has at most four taps: hw holds them padded to four per output column
+    const float* vw;            // [tiles_y * toh][8]: V window of an output row padded with zeros to the six source rows of its quad
+    const uint32_t* vq;         // [tiles_y * toh / 4]: first of the quad's six source rows + 1, or 0 if its windows do not fit
+    const float* hw;            // [tiles_x * tow][4] (h4 only)
 };

@@ -45,7 +45,28 @@ def run_tile2(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=14, lin
     tiles_x, tiles_y = (w + 63) // 64, (h + th - 1) // th
     max_ic = max(int(hr[min(tx * 64 + 64, w) - 1]) - int(hl[tx * 64]) + 1 for tx in range(tiles_x))
     max_ir = max(int(vr[min(ty * th + th, h) - 1]) - int(vl[ty * th]) + 1 for ty in range(tiles_y))
-    plan = np.array([iw, ih, w, h, 64, th, tiles_x, tiles_y, max_ic, max_ir], np.int32)
+    # the padded windows of the register forms, as build_tile() lays them out (ifb_engine.cu)
+    span = 6
+    t_vw = np.zeros((tiles_y * th, 8), np.float32); t_vq = np.zeros(tiles_y * th // 4, np.uint32)
+    for ty in range(tiles_y):
+        ya, yb = ty * th, min(ty * th + th, h)
+        r0, r1 = int(vl[ya]), int(vr[yb - 1])
+        for yq in range(ya, yb, 4):
+            b0 = min(int(vl[yq]), max(r1 - min(r1, span - 1), r0))
+            rows = range(yq, min(yq + 4, yb))
+            fit = r1 - r0 + 1 >= span and all(int(vl[yy]) >= b0 and int(vr[yy]) < b0 + span for yy in rows)
+            t_vq[yq // 4] = b0 + 1 if fit else 0
+            if fit:
+                for yy in rows:
+                    for j in range(int(vl[yy]), int(vr[yy]) + 1):
+                        t_vw[yy, j - b0] = vw[int(vo[yy]) + j - int(vl[yy])]
+    h4 = int(max(int(r) - int(l) + 1 for l, r in zip(hl, hr)) <= 4)
+    t_hw = np.zeros((tiles_x * 64, 4), np.float32)
+    if h4:
+        for xx in range(w):
+            for j in range(int(hl[xx]), int(hr[xx]) + 1):
+                t_hw[xx, j - int(hl[xx])] = hw[int(ho[xx]) + j - int(hl[xx])]
+    plan = np.array([iw, ih, w, h, 64, th, tiles_x, tiles_y, max_ic, max_ir, h4], np.int32)
     t_lin, t_srgb, lut = (np.zeros(256, np.float32), np.zeros(256, np.float32), np.zeros(16384, np.uint8))
     f32p, u8p = C.POINTER(C.c_float), C.POINTER(C.c_uint8)
     ifb.lib().ifb200_byte_to_float_table(1, t_lin.ctypes.data_as(f32p)); ifb.lib().ifb200_byte_to_float_table(0, t_srgb.ctypes.data_as(f32p))
@@ -79,7 +100,7 @@ def run_tile2(lib, ifb, inp, canvas, *, x=0, y=0, w=None, h=None, filter=14, lin
     rc = L.emu_tile2_launch(ch, int(linear), compose, int(color_matrix is not None), grid, C.cast(jobs, C.c_void_p), jobs_repeat,
                             p(t_lin, C.c_float), p(t_srgb, C.c_float), p(lut, C.c_uint8),
                             p(vl, u32), p(vr, u32), p(vo, u32), p(vw, C.c_float), p(hl, u32), p(hr, u32), p(ho, u32), p(hw, C.c_float),
-                            p(plan, C.c_int32))
+                            p(plan, C.c_int32), p(t_vw, C.c_float), p(t_vq, u32), p(t_hw, C.c_float))
     assert rc == 0
     return outs
 
@@ -89,7 +110,7 @@ def load_tile2(so):
     L.emu_tile2_sizeof_jobdev.restype = u32
     L.emu_tile2_tile_h.restype = C.c_int
     L.emu_tile2_launch.restype = C.c_int
-    L.emu_tile2_launch.argtypes = [C.c_int] * 4 + [C.c_uint, C.c_void_p, u32] + [C.c_void_p] * 11 + [C.c_void_p]
+    L.emu_tile2_launch.argtypes = [C.c_int] * 4 + [C.c_uint, C.c_void_p, u32] + [C.c_void_p] * 11 + [C.c_void_p] * 4
     return L
 
 

@@ -107,12 +107,13 @@ extern "C" int emu_tile2_launch(int ch, int linear, int compose, int cm, unsigne
                                 const float* t_lin, const float* t_srgb, const uint8_t* lut16k,
                                 const uint32_t* v_left, const uint32_t* v_right, const uint32_t* v_off, const float* v_w,
                                 const uint32_t* h_left, const uint32_t* h_right, const uint32_t* h_off, const float* h_w,
-                                const int32_t* plan10) {
+                                const int32_t* plan10, const float* tile_vw, const uint32_t* tile_vq, const float* tile_hw) {
     KernelFn fn = pick(ch, linear, ch == 4 ? compose : 0, cm);
     if (!fn) return 1;
     TilePlanDev pl{};
     pl.in_w = (uint32_t)plan10[0]; pl.in_h = (uint32_t)plan10[1]; pl.out_w = (uint32_t)plan10[2]; pl.out_h = (uint32_t)plan10[3];
     pl.tow = plan10[4]; pl.toh = plan10[5]; pl.tiles_x = plan10[6]; pl.tiles_y = plan10[7]; pl.max_ic = plan10[8]; pl.max_ir = plan10[9];
+    pl.h4 = plan10[10]; pl.vw = tile_vw; pl.vq = tile_vq; pl.hw = tile_hw;
     const Tables tb{t_lin, t_srgb, lut16k};
     const AxisDev av{v_left, v_right, v_off, v_w}, ah{h_left, h_right, h_off, h_w};
     const size_t smem_bytes = Tile2Smem::make(pl.max_ir, pl.max_ic, linear != 0).total;
