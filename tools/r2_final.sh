@@ -11,6 +11,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TA
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_line.json 2>gpurun_out/${TAG}_bench_line.err; note "bench rc=$? $(python tools/kms.py gpurun_out/${TAG}_bench_line.json)"
 timeout 900 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2>gpurun_out/${TAG}_bench_ref.err; note "bench reference rc=$? $(tail -c 400 gpurun_out/${TAG}_bench_ref.json)"
 timeout 600 python bench.py --ncu-traffic --no-cpu --no-e2e --no-others --steps 2 > gpurun_out/${TAG}_traffic.log 2>&1; note "traffic rc=$? $(cat profiles/traffic_c2_4k_to_512_robidoux.json | tr '\n' ' ' | head -c 400)"
+for w in c4_1080p_to_4k_mitchell_sepia_over c2_4k_to_512_lanczos3 c3_8k_to_1080p_robidoux_sharpen; do
+  timeout 300 python bench.py --ncu-traffic --workload $w --no-cpu --no-e2e --no-others --steps 2 > gpurun_out/${TAG}_traffic_$w.log 2>&1; note "traffic $w rc=$? $(cat profiles/traffic_$w.json | tr '\n' ' ' | head -c 300)"
+done
 cp profiles/traffic_*.json gpurun_out/ 2>/dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e --no-others --no-check > gpurun_out/${TAG}_launches.log 2>&1; note "launch list rc=$? $(wc -l < gpurun_out/${TAG}_launches.csv) lines"
 for tool in racecheck memcheck; do
