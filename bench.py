@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true")
-    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE.json configurations")
+    ap.add_argument("--no-others", action="store_true", help="skip the runs of the other BASELINE.json configurations")
     ap.add_argument("--ncu-traffic", action="store_true", help="measure the kernel's DRAM traffic with ncu and rewrite profiles/traffic_<workload>.json")
     ap.add_argument("--strip-cols", type=int, default=0, help="ring kernel: widest strip of output columns per warp (0 = library default)")
     ap.add_argument("--min-items", type=int, default=-1, help="ring kernel: band split target (-1 = library default)")
@@ -349,6 +349,7 @@ class DeviceWorkload:
 
     def close(self):
         self.batch.close()
+        self.descs = self.keep = None
         del self.inp, self.out, self.canvas0
         self.torch.cuda.empty_cache()
 
@@ -535,12 +536,12 @@ def main():
         v_pageable, _ = e2e_leg(False)
         e2e["pageable"] = {"value": v_pageable, "unit": "Mpx/s", "host_memory": "pageable (what Bitmap buffers are: aligned_buffer.rs:40-43)"}
 
-    # ---- the other configurations of BASELINE.json, short batches on the same GPU (rank 0 of a 1-GPU run): driver-visible numbers
+    # ---- the other configurations of BASELINE.json at their own batch sizes on the same GPU (rank 0 of a 1-GPU run): driver-visible numbers
     others = None
     if rank == 0 and world == 1 and not args.no_others and args.workload == DEFAULT_WORKLOAD:
         others = {}
         w.close()
-        for name, nb in (("c2_4k_to_512_lanczos3", 256), ("c3_8k_to_1080p_robidoux_sharpen", 64), ("c4_1080p_to_4k_mitchell_sepia_over", 128)):
+        for name, nb in (("c2_4k_to_512_lanczos3", 0), ("c3_8k_to_1080p_robidoux_sharpen", 0), ("c4_1080p_to_4k_mitchell_sepia_over", 0)):   # 0: the configuration's own batch
             try:
                 ow_ = DeviceWorkload(args, name, local, batch_override=nb)
                 ow_.warm(3, seconds=0.3)
