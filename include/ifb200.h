@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define IFB200_ABI_VERSION_MAJOR 1
-#define IFB200_ABI_VERSION_MINOR 1
+#define IFB200_ABI_VERSION_MINOR 2
 
 /* Error codes.  1..3 map onto the imageflow ErrorKind values raised by scale_and_render
  * (scaling.rs:24-48,145,191,202,240); 10..12 onto WeightsError (weights.rs:494-504). */

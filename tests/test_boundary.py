@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (ifb200_[a-z0-9_]+)", out))
     assert exported == set(declared)
-    assert L.ifb200_abi_version() == (1 << 16) | 1
+    assert L.ifb200_abi_version() == (1 << 16) | 2
 
 
 def test_desc_struct_layout_matches_header():
