@@ -2,9 +2,10 @@
  * (imageflow_b200/csrc/ifb_tile2_kernel.cuh, t2_div3): three numerators share one divisor d,
  *     y = RN(1 / d);  q0 = RN(x * y);  q = RN(q0 + RN_exact(x - d * q0) * y)         (two fused multiply-adds)
  * against the IEEE quotient RN(x / d) that the reference computes (scaling.rs:254-287).  Guards replicated from the kernel:
- * d a positive normal in [2^-31, 2^33) whose significand is not all ones, every numerator 0 or 2^-100 <= |x| (bounded above
- * by construction: sums of bytes times filter weights).  Operands outside the guards take the library division in the kernel
- * and are not tested here.  Trials: uniformly random bit patterns inside the guards, and "hard" cases built next to rounding
+ * d a positive normal in [2^-31, 2^33) whose significand is not all ones (other divisors take the library division in the
+ * kernel).  Numerators are tested from 2^-100 up (bounded above by construction: sums of bytes times filter weights); below
+ * that the residual x - d * q0 may be inexact, the kernel does not test for it, and does not need to: the quotient is then
+ * below 2^-69 on either path and every encoding (x 16383 or x 255, truncated) sends it to the same byte as 0.  Trials: uniformly random bit patterns inside the guards, and "hard" cases built next to rounding
  * midpoints of the quotient (x = RN((q + ulp/2) * d) and its two neighbours).  Build: gcc -O2 -ffp-contract=off -o crs
  * tools/check_shared_reciprocal.c -lm ; run: ./crs [millions of trials per class, default 200].  Prints the mismatch count. */
 #include <math.h>
