@@ -16,7 +16,7 @@ SYMBOLS = [
     "ifb200_transpose_bgra8", "ifb200_flip_vertical_bgra8", "ifb200_flip_horizontal_bgra8",
     "ifb200_batch_transpose", "ifb200_batch_flip_vertical", "ifb200_batch_flip_horizontal",
     "ifb200_white_balance_srgb_bgra8", "ifb200_batch_white_balance",
-    "ifb200_detect_content_bgra8", "ifb200_batch_detect_content", "ifb200_detect_content_from_codes", "ifb200_batch_whitespace_codes",
+    "ifb200_detect_content_bgra8", "ifb200_batch_detect_content", "ifb200_detect_content_from_codes", "ifb200_batch_whitespace_codes", "ifb200_set_dropin_device",
     "ifb200_batch_create", "ifb200_batch_enqueue", "ifb200_batch_color_matrix", "ifb200_batch_sync",
     "ifb200_batch_destroy", "ifb200_batch_set_option", "ifb200_batch_kernel_launches", "ifb200_batch_host_profile",
     "ifb200_batch_fused_jobs", "ifb200_batch_generic_jobs", "ifb200_batch_tile_jobs", "ifb200_batch_ring_status", "ifb200_hv_plan_tables",

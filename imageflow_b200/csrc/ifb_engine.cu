@@ -1301,23 +1301,28 @@ ifb200_batch* create_batch(int device) {
     return b.release();
 }
 
+std::atomic<int> g_dropin_device{-1};             // ifb200_set_dropin_device(); -1: IFB200_DEVICE, else device 0
+
 HostCtx& host_ctx() {
     if (!t_ctx.batch) {
-        int dev = 0;
-        if (const char* s = getenv("IFB200_DEVICE")) dev = atoi(s);
+        int dev = g_dropin_device.load();
+        if (dev < 0) { dev = 0; if (const char* s = getenv("IFB200_DEVICE")) dev = atoi(s); }
         t_ctx.batch = create_batch(dev);
         for (auto& sl : t_ctx.slot) CUDA_OK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     }
     return t_ctx;
 }
 
+// Staging buffers of the drop-in path grow geometrically (a stream of mixed sizes reallocates O(log) times, not at every new maximum)
+size_t grown(size_t cap, size_t need) { return std::max(need, cap + cap / 2); }
 void ensure(uint8_t*& p, size_t& cap, size_t need, cudaStream_t st) {
     if (cap >= need) return;
+    const size_t want = grown(cap, need);
     CUDA_OK(cudaStreamSynchronize(st));           // nothing may still be using the old buffer
     if (p) CUDA_OK(cudaFree(p));
     p = nullptr; cap = 0;
-    CUDA_OK(cudaMalloc(&p, need));
-    cap = need;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; CUDA_OK(cudaMalloc(&p, need)); cap = need; return; }
+    cap = want;
 }
 
 }  // namespace
@@ -1326,6 +1331,14 @@ void ensure(uint8_t*& p, size_t& cap, size_t need, cudaStream_t st) {
 extern "C" {
 
 uint32_t ifb200_abi_version(void) { return (IFB200_ABI_VERSION_MAJOR << 16) | IFB200_ABI_VERSION_MINOR; }
+
+int ifb200_set_dropin_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return IFB200_ERR_CUDA; }
+    if (device < 0 || device >= n) return IFB200_ERR_INVALID_ARGUMENT;
+    g_dropin_device.store(device);
+    return IFB200_OK;
+}
 
 const char* ifb200_status_name(int s) {
     switch (s) {
@@ -1578,10 +1591,11 @@ bool is_pageable(const void* p) {
 }
 void ensure_pinned(uint8_t*& p, size_t& cap, size_t need) {
     if (cap >= need) return;
+    const size_t want = grown(cap, need);
     if (p) CUDA_OK(cudaFreeHost(p));
     p = nullptr; cap = 0;
-    CUDA_OK(cudaMallocHost(&p, need));
-    cap = need;
+    if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; CUDA_OK(cudaMallocHost(&p, need)); cap = need; return; }
+    cap = want;
 }
 // the result parked in the slot's pinned buffer (if any) goes to the caller's canvas; the slot's stream must have been synchronised
 void flush_result(HostCtx& c, HostSlot& sl) {

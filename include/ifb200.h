@@ -80,6 +80,9 @@ typedef struct ifb200_resample_desc {
 
 /* ---- library / device ---------------------------------------------------------------------- */
 uint32_t    ifb200_abi_version(void);                      /* (major << 16) | minor */
+/* Device of the host-buffer (drop-in) calls made by threads that have not made one yet (each calling thread keeps its own context on
+ * the device that was selected when it made its first call).  Default: the IFB200_DEVICE environment variable, else device 0. */
+int         ifb200_set_dropin_device(int device);
 const char* ifb200_status_name(int status);
 int         ifb200_device_count(void);                     /* 0 when no CUDA device / driver is usable */
 
